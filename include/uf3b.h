@@ -1,0 +1,157 @@
+/*
+ * uf3b.h — C ABI of the B200-native UF3 hot path (libuf3b.so, sm_100a).
+ *
+ * The reference (uf3/uf3, pure Python) has no FFI for this path: its boundary is the
+ * Python object API.  This header is the boundary a binding would
+ * target instead; each entry point names the reference code it replaces.  The Python
+ * host layer in uf3_b200/ (process.BasisFeaturizer, calculator.UFCalculator) calls
+ * exactly these functions through ctypes — see INTEGRATION.md for the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative uf3b_status otherwise; the
+ *     message for the calling thread's last failure is uf3b_last_error()
+ *   - handles are opaque; one handle per (process, device); not thread-safe
+ *   - the caller owns every buffer passed in; array arguments may be HOST or DEVICE
+ *     pointers (detected with cudaPointerGetAttributes) — device pointers avoid the
+ *     host round trip in frame loops
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls with
+ *     host output buffers synchronise that stream before returning
+ *   - all floating point is IEEE float64; indices are int32 on device, int64 on export
+ *   - "supercell index" = image_rank * n_atoms + atom, image_rank in the order of the
+ *     image table handed to uf3b_neighbors_build (reference: data/geometry.py:141-149)
+ */
+#ifndef UF3B_H
+#define UF3B_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UF3B_ABI_VERSION 1
+
+typedef enum {
+    UF3B_OK = 0,
+    UF3B_ERR_INVALID = -1,      /* bad argument / inconsistent descriptor          */
+    UF3B_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError)  */
+    UF3B_ERR_ELEMENT = -3,      /* atomic number not in the basis' element list    */
+    UF3B_ERR_CAPACITY = -4,     /* index range exceeded (int32 offsets)            */
+    UF3B_ERR_STATE = -5         /* call order violated (e.g. coefficients not set) */
+} uf3b_status;
+
+typedef struct uf3b_basis uf3b_basis;     /* device-resident basis tables            */
+typedef struct uf3b_nlist uf3b_nlist;     /* one configuration: binned ghosts + CSR  */
+typedef struct uf3b_gram uf3b_gram;       /* normal-equation accumulator             */
+
+/*
+ * Flattened BSplineBasis (reference: representation/bspline.py:20-720, the host-side
+ * descriptor that stays the user-facing API).  Interactions are indexed the way
+ * ChemicalSystem orders them (data/composition.py:113-132): elements by ascending Z;
+ * pair (a<=b) -> a*ne - a*(a-1)/2 + (b-a); trio (c; a<=b) -> c*n_pairs + pair(a,b).
+ * Feature columns follow bspline.py:525-575: [one per element][pairs][trios], WITHOUT
+ * the leading "y" column.
+ */
+typedef struct {
+    int32_t n_elements;
+    const int32_t *atomic_numbers;   /* [n_elements], ascending                                 */
+    int32_t n_feats;                 /* total feature columns                                   */
+    int32_t leading_trim_2b, trailing_trim_2b;   /* bspline.py:66-67, applied per basis index  */
+    int32_t leading_trim_3b, trailing_trim_3b;
+    /* pairs */
+    const int32_t *pair_n_knots;     /* [n_pairs]                                               */
+    const double *pair_knots;        /* concatenated knot sequences                             */
+    const double *pair_r_min;        /* [n_pairs] r_min_map; bound used is max(r_min, 0)        */
+    const double *pair_r_max;        /* [n_pairs] r_max_map                                     */
+    const int32_t *pair_col;         /* [n_pairs] first feature column                          */
+    /* trios (n_trios = 0 for a 2-body basis, else n_elements * n_pairs) */
+    int32_t n_trios;
+    const int32_t *trio_n_knots;     /* [n_trios*3] l, m, n legs                                */
+    const double *trio_knots;        /* concatenated, trio-major then leg                       */
+    const int32_t *trio_col;         /* [n_trios] first feature column                          */
+    const int32_t *trio_n_cols;      /* [n_trios] compressed column count                       */
+    /* compression (bspline.py:664-719 as a map): for every bin of the full L*M*N grid,  */
+    /* trio-major and C-ordered: compressed column (or -1) and folding weight.             */
+    const int32_t *bin_col;
+    const double *bin_weight;
+    const int32_t *trio_symmetry;    /* [n_trios] 1, 2 or 3 (bspline.py:723-763)                */
+} uf3b_basis_desc;
+
+const char *uf3b_last_error(void);
+int uf3b_abi_version(void);
+
+/* Device used by subsequent create calls (default: current device). */
+int uf3b_set_device(int device);
+
+/* -- basis ------------------------------------------------------------------------ */
+/* replaces: BSplineBasis.update_basis_functions / generate_basis_functions
+ * (bspline.py:322-369, :791-807): builds per-interval cubic pieces of every basis
+ * function and uploads all tables. */
+int uf3b_basis_create(const uf3b_basis_desc *desc, uf3b_basis **out);
+/* replaces: calculator.coefficients_by_interaction / construct_pair_potentials /
+ * construct_trio_potentials (forcefield/calculator.py:490-573).  `coefficients` is the
+ * flat model vector of length n_feats (host pointer). */
+int uf3b_basis_set_coefficients(uf3b_basis *basis, const double *coefficients, int32_t n);
+void uf3b_basis_destroy(uf3b_basis *basis);
+
+/* -- neighbour lists -------------------------------------------------------------- */
+/* replaces: geometry.get_supercell + distances.get_distance_matrix + the boolean masks
+ * (data/geometry.py:14-51; representation/distances.py:19-75,146-169;
+ * representation/angles.py:289-346).
+ *   positions      [n_atoms*3]  row-major x,y,z
+ *   atomic_numbers [n_atoms]
+ *   image_offsets  [n_images*3] cartesian offset of every periodic image, image 0 = 0
+ *   image_abc      [n_images*3] integer image coordinates (to pair image g with -g)
+ * Builds, for every real atom, (a) the pair list  max(r_min,0) < d < r_max  per
+ * interaction and (b) the 3-body list  r3_min < d <= r3_max, both sorted by supercell
+ * index.  If *inout is non-NULL its buffers are reused. */
+int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *positions,
+                         const int32_t *atomic_numbers, int32_t n_images,
+                         const double *image_offsets, const int32_t *image_abc,
+                         uf3b_nlist **inout, void *stream);
+/* Number of entries in list `which` (2 or 3). */
+int uf3b_neighbors_count(const uf3b_nlist *nl, int which, int64_t *n_entries);
+/* Parity hook: CSR offsets [n_atoms+1] and supercell indices [n_entries] (host). */
+int uf3b_neighbors_export(const uf3b_nlist *nl, int which, int64_t *offsets,
+                          int64_t *supercell_index);
+void uf3b_nlist_destroy(uf3b_nlist *nl);
+
+/* -- fit path --------------------------------------------------------------------- */
+/* replaces: BasisFeaturizer.featurize_energy_2B/3B, featurize_force_2B/3B and the row
+ * assembly of evaluate_configuration (representation/process.py:293-506).
+ *   x_energy [n_feats] or NULL           (columns incl. the element counts)
+ *   x_forces [3*n_atoms rows] or NULL    row c*n_atoms + a, `ld` doubles apart
+ *                                        (ld >= n_feats; ld = n_feats+1 leaves room
+ *                                        for a y column when the pointer is offset) */
+int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy,
+                   double *x_forces, int64_t ld, void *stream);
+
+/* -- inference path --------------------------------------------------------------- */
+/* replaces: UFCalculator._get_potential_energy / _get_forces
+ * (forcefield/calculator.py:156-343).  energy: 1 double or NULL; forces [n_atoms*3] or
+ * NULL; virial [9] or NULL (sum over pairs/triplets of r (x) f, for analytic stress). */
+int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, double *energy,
+                       double *forces, double *virial, void *stream);
+
+/* -- normal equations (regression/least_squares.py:733-771) ------------------------ */
+/* G += X^T X, b += X^T y over `rows` rows of X (row stride ld, n_cols columns, device
+ * or host).  Two accumulators are kept, selected by is_force. */
+int uf3b_gram_create(int32_t n_cols, uf3b_gram **out);
+int uf3b_gram_accumulate(uf3b_gram *gram, const double *x, const double *y, int64_t rows,
+                         int64_t ld, int is_force, void *stream);
+int uf3b_gram_export(const uf3b_gram *gram, int is_force, double *gram_out, double *ord_out);
+void uf3b_gram_destroy(uf3b_gram *gram);
+
+/* -- instrumentation ---------------------------------------------------------------- */
+/* Kernels launched by this library in this process since load (for bench.py). */
+int64_t uf3b_launch_count(void);
+/* Device time (ms) of the most recent uf3b_featurize / uf3b_energy_forces main kernel,
+ * measured with CUDA events on the call's stream; enable with uf3b_set_timing(1). */
+int uf3b_set_timing(int enabled);
+double uf3b_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UF3B_H */
