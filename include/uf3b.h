@@ -143,6 +143,14 @@ int uf3b_gram_accumulate(uf3b_gram *gram, const double *x, const double *y, int6
 int uf3b_gram_export(const uf3b_gram *gram, int is_force, double *gram_out, double *ord_out);
 void uf3b_gram_destroy(uf3b_gram *gram);
 
+/* -- host-side probe ----------------------------------------------------------------- */
+/* Runs the table builder of uf3b_basis_create on one knot vector and evaluates the four
+ * non-zero cubic basis functions and their first derivatives at r ON THE HOST (no GPU
+ * needed): the same polynomial pieces and the same evaluation routine the kernels use.
+ * Returns the first basis index (searchsorted(knots, r, 'left') - 4, bspline.py:966),
+ * or -1 when r is outside (knots[3], knots[n-4]].  Used by the CPU test-suite. */
+int uf3b_host_eval_basis(const double *knots, int32_t n_knots, double r, double *v, double *dv);
+
 /* -- instrumentation ---------------------------------------------------------------- */
 /* Kernels launched by this library in this process since load (for bench.py). */
 int64_t uf3b_launch_count(void);

@@ -1,0 +1,170 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against
+ (a) golden vectors produced by the unmodified reference (tests/golden/, oracle/make_golden.py)
+ (b) the CPU oracle (oracle/uf3_oracle.c) on seeded synthetic frames the reference cannot hold.
+
+Bars: neighbour indices bit-exact; features np.allclose(rtol=1e-5, atol=1e-8) as the
+reference's own tests use AND max error <= 1e-6 relative to the largest entry
+(BASELINE.json north_star); energies / forces within 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle import uf3_oracle as orc
+from uf3_b200 import geometry
+from uf3_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+
+
+def _engine_for(case):
+    basis = case.basis()
+    eng = Engine(basis)
+    images = geometry.image_table(case.cell, case.pbc, basis.r_cut)
+    eng.build_neighbors(case.positions, case.numbers, images=images)
+    return basis, eng, images
+
+
+@pytest.mark.parametrize("name", gu.case_names("featurize"))
+def test_neighbor_lists_bit_exact(name):
+    case = gu.Case(name)
+    if "nl2_i" not in case:
+        pytest.skip("fixture holds no neighbour lists")
+    basis, eng, _ = _engine_for(case)
+    n = len(case.numbers)
+    want_off, want_j = gu.csr_from_pairs(case["nl2_i"], case["nl2_j"], n)
+    off, idx = eng.neighbor_list(2)
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(idx, want_j)
+    if basis.degree > 2:
+        want_off, want_j = gu.csr_from_pairs(case["nl3_i"], case["nl3_j"], n)
+        off, idx = eng.neighbor_list(3)
+        assert np.array_equal(off, want_off)
+        assert np.array_equal(idx, want_j)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", gu.case_names("featurize"))
+def test_feature_rows_match_reference(name):
+    case = gu.Case(name)
+    basis, eng, _ = _engine_for(case)
+    want_forces = "x_forces" in case
+    xe, xf = eng.featurize(energy=True, forces=want_forces)
+    assert np.allclose(xe, case["x_energy"], rtol=1e-5, atol=1e-8)
+    assert gu.rel_err(xe, case["x_energy"]) <= REL
+    if want_forces:
+        assert xf.shape == case["x_forces"].shape
+        assert np.allclose(xf, case["x_forces"], rtol=1e-5, atol=1e-8)
+        assert gu.rel_err(xf, case["x_forces"]) <= REL
+    # energy-only and force-only calls give the same rows
+    xe2, _ = eng.featurize(energy=True, forces=False)
+    assert np.array_equal(xe, xe2)
+    if want_forces:
+        _, xf2 = eng.featurize(energy=False, forces=True)
+        assert np.array_equal(xf, xf2)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", gu.case_names("calculator"))
+def test_energy_forces_match_reference(name):
+    case = gu.Case(name)
+    basis, eng, _ = _engine_for(case)
+    eng.set_coefficients(case["coefficients"])
+    e, f = eng.energy_forces()
+    want_e, want_f = float(case["energy"]), case["forces"]
+    assert abs(e - want_e) <= REL * max(abs(want_e), 1e-12)
+    assert gu.rel_err(f, want_f) <= REL
+    e_only, _ = eng.energy_forces(energy=True, forces=False)
+    assert e_only == e
+    eng.close()
+
+
+def test_reference_known_answers():
+    """tests/test_calculator.py:40-50, :109-114 of the reference (values as printed there)."""
+    case = gu.Case("calc_w_dimer_free")
+    _, eng, _ = _engine_for(case)
+    eng.set_coefficients(case["coefficients"])
+    e, f = eng.energy_forces()
+    assert np.isclose(e, -1.21578, atol=1e-5)
+    assert np.allclose(np.abs(f), 3.96244881, atol=1e-6)
+    eng.close()
+    case = gu.Case("calc_nexe_dimer")
+    _, eng, _ = _engine_for(case)
+    eng.set_coefficients(case["coefficients"])
+    e, f = eng.energy_forces()
+    assert np.isclose(e, 0.3464031387757268, rtol=1e-10)
+    assert np.allclose(f[:, 0], [-0.28138023, 0.28138023], atol=1e-7)
+    eng.close()
+
+
+# ----------------------------------------------------------------- vs the CPU oracle
+def _bcc_w(reps, a=3.165, sigma=0.05, seed=0):
+    rng = np.random.default_rng(seed)
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0.5]])
+    cells = np.array([[i, j, k] for i in range(reps[0]) for j in range(reps[1])
+                      for k in range(reps[2])])
+    pos = (cells[:, None, :] + base[None, :, :]).reshape(-1, 3) * a
+    pos = pos + rng.normal(0, sigma, pos.shape)
+    return pos, np.full(len(pos), 74), np.diag(np.array(reps) * a), np.array([True] * 3)
+
+
+@pytest.mark.parametrize("fixture, reps", [("syn_w54_demo", (6, 7, 8)),
+                                           ("syn_w54_manuscript", (5, 5, 6))])
+def test_feature_rows_match_oracle_mid_size(fixture, reps):
+    """Sizes the reference cannot hold (dense M x M matrices); oracle = restated C path."""
+    basis = gu.Case(fixture).basis()
+    pos, numbers, cell, pbc = _bcc_w(reps, seed=21)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    packed = orc.PackedBasis(basis)
+    want_e, want_f = orc.featurize(packed, pos, numbers, images[1])
+    eng = Engine(basis)
+    eng.build_neighbors(pos, numbers, images=images)
+    for which in (2, 3):
+        off, idx = eng.neighbor_list(which)
+        want_off, want_idx = orc.neighbor_lists(packed, pos, numbers, images[1], which)
+        assert np.array_equal(off, want_off) and np.array_equal(idx, want_idx)
+    xe, xf = eng.featurize()
+    assert gu.rel_err(xe, want_e) <= REL and gu.rel_err(xf, want_f) <= REL
+    assert np.allclose(xf, want_f, rtol=1e-5, atol=1e-8)
+    eng.close()
+
+
+def test_energy_forces_match_oracle_mid_size():
+    case = gu.Case("calc_syn_w54_model23")
+    basis = case.basis()
+    pos, numbers, cell, pbc = _bcc_w((7, 7, 7), sigma=0.12, seed=33)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    packed = orc.PackedBasis(basis)
+    want_e, want_f = orc.energy_forces(basis, packed, case["coefficients"], pos, numbers, images[1])
+    eng = Engine(basis)
+    eng.set_coefficients(case["coefficients"])
+    eng.build_neighbors(pos, numbers, images=images)
+    e, f = eng.energy_forces()
+    assert abs(e - want_e) <= REL * abs(want_e)
+    assert gu.rel_err(f, want_f) <= REL
+    eng.close()
+
+
+def test_empty_and_single_atom():
+    basis = gu.Case("syn_w16_demo").basis()
+    eng = Engine(basis)
+    eng.build_neighbors(np.zeros((0, 3)), np.zeros(0, dtype=np.int32))
+    xe, xf = eng.featurize()
+    assert np.all(xe == 0) and xf.shape == (0, basis.n_feats)
+    eng.build_neighbors(np.zeros((1, 3)), np.array([74]))
+    xe, xf = eng.featurize()
+    assert xe[0] == 1 and np.all(xe[1:] == 0) and np.all(xf == 0)
+    off, idx = eng.neighbor_list(2)
+    assert off.tolist() == [0, 0] and len(idx) == 0
+    eng.close()
+
+
+def test_unknown_element_is_an_error():
+    from uf3_b200 import _native
+    basis = gu.Case("syn_w16_demo").basis()
+    eng = Engine(basis)
+    with pytest.raises(_native.ElementError):
+        eng.build_neighbors(np.zeros((2, 3)), np.array([74, 26]))
+    eng.close()

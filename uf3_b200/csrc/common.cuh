@@ -1,0 +1,151 @@
+// common.cuh — shared declarations of libuf3b (sm_100a): error handling, device buffers,
+// the device-side basis table and the per-configuration frame / neighbour-list views.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/uf3b.h"
+
+namespace uf3b {
+
+// ------------------------------------------------------------------ host utilities
+int fail(int code, const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+extern bool g_timing;
+extern double g_last_kernel_ms;
+
+#define UF3B_CUDA(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return uf3b::fail(UF3B_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));    \
+    } while (0)
+
+// kernel<<<grid, block, smem, stream>>>(args...) with launch accounting and error check.
+#define UF3B_LAUNCH(kernel, grid, block, smem, stream, ...)                               \
+    do {                                                                                  \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                       \
+        uf3b::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+        cudaError_t e_ = cudaGetLastError();                                              \
+        if (e_ != cudaSuccess)                                                            \
+            return uf3b::fail(UF3B_ERR_CUDA, "launch %s: %s", #kernel,                    \
+                              cudaGetErrorString(e_));                                    \
+    } while (0)
+
+// Grow-only device buffer owned by a handle.
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = n + n / 4 + 16;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+};
+
+inline bool is_device_pointer(const void *ptr) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int sm_count();
+
+// ------------------------------------------------------------------ device tables
+// Flattened BSplineBasis on the device.  Pair p = (a<=b) -> a*ne - a*(a-1)/2 + (b-a);
+// trio t = centre*n_pairs + pair(j,k).  Every knot vector owns (n_knots - 7) cubic
+// pieces of 16 doubles: piece i-3 holds, for the four basis functions that are
+// non-zero on (t[i], t[i+1]], the coefficients of u^0..u^3 with u = r - t[i].
+struct BasisTab {
+    int ne, n_pairs, n_trios, n_feats;
+    int lead2, trail2, lead3, trail3;
+    double r3min, r3max;      // angles.py:312-325
+    double r_search;          // max over pair r_max and r3max (cell edge)
+    const int *pair_nk, *pair_koff, *pair_poff, *pair_col;
+    const double *pair_lo, *pair_hi;   // strict bounds max(r_min,0) < d < r_max
+    const double *knots2, *poly2;
+    const int *trio_nk, *trio_koff, *trio_poff;   // [3*t + leg]
+    const int *trio_col, *trio_goff, *trio_sym;   // [t]
+    const double *knots3, *poly3;
+    const int *bin_col;       // full grid bin -> compressed column (or -1), trio-major
+    const double *bin_w;      // folding weight of the bin
+    const double *coeff;      // flat model coefficients [n_feats]   (inference only)
+    const double *c_grid;     // decompressed 3-body coefficient grids, bin layout
+    const int *z_to_spec;     // [128] atomic number -> element index or -1
+};
+
+// One binned supercell atom (32 B so that a run of cells is one aligned bulk copy).
+struct __align__(32) Slot {
+    double x, y, z;
+    int m;        // supercell index  image_rank * n_atoms + atom
+    int spec;     // element index
+};
+
+// Read-only view of one configuration and its neighbour lists.
+struct FrameView {
+    int n;                    // real atoms
+    int n_img;
+    const double *pos;        // [n*3]
+    const int *spec;          // [n]
+    const double *img_off;    // [n_img*3]
+    const int *img_inv;       // [n_img] rank of the image with negated coordinates
+    const int *off2, *idx2;   // pair list CSR   (max(r_min,0) < d < r_max per pair)
+    const int *off3, *idx3;   // 3-body list CSR (r3min < d <= r3max)
+};
+
+}  // namespace uf3b
+
+// ------------------------------------------------------------------ opaque handles
+struct uf3b_basis {
+    uf3b::BasisTab tab;            // device pointers into `blob`
+    void *blob = nullptr;          // one allocation holding every table
+    double *coeff = nullptr;       // [n_feats]
+    double *c_grid = nullptr;      // [n_bins]
+    int n_bins = 0;
+    int n_feats = 0;
+    bool has_coeff = false;
+    int device = 0;
+    std::vector<int> h_trio_goff, h_bin_col, h_trio_col;
+    std::vector<double> h_bin_w;
+    std::vector<int> h_numbers;
+    // scratch for energy partial sums and force-row staging (grow-only)
+    uf3b::DevBuf<double> partials;
+    uf3b::DevBuf<double> stage;
+    uf3b::DevBuf<double> stage_e;
+};
+
+struct uf3b_nlist {
+    int64_t n = 0;
+    int n_img = 0;
+    int64_t total2 = 0, total3 = 0;
+    uf3b::DevBuf<double> pos, img_off;
+    uf3b::DevBuf<int> z, spec, img_inv;
+    uf3b::DevBuf<int> off2, off3, idx2, idx3, scratch, cnt;
+    uf3b::DevBuf<int> cell_of, cell_start, cell_cursor;
+    uf3b::DevBuf<uf3b::Slot> slots;
+    uf3b::DevBuf<double> misc;     // bbox (6) on device
+    uf3b::DevBuf<long long> totals;
+    uf3b::FrameView view() const;
+};

@@ -1,0 +1,233 @@
+// evaluate.cu — Kernel B (inference path): energy and forces from fitted coefficients.
+//
+// Replaces UFCalculator._energy_1b/_energy_2b/_energy_3b and _forces_2b/_forces_3b
+// (forcefield/calculator.py:183-343), which call ndsplines.NDSpline on dense distance
+// and direction-cosine arrays.  One warp owns one real atom; lanes walk its pairs and
+// the triangles it takes part in (triangle.cuh), contract the 4 (pair) or 4x4x4
+// (triplet) non-zero basis products against the coefficient vector / decompressed
+// coefficient grid, and the atom's force is reduced across the warp with shuffles.
+// As in the reference, no trimming is applied at evaluation time: trimmed basis
+// functions carry zero coefficients (calculator.py:207,286,565-571).
+#include "common.cuh"
+#include "geom.cuh"
+#include "spline.cuh"
+#include "triangle.cuh"
+
+namespace uf3b {
+
+// value and the three leg-partials of  sum_pqr C[il+p, im+q, in+r] Bl_p Bm_q Bn_r
+__device__ __forceinline__ void contract(const double *__restrict__ grid, const Triangle &T,
+                                         double &val, double &gl, double &gm, double &gn) {
+    val = gl = gm = gn = 0.0;
+    const int mn = T.dim_m * T.dim_n;
+    const double *base = grid + (T.il * T.dim_m + T.im) * T.dim_n + T.in;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double *row = base + p * mn + q * T.dim_n;
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double c = __ldg(row + r);
+                t0 += c * T.v[2][r];
+                t1 += c * T.dv[2][r];
+            }
+            u0 += t0 * T.v[1][q];
+            u1 += t0 * T.dv[1][q];
+            u2 += t1 * T.v[1][q];
+        }
+        val += u0 * T.v[0][p];
+        gl += u0 * T.dv[0][p];
+        gm += u1 * T.v[0][p];
+        gn += u2 * T.v[0][p];
+    }
+}
+
+constexpr int EV_WARPS = 4;
+
+__global__ void __launch_bounds__(EV_WARPS * 32)
+k_energy_forces(const BasisTab B, const FrameView f, double *__restrict__ forces,
+                double *__restrict__ e_partials, int want_e_, int want_f_) {
+    __shared__ RoleViews s_views[EV_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * EV_WARPS + warp, n_gw = gridDim.x * EV_WARPS;
+    const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
+    RoleViews *views = s_views + warp;
+    double e_acc = 0.0;
+
+    for (int a = gw; a < f.n; a += n_gw) {
+        const int sa = __ldg(f.spec + a);
+        const Vec3 pa = real_position(f, a);
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        if (lane == 0) e_acc += __ldg(B.coeff + sa);                    // calculator.py:183-189
+
+        // ---- 2-body: E += S(r) per ordered pair; F_a = 2 sum_j S'(r_aj) (x_j - x_a)/r_aj
+        const int r0 = __ldg(f.off2 + a), r1 = __ldg(f.off2 + a + 1);
+        for (int e = r0 + lane; e < r1; e += 32) {
+            int aj;
+            const Vec3 pj = super_position(f, __ldg(f.idx2 + e), aj);
+            const double d = dist_rn(pa, pj);
+            const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
+            double v[4], dv[4];
+            const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr),
+                                     B.poly2 + __ldg(B.pair_poff + pr), d, 0, 0, v, dv);
+            if (idx < 0) continue;
+            const double *c = B.coeff + __ldg(B.pair_col + pr) + idx;
+            double s = 0.0, ds = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double cr = __ldg(c + r);
+                s += cr * v[r];
+                ds += cr * dv[r];
+            }
+            e_acc += s;
+            const double k = 2.0 * ds / d;
+            fx += k * (pj.x - pa.x);
+            fy += k * (pj.y - pa.y);
+            fz += k * (pj.z - pa.z);
+        }
+
+        // ---- 3-body
+        if (B.n_trios > 0) {
+            const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.off3 + a + 1) - row0;
+            const int n_tri = n3a * (n3a - 1) / 2;
+            for (int t = lane; t < n_tri; t += 32) {
+                int qj, qk;
+                unrank_pair(t, qj, qk);
+                Triangle T;
+                if (!eval_triangle(B, f, pa, sa, __ldg(f.idx3 + row0 + qj), __ldg(f.idx3 + row0 + qk), 0,
+                                   0, 0, T))
+                    continue;
+                double val, gl, gm, gn;
+                contract(B.c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
+                e_acc += val;
+                fx += gl * T.A[0] + gm * T.B[0];
+                fy += gl * T.A[1] + gm * T.B[1];
+                fz += gl * T.A[2] + gm * T.B[2];
+            }
+            if (want_f) {
+                for (int vbase = 0; vbase < n3a; vbase += 32) {
+                    const int total = publish_views(B, f, a, vbase, n3a, lane, views);
+                    for (int it = lane; it < total; it += 32) {
+                        const int v = find_view(views, it);
+                        const int ci = views->centre[v], apr = views->a_prime[v];
+                        const int mk = __ldg(f.idx3 + __ldg(f.off3 + ci) + (it - views->prefix[v]));
+                        if (mk == apr) continue;
+                        const bool first = apr < mk;
+                        Triangle T;
+                        if (!eval_triangle(B, f, real_position(f, ci), __ldg(f.spec + ci), first ? apr : mk,
+                                           first ? mk : apr, first ? 1 : 2, 0, 0, T))
+                            continue;
+                        double val, gl, gm, gn;
+                        contract(B.c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
+                        fx += gl * T.A[0] + gm * T.B[0] + gn * T.C[0];
+                        fy += gl * T.A[1] + gm * T.B[1] + gn * T.C[1];
+                        fz += gl * T.A[2] + gm * T.B[2] + gn * T.C[2];
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (want_f) {
+            fx = warp_sum(fx);
+            fy = warp_sum(fy);
+            fz = warp_sum(fz);
+            if (lane == 0) {
+                forces[3 * (size_t)a + 0] = fx;
+                forces[3 * (size_t)a + 1] = fy;
+                forces[3 * (size_t)a + 2] = fz;
+            }
+        }
+    }
+    if (want_e) {
+        e_acc = warp_sum(e_acc);
+        if (lane == 0) e_partials[gw] = e_acc;
+    }
+}
+
+// Fixed-order sum of the per-warp energies.
+__global__ void __launch_bounds__(256) k_energy_sum(const double *__restrict__ partials, int n,
+                                                    double *__restrict__ energy) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) s += partials[r];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+        if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *energy = red[0];
+}
+
+}  // namespace uf3b
+
+using namespace uf3b;
+
+extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, double *energy,
+                                  double *forces, double *virial, void *stream_) {
+    if (!basis || !nl) return fail(UF3B_ERR_INVALID, "null handle");
+    if (!basis->has_coeff) return fail(UF3B_ERR_STATE, "coefficients not set");
+    if (virial) return fail(UF3B_ERR_INVALID, "analytic virial is not implemented yet; pass NULL");
+    if (!energy && !forces) return UF3B_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n = (int)nl->n;
+    const bool e_dev = energy && is_device_pointer(energy);
+    const bool f_dev = forces && is_device_pointer(forces);
+    if (n == 0) {
+        if (energy) {
+            if (e_dev) UF3B_CUDA(cudaMemsetAsync(energy, 0, sizeof(double), stream));
+            else *energy = 0.0;
+        }
+        return UF3B_OK;
+    }
+    int per_sm = 1;
+    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_energy_forces, EV_WARPS * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count() * per_sm;
+    const int need = (n + EV_WARPS - 1) / EV_WARPS;
+    if (grid > need) grid = need;
+    const int n_gw = grid * EV_WARPS;
+    UF3B_CUDA(basis->partials.reserve((size_t)n_gw + 1));
+    double *d_f = forces;
+    if (forces && !f_dev) {
+        UF3B_CUDA(basis->stage.reserve((size_t)3 * n));
+        d_f = basis->stage.p;
+    }
+    double *d_e = energy;
+    if (energy && !e_dev) {
+        UF3B_CUDA(basis->stage_e.reserve(1));
+        d_e = basis->stage_e.p;
+    }
+    const FrameView view = nl->view();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_timing) {
+        UF3B_CUDA(cudaEventCreate(&ev0));
+        UF3B_CUDA(cudaEventCreate(&ev1));
+        UF3B_CUDA(cudaEventRecord(ev0, stream));
+    }
+    UF3B_LAUNCH(k_energy_forces, grid, EV_WARPS * 32, 0, stream, basis->tab, view, d_f,
+                basis->partials.p, energy ? 1 : 0, forces ? 1 : 0);
+    if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
+    if (energy) UF3B_LAUNCH(k_energy_sum, 1, 256, 0, stream, basis->partials.p, n_gw, d_e);
+    bool need_sync = g_timing;
+    if (forces && !f_dev) {
+        UF3B_CUDA(cudaMemcpyAsync(forces, d_f, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, stream));
+        need_sync = true;
+    }
+    if (energy && !e_dev) {
+        UF3B_CUDA(cudaMemcpyAsync(energy, d_e, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        need_sync = true;
+    }
+    if (need_sync) UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (g_timing) {
+        float ms = 0.f;
+        UF3B_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        g_last_kernel_ms = ms;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return UF3B_OK;
+}

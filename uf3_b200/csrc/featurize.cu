@@ -1,0 +1,383 @@
+// featurize.cu — Kernel B (fit path): fused pair + triplet B-spline feature rows.
+//
+// Replaces BasisFeaturizer.featurize_energy_2B/3B, featurize_force_2B/3B and the row
+// assembly of evaluate_configuration (representation/process.py:293-506), i.e.
+// bspline.evaluate_basis_functions / featurize_force_2B (bspline.py:810-895) and
+// angles.featurize_energy_3b / featurize_force_3b with their numba scatters
+// (angles.py:17-286) followed by compress_3B (bspline.py:664-690).
+//
+// One warp owns one real atom and produces that atom's three force rows (fx, fy, fz)
+// plus its share of the energy row.  Accumulators live in shared memory
+// ([column][e, fx, fy, fz]); nothing is scattered to other atoms' rows, so there are no
+// atomics and the result is bit-reproducible run to run.
+//   2-body: lanes evaluate 32 pairs at a time into shared records, then every lane
+//           gathers the records that touch ITS feature column.
+//   3-body: lanes evaluate 32 triangles at a time (three legs each) into shared records;
+//           then the warp walks the records with lane = (p, q, r-pair) of the 4x4x4
+//           block of non-zero basis products and adds them into the compressed column
+//           of each bin.  Bins that fold onto the same column under the trio's
+//           permutation symmetry are applied in separate phases.
+#include "common.cuh"
+#include "geom.cuh"
+#include "spline.cuh"
+#include "triangle.cuh"
+
+namespace uf3b {
+
+struct __align__(16) TriRec {
+    double v[3][4], dv[3][4];
+    double A[3], B[3], C[3];
+    int base;              // bin index of (il, im, in), trio offset included
+    int mn, nn;            // bin strides of l and m
+    int dlm, dmn, dln;     // il-im, im-in, il-in (mirror classes of symmetric trios)
+    int col0;              // first feature column of the trio
+    int flags;             // bit0 valid, bit1 centre role, bits 8+: symmetry order
+};
+
+struct __align__(16) PairRec {
+    double v[4], dv[4];
+    double u[3];
+    int col0;              // first feature column hit, or a value no column can match
+    int pad;
+};
+
+constexpr int CHUNK = 32;
+constexpr size_t WARP_SCRATCH = CHUNK * sizeof(TriRec) + sizeof(RoleViews);
+
+__host__ __device__ inline size_t featurize_warp_bytes(int n_feats) {
+    return (((size_t)4 * n_feats * sizeof(double) + 15) & ~size_t(15)) + ((WARP_SCRATCH + 15) & ~size_t(15));
+}
+
+__device__ __forceinline__ void store_record(TriRec *rec, const Triangle &T, const BasisTab &B, int role) {
+#pragma unroll
+    for (int leg = 0; leg < 3; ++leg)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { rec->v[leg][q] = T.v[leg][q]; rec->dv[leg][q] = T.dv[leg][q]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { rec->A[c] = T.A[c]; rec->B[c] = T.B[c]; rec->C[c] = T.C[c]; }
+    rec->mn = T.dim_m * T.dim_n;
+    rec->nn = T.dim_n;
+    rec->base = __ldg(B.trio_goff + T.trio) + (T.il * T.dim_m + T.im) * T.dim_n + T.in;
+    rec->dlm = T.il - T.im;
+    rec->dmn = T.im - T.in;
+    rec->dln = T.il - T.in;
+    rec->col0 = __ldg(B.trio_col + T.trio);
+    rec->flags = 1 | (role == 0 ? 2 : 0) | (__ldg(B.trio_sym + T.trio) << 8);
+}
+
+// Phase B: scatter `count` records into the warp's accumulators.
+__device__ __forceinline__ void scatter_records(const BasisTab &B, const TriRec *recs, int count,
+                                                double *acc, int lane, bool want_e, bool want_f) {
+    const int p = lane >> 3, q = (lane >> 1) & 3, rh = lane & 1;
+    for (int t = 0; t < count; ++t) {
+        const TriRec *rec = recs + t;
+        const int flags = rec->flags;
+        if (!(flags & 1)) continue;
+        const bool centre = (flags & 2) != 0;
+        const int sym = flags >> 8;
+        const double vl = rec->v[0][p], dvl = rec->dv[0][p];
+        const double vm = rec->v[1][q], dvm = rec->dv[1][q];
+        const double c_ = vl * vm;
+        double q1[3], q2[3];
+        if (want_f) {
+            const double a_ = dvl * vm, b_ = vl * dvm;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                q1[c] = a_ * rec->A[c] + b_ * rec->B[c];
+                q2[c] = c_ * rec->C[c];
+            }
+        }
+        const int bin_pq = rec->base + p * rec->mn + q * rec->nn;
+        const int col0 = rec->col0;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * rh + rr;
+            const double vn = rec->v[2][r], dvn = rec->dv[2][r];
+            const int bin = bin_pq + r;
+            const int col = __ldg(B.bin_col + bin);
+            int cls = 0, n_cls = 1;
+            if (sym == 2) {
+                cls = (p + rec->dlm) > q;
+                n_cls = 2;
+            } else if (sym >= 3) {      // stable-sort class of (il+p, im+q, in+r)
+                cls = ((p + rec->dlm) > q) | (((q + rec->dmn) > r) << 1) | (((p + rec->dln) > r) << 2);
+                n_cls = 8;
+            }
+            double add[4] = {0.0, 0.0, 0.0, 0.0};
+            if (col >= 0) {
+                const double w = __ldg(B.bin_w + bin);
+                if (centre && want_e) add[0] = w * (c_ * vn);
+                if (want_f) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) add[1 + c] = w * (vn * q1[c] + dvn * q2[c]);
+                }
+            }
+            double *dst = acc + 4 * (size_t)(col0 + (col >= 0 ? col : 0));
+            for (int ph = 0; ph < n_cls; ++ph) {
+                if (col >= 0 && cls == ph) {
+                    if (centre && want_e) dst[0] += add[0];
+                    if (want_f) { dst[1] += add[1]; dst[2] += add[2]; dst[3] += add[3]; }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long long ld,
+            double *__restrict__ partials, int want_e_, int want_f_) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int gw = blockIdx.x * nw + warp, n_gw = gridDim.x * nw;
+    const int F = B.n_feats;
+    const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
+    unsigned char *mine = smem + (size_t)warp * featurize_warp_bytes(F);
+    double *acc = (double *)mine;
+    unsigned char *scratch = mine + (((size_t)4 * F * sizeof(double) + 15) & ~size_t(15));
+    TriRec *recs = (TriRec *)scratch;
+    PairRec *prec = (PairRec *)scratch;
+    RoleViews *views = (RoleViews *)(scratch + CHUNK * sizeof(TriRec));
+
+    for (int k = lane; k < 4 * F; k += 32) acc[k] = 0.0;
+    __syncwarp();
+
+    for (int a = gw; a < f.n; a += n_gw) {
+        const int sa = __ldg(f.spec + a);
+        const Vec3 pa = real_position(f, a);
+
+        // ------------------------------------------------ 2-body (bspline.py:810-895)
+        {
+            const int r0 = __ldg(f.off2 + a), r1 = __ldg(f.off2 + a + 1);
+            for (int base = r0; base < r1; base += CHUNK) {
+                const int e = base + lane;
+                PairRec rec;
+                rec.col0 = -(1 << 20);
+                if (e < r1) {
+                    int aj;
+                    const Vec3 pj = super_position(f, __ldg(f.idx2 + e), aj);
+                    const double d = dist_rn(pa, pj);
+                    const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
+                    const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr),
+                                             B.poly2 + __ldg(B.pair_poff + pr), d, B.lead2, B.trail2,
+                                             rec.v, rec.dv);
+                    if (idx >= 0) {
+                        rec.col0 = __ldg(B.pair_col + pr) + idx;
+                        const double inv = 1.0 / d;
+                        rec.u[0] = (pj.x - pa.x) * inv;
+                        rec.u[1] = (pj.y - pa.y) * inv;
+                        rec.u[2] = (pj.z - pa.z) * inv;
+                    }
+                }
+                prec[lane] = rec;
+                __syncwarp();
+                const int count = min(CHUNK, r1 - base);
+                for (int sj = 0; sj < B.ne; ++sj) {
+                    const int pr = pair_index(B.ne, sa, sj);
+                    const int c0 = __ldg(B.pair_col + pr), nb = __ldg(B.pair_nk + pr) - 4;
+                    for (int cb = 0; cb < nb; cb += 32) {
+                        const int col = c0 + cb + lane;
+                        double se = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+                        for (int t = 0; t < count; ++t) {
+                            const unsigned r = (unsigned)(col - prec[t].col0);
+                            if (r < 4u) {
+                                se += prec[t].v[r];
+                                const double dv = prec[t].dv[r];
+                                sx += dv * prec[t].u[0];
+                                sy += dv * prec[t].u[1];
+                                sz += dv * prec[t].u[2];
+                            }
+                        }
+                        if (cb + lane < nb) {
+                            // every bond is seen from both ends (distances.py:118-120):
+                            // x[a] = 2 * sum_j B'(r_aj) (x_j - x_a) / r_aj
+                            double *dst = acc + 4 * (size_t)col;
+                            dst[0] += se;
+                            dst[1] += 2.0 * sx;
+                            dst[2] += 2.0 * sy;
+                            dst[3] += 2.0 * sz;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ------------------------------------------------ 3-body (angles.py:17-286)
+        if (B.n_trios > 0) {
+            const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.off3 + a + 1) - row0;
+            // (i) `a` as the centre: every j<k pair of its own list
+            const int n_tri = n3a * (n3a - 1) / 2;
+            for (int t0 = 0; t0 < n_tri; t0 += CHUNK) {
+                const int t = t0 + lane;
+                recs[lane].flags = 0;
+                if (t < n_tri) {
+                    int qj, qk;
+                    unrank_pair(t, qj, qk);
+                    Triangle T;
+                    if (eval_triangle(B, f, pa, sa, __ldg(f.idx3 + row0 + qj), __ldg(f.idx3 + row0 + qk),
+                                      0, B.lead3, B.trail3, T))
+                        store_record(recs + lane, T, B, 0);
+                }
+                __syncwarp();
+                scatter_records(B, recs, min(CHUNK, n_tri - t0), acc, lane, want_e, want_f);
+                __syncwarp();
+            }
+            // (ii) `a` as a neighbour of each centre in its list (force rows only)
+            if (want_f) {
+                for (int vbase = 0; vbase < n3a; vbase += 32) {
+                    const int total = publish_views(B, f, a, vbase, n3a, lane, views);
+                    for (int it0 = 0; it0 < total; it0 += CHUNK) {
+                        const int it = it0 + lane;
+                        recs[lane].flags = 0;
+                        if (it < total) {
+                            const int v = find_view(views, it);
+                            const int ci = views->centre[v], apr = views->a_prime[v];
+                            const int mk = __ldg(f.idx3 + __ldg(f.off3 + ci) + (it - views->prefix[v]));
+                            if (mk != apr) {
+                                Triangle T;
+                                const bool first = apr < mk;
+                                if (eval_triangle(B, f, real_position(f, ci), __ldg(f.spec + ci),
+                                                  first ? apr : mk, first ? mk : apr, first ? 1 : 2,
+                                                  B.lead3, B.trail3, T))
+                                    store_record(recs + lane, T, B, first ? 1 : 2);
+                            }
+                        }
+                        __syncwarp();
+                        scatter_records(B, recs, min(CHUNK, total - it0), acc, lane, false, true);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+
+        // ------------------------------------------------ rows fx_a, fy_a, fz_a
+        __syncwarp();
+        if (want_f) {
+            for (int col = lane; col < F; col += 32) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    xf[((long long)c * f.n + a) * ld + col] = acc[4 * col + 1 + c];
+                    acc[4 * col + 1 + c] = 0.0;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (want_e)
+        for (int col = lane; col < F; col += 32) partials[(size_t)gw * F + col] = acc[4 * col];
+}
+
+// Energy row = element counts (composition.py:96-111) + fixed-order sum of the warps'
+// partial rows.  One block per feature column.
+__global__ void __launch_bounds__(256)
+k_energy_row(const double *__restrict__ partials, int n_rows, int n_feats, int ne,
+             const int *__restrict__ spec, int n, double *__restrict__ xe) {
+    __shared__ double red[256];
+    const int col = blockIdx.x;
+    double s = 0.0;
+    if (col < ne) {
+        for (int a = threadIdx.x; a < n; a += blockDim.x) s += (spec[a] == col) ? 1.0 : 0.0;
+    } else {
+        for (int r = threadIdx.x; r < n_rows; r += blockDim.x) s += partials[(size_t)r * n_feats + col];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+        if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) xe[col] = red[0];
+}
+
+}  // namespace uf3b
+
+using namespace uf3b;
+
+extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy,
+                              double *x_forces, int64_t ld, void *stream_) {
+    if (!basis || !nl) return fail(UF3B_ERR_INVALID, "null handle");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int F = basis->n_feats;
+    const int n = (int)nl->n;
+    if (x_forces && ld < F) return fail(UF3B_ERR_INVALID, "ld smaller than n_feats");
+    if (!x_energy && !x_forces) return UF3B_OK;
+    const bool e_dev = x_energy && is_device_pointer(x_energy);
+    const bool f_dev = x_forces && is_device_pointer(x_forces);
+    if (n == 0) {
+        if (x_energy) {
+            if (e_dev) UF3B_CUDA(cudaMemsetAsync(x_energy, 0, sizeof(double) * F, stream));
+            else for (int k = 0; k < F; ++k) x_energy[k] = 0.0;
+        }
+        return UF3B_OK;
+    }
+
+    // launch shape: as many warps per block as fit, grid sized to the SM count
+    const size_t per_warp = featurize_warp_bytes(F);
+    int dev = 0, smem_max = 0;
+    UF3B_CUDA(cudaGetDevice(&dev));
+    UF3B_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (per_warp > (size_t)smem_max)
+        return fail(UF3B_ERR_CAPACITY, "n_feats = %d needs %zu B of shared memory per warp (limit %d)",
+                    F, per_warp, smem_max);
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * per_warp > (size_t)smem_max / 2) warps >>= 1;
+    while ((size_t)warps * per_warp > (size_t)smem_max) warps >>= 1;
+    const size_t smem = (size_t)warps * per_warp;
+    UF3B_CUDA(cudaFuncSetAttribute(k_featurize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_featurize, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count() * per_sm;
+    const int need = (n + warps - 1) / warps;
+    if (grid > need) grid = need;
+    const int n_gw = grid * warps;
+
+    double *d_xf = x_forces;
+    long long d_ld = ld;
+    if (x_forces && !f_dev) {
+        UF3B_CUDA(basis->stage.reserve((size_t)3 * n * F));
+        d_xf = basis->stage.p;
+        d_ld = F;
+    }
+    double *d_xe = x_energy;
+    if (x_energy) {
+        UF3B_CUDA(basis->partials.reserve((size_t)n_gw * F));
+        if (!e_dev) {
+            UF3B_CUDA(basis->stage_e.reserve(F));
+            d_xe = basis->stage_e.p;
+        }
+    }
+    const FrameView view = nl->view();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_timing) {
+        UF3B_CUDA(cudaEventCreate(&ev0));
+        UF3B_CUDA(cudaEventCreate(&ev1));
+        UF3B_CUDA(cudaEventRecord(ev0, stream));
+    }
+    UF3B_LAUNCH(k_featurize, grid, warps * 32, smem, stream, basis->tab, view, d_xf, d_ld,
+                basis->partials.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
+    if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
+    if (x_energy)
+        UF3B_LAUNCH(k_energy_row, F, 256, 0, stream, basis->partials.p, n_gw, F, basis->tab.ne,
+                    view.spec, n, d_xe);
+    bool need_sync = g_timing;
+    if (x_forces && !f_dev) {
+        UF3B_CUDA(cudaMemcpy2DAsync(x_forces, sizeof(double) * ld, d_xf, sizeof(double) * F,
+                                    sizeof(double) * F, (size_t)3 * n, cudaMemcpyDeviceToHost, stream));
+        need_sync = true;
+    }
+    if (x_energy && !e_dev) {
+        UF3B_CUDA(cudaMemcpyAsync(x_energy, d_xe, sizeof(double) * F, cudaMemcpyDeviceToHost, stream));
+        need_sync = true;
+    }
+    if (need_sync) UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (g_timing) {
+        float ms = 0.f;
+        UF3B_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        g_last_kernel_ms = ms;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return UF3B_OK;
+}

@@ -1,0 +1,50 @@
+// geom.cuh — device helpers shared by the neighbour, featurize and evaluate kernels.
+#pragma once
+#include "common.cuh"
+
+namespace uf3b {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int pair_index(int ne, int a, int b) {
+    if (a > b) { int t = a; a = b; b = t; }
+    return a * ne - a * (a - 1) / 2 + (b - a);
+}
+
+struct Vec3 { double x, y, z; };
+
+// Ghost position exactly as the reference builds it (data/geometry.py:146-147):
+// positions + image offset, one rounded addition per component.
+__device__ __forceinline__ Vec3 super_position(const FrameView &f, int m, int &atom) {
+    const int g = (int)((unsigned)m / (unsigned)f.n);
+    atom = m - g * f.n;
+    Vec3 p;
+    p.x = __dadd_rn(__ldg(f.pos + 3 * atom + 0), __ldg(f.img_off + 3 * g + 0));
+    p.y = __dadd_rn(__ldg(f.pos + 3 * atom + 1), __ldg(f.img_off + 3 * g + 1));
+    p.z = __dadd_rn(__ldg(f.pos + 3 * atom + 2), __ldg(f.img_off + 3 * g + 2));
+    return p;
+}
+
+__device__ __forceinline__ Vec3 real_position(const FrameView &f, int atom) {
+    Vec3 p;
+    p.x = __ldg(f.pos + 3 * atom + 0);
+    p.y = __ldg(f.pos + 3 * atom + 1);
+    p.z = __ldg(f.pos + 3 * atom + 2);
+    return p;
+}
+
+// Euclidean distance with scipy cdist's operation order and no FMA contraction, so the
+// strict / inclusive cutoff tests decide exactly like the reference's dense masks
+// (representation/distances.py:66,134; angles.py:340,502-507).
+__device__ __forceinline__ double dist_rn(const Vec3 &p, const Vec3 &q) {
+    const double dx = __dsub_rn(p.x, q.x), dy = __dsub_rn(p.y, q.y), dz = __dsub_rn(p.z, q.z);
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
+    return v;
+}
+
+}  // namespace uf3b

@@ -1,0 +1,154 @@
+// gram.cu — normal-equation accumulation  G += X^T X,  b += X^T y  in float64.
+//
+// Replaces regression/least_squares.py:733-771 (batched_moore_penrose) for feature rows
+// that are already on the device, so a frame's 3N x F force rows never have to be
+// copied to the host before the fit.  Two accumulators (energy rows / force rows) are
+// kept, as WeightedLinearModel.fit_from_file does (:393-412).
+#include "common.cuh"
+
+struct uf3b_gram {
+    int n_cols = 0;
+    double *g[2] = {nullptr, nullptr};    // [n_cols * n_cols] row-major, upper blocks filled
+    double *b[2] = {nullptr, nullptr};    // [n_cols]
+    uf3b::DevBuf<double> stage_x, stage_y;
+};
+
+namespace uf3b {
+
+constexpr int GT = 64;        // output tile edge
+constexpr int GK = 16;        // rows per shared-memory stage
+constexpr int GROWS = 512;    // rows per block (split over the row dimension)
+
+// Tile (bi <= bj) of X^T X over rows [z*GROWS, (z+1)*GROWS); 256 threads, 4x4 per thread.
+__global__ void __launch_bounds__(256)
+k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols,
+       double *__restrict__ g) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    __shared__ double sa[GK][GT + 1], sb[GK][GT + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long r_begin = (long long)blockIdx.z * GROWS;
+    const long long r_end = r_begin + GROWS < rows ? r_begin + GROWS : rows;
+    double acc[4][4] = {};
+    for (long long r0 = r_begin; r0 < r_end; r0 += GK) {
+        for (int k = threadIdx.x; k < GK * GT; k += 256) {
+            const int rr = k / GT, cc = k % GT;
+            const long long r = r0 + rr;
+            const int ca = bi * GT + cc, cb = bj * GT + cc;
+            sa[rr][cc] = (r < r_end && ca < n_cols) ? x[r * ld + ca] : 0.0;
+            sb[rr][cc] = (r < r_end && cb < n_cols) ? x[r * ld + cb] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < GK; ++rr) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sa[rr][ty * 4 + i]; b[i] = sb[rr][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = bi * GT + ty * 4 + i, col = bj * GT + tx * 4 + j;
+            if (row < n_cols && col < n_cols && acc[i][j] != 0.0)
+                atomicAdd(g + (size_t)row * n_cols + col, acc[i][j]);
+        }
+}
+
+__global__ void __launch_bounds__(256)
+k_ordinate(const double *__restrict__ x, long long ld, const double *__restrict__ y, long long rows,
+           int n_cols, double *__restrict__ b) {
+    const long long r_begin = (long long)blockIdx.x * GROWS;
+    const long long r_end = r_begin + GROWS < rows ? r_begin + GROWS : rows;
+    for (int col = threadIdx.x; col < n_cols; col += blockDim.x) {
+        double s = 0.0;
+        for (long long r = r_begin; r < r_end; ++r) s += x[r * ld + col] * y[r];
+        if (s != 0.0) atomicAdd(b + col, s);
+    }
+}
+
+}  // namespace uf3b
+
+using namespace uf3b;
+
+extern "C" {
+
+int uf3b_gram_create(int32_t n_cols, uf3b_gram **out) {
+    if (n_cols < 1 || !out) return fail(UF3B_ERR_INVALID, "bad argument");
+    uf3b_gram *gm = new uf3b_gram();
+    gm->n_cols = n_cols;
+    for (int k = 0; k < 2; ++k) {
+        cudaError_t e = cudaMalloc((void **)&gm->g[k], sizeof(double) * n_cols * n_cols);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&gm->b[k], sizeof(double) * n_cols);
+        if (e == cudaSuccess) e = cudaMemset(gm->g[k], 0, sizeof(double) * n_cols * n_cols);
+        if (e == cudaSuccess) e = cudaMemset(gm->b[k], 0, sizeof(double) * n_cols);
+        if (e != cudaSuccess) {
+            uf3b_gram_destroy(gm);
+            return fail(UF3B_ERR_CUDA, "gram alloc: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = gm;
+    return UF3B_OK;
+}
+
+int uf3b_gram_accumulate(uf3b_gram *gm, const double *x, const double *y, int64_t rows, int64_t ld,
+                         int is_force, void *stream_) {
+    if (!gm || !x || !y) return fail(UF3B_ERR_INVALID, "null argument");
+    if (rows < 0 || ld < gm->n_cols) return fail(UF3B_ERR_INVALID, "bad rows / ld");
+    if (rows == 0) return UF3B_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int which = is_force ? 1 : 0;
+    const double *dx = x, *dy = y;
+    long long dld = ld;
+    if (!is_device_pointer(x)) {
+        UF3B_CUDA(gm->stage_x.reserve((size_t)rows * gm->n_cols));
+        UF3B_CUDA(cudaMemcpy2DAsync(gm->stage_x.p, sizeof(double) * gm->n_cols, x, sizeof(double) * ld,
+                                    sizeof(double) * gm->n_cols, (size_t)rows, cudaMemcpyHostToDevice, stream));
+        dx = gm->stage_x.p;
+        dld = gm->n_cols;
+    }
+    if (!is_device_pointer(y)) {
+        UF3B_CUDA(gm->stage_y.reserve((size_t)rows));
+        UF3B_CUDA(cudaMemcpyAsync(gm->stage_y.p, y, sizeof(double) * rows, cudaMemcpyHostToDevice, stream));
+        dy = gm->stage_y.p;
+    }
+    const int nb = (gm->n_cols + GT - 1) / GT;
+    const unsigned nz = (unsigned)((rows + GROWS - 1) / GROWS);
+    if (nz > 65535) return fail(UF3B_ERR_CAPACITY, "too many rows in one call (max %d)", 65535 * GROWS);
+    UF3B_LAUNCH(k_gram, dim3(nb, nb, nz), 256, 0, stream, dx, dld, (long long)rows, gm->n_cols, gm->g[which]);
+    UF3B_LAUNCH(k_ordinate, nz, 256, 0, stream, dx, dld, dy, (long long)rows, gm->n_cols, gm->b[which]);
+    if (dx != x || dy != y) UF3B_CUDA(cudaStreamSynchronize(stream));
+    return UF3B_OK;
+}
+
+int uf3b_gram_export(const uf3b_gram *gm, int is_force, double *gram_out, double *ord_out) {
+    if (!gm) return fail(UF3B_ERR_INVALID, "null handle");
+    const int which = is_force ? 1 : 0, n = gm->n_cols;
+    UF3B_CUDA(cudaDeviceSynchronize());
+    if (gram_out) {
+        UF3B_CUDA(cudaMemcpy(gram_out, gm->g[which], sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+        // only tiles with block-row <= block-col were accumulated: mirror the rest
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < i; ++j)
+                if (i / GT > j / GT) gram_out[(size_t)i * n + j] = gram_out[(size_t)j * n + i];
+    }
+    if (ord_out) UF3B_CUDA(cudaMemcpy(ord_out, gm->b[which], sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return UF3B_OK;
+}
+
+void uf3b_gram_destroy(uf3b_gram *gm) {
+    if (!gm) return;
+    for (int k = 0; k < 2; ++k) {
+        if (gm->g[k]) cudaFree(gm->g[k]);
+        if (gm->b[k]) cudaFree(gm->b[k]);
+    }
+    delete gm;
+}
+
+}  // extern "C"

@@ -1,0 +1,415 @@
+// neighbors.cu — Kernel A: neighbour lists over a cell-linked grid of the ghost supercell.
+//
+// Replaces geometry.get_supercell + distances.get_distance_matrix + the boolean masks of
+// the reference (data/geometry.py:14-51; representation/distances.py:19-75,146-169;
+// representation/angles.py:289-346), which materialise a dense (atoms x supercell)
+// distance matrix.  Here every periodic image that can lie within the search radius of
+// the real atoms is binned into cells of edge >= r_search (counting sort, 32-byte slots,
+// z-runs of cells contiguous), one thread block walks one cell, one warp one real centre,
+// and ragged per-centre hit counts are compacted with warp ballots.  Two CSR lists are
+// produced per centre, both sorted by supercell index (image_rank * n_atoms + atom):
+//   list 2:  max(r_min,0) < d < r_max  of the pair's own bounds    (distances.py:60-66)
+//   list 3:  r3min < d <= r3max                                      (angles.py:340)
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace uf3b {
+
+struct GridParams {
+    double ox, oy, oz;     // lower corner of the binned region
+    double hx, hy, hz;     // upper corner (ghosts outside are dropped)
+    double edge;
+    int nx, ny, nz;
+};
+
+// species lookup + bounding box of the real atoms (one block).
+__global__ void __launch_bounds__(1024) k_prepare(int n, const int *__restrict__ z,
+                                                  const int *__restrict__ z_to_spec,
+                                                  const double *__restrict__ pos,
+                                                  int *__restrict__ spec, double *__restrict__ bbox,
+                                                  int *__restrict__ err) {
+    __shared__ double red[6][32];
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int bad = 0;
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        const int zz = z[a];
+        const int s = (zz >= 0 && zz < 128) ? z_to_spec[zz] : -1;
+        spec[a] = s < 0 ? 0 : s;
+        if (s < 0) bad = 1;
+        for (int c = 0; c < 3; ++c) {
+            const double v = pos[3 * a + c];
+            lo[c] = fmin(lo[c], v);
+            hi[c] = fmax(hi[c], v);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = 0; c < 3; ++c) {
+        for (int s = 16; s > 0; s >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(FULL, lo[c], s));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(FULL, hi[c], s));
+        }
+        if (lane == 0) { red[c][warp] = lo[c]; red[3 + c][warp] = hi[c]; }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *err = 1;
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int c = 0; c < 3; ++c) {
+            double l = lane < nw ? red[c][lane] : INFINITY;
+            double h = lane < nw ? red[3 + c][lane] : -INFINITY;
+            for (int s = 16; s > 0; s >>= 1) {
+                l = fmin(l, __shfl_xor_sync(FULL, l, s));
+                h = fmax(h, __shfl_xor_sync(FULL, h, s));
+            }
+            if (lane == 0) { bbox[c] = l; bbox[3 + c] = h; }
+        }
+    }
+}
+
+__device__ __forceinline__ int cell_coord(double p, double o, double edge, int n) {
+    int c = (int)floor((p - o) / edge);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+// One thread per supercell atom m = g*n + a: drop ghosts outside the padded bounding box
+// of the real atoms, count the rest per cell.
+__global__ void k_bin_count(int n, long long n_sup, const double *__restrict__ pos,
+                            const double *__restrict__ img_off, GridParams G,
+                            int *__restrict__ cell_of, int *__restrict__ cell_cnt) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_sup;
+         m += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(m / n), a = (int)(m - (long long)g * n);
+        const double x = __dadd_rn(pos[3 * a + 0], img_off[3 * g + 0]);
+        const double y = __dadd_rn(pos[3 * a + 1], img_off[3 * g + 1]);
+        const double z = __dadd_rn(pos[3 * a + 2], img_off[3 * g + 2]);
+        int cell = -1;
+        if (g == 0 || (x >= G.ox && x <= G.hx && y >= G.oy && y <= G.hy && z >= G.oz && z <= G.hz)) {
+            const int cx = cell_coord(x, G.ox, G.edge, G.nx);
+            const int cy = cell_coord(y, G.oy, G.edge, G.ny);
+            const int cz = cell_coord(z, G.oz, G.edge, G.nz);
+            cell = (cx * G.ny + cy) * G.nz + cz;
+            atomicAdd(cell_cnt + cell, 1);
+        }
+        cell_of[m] = cell;
+    }
+}
+
+__global__ void k_bin_fill(int n, long long n_sup, const double *__restrict__ pos,
+                           const double *__restrict__ img_off, const int *__restrict__ spec,
+                           const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                           int *__restrict__ cursor, Slot *__restrict__ slots) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_sup;
+         m += (long long)gridDim.x * blockDim.x) {
+        const int cell = cell_of[m];
+        if (cell < 0) continue;
+        const int g = (int)(m / n), a = (int)(m - (long long)g * n);
+        Slot s;
+        s.x = __dadd_rn(pos[3 * a + 0], img_off[3 * g + 0]);
+        s.y = __dadd_rn(pos[3 * a + 1], img_off[3 * g + 1]);
+        s.z = __dadd_rn(pos[3 * a + 2], img_off[3 * g + 2]);
+        s.m = (int)m;
+        s.spec = spec[a];
+        slots[cell_start[cell] + atomicAdd(cursor + cell, 1)] = s;
+    }
+}
+
+// Exclusive scan of up to two int arrays (block b scans array b); out[n] = total.
+constexpr int SCAN_ITEMS = 8;
+__global__ void __launch_bounds__(1024) k_scan(const int *in0, int *out0, const int *in1,
+                                               int *out1, int n, long long *totals) {
+    const int *in = blockIdx.x ? in1 : in0;
+    int *out = blockIdx.x ? out1 : out0;
+    __shared__ long long warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long carry = 0;
+    for (long long base = 0; base < n; base += 1024 * SCAN_ITEMS) {
+        const long long i0 = base + (long long)threadIdx.x * SCAN_ITEMS;
+        int vals[SCAN_ITEMS];
+        long long local = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            vals[k] = (i0 + k < n) ? in[i0 + k] : 0;
+            local += vals[k];
+        }
+        long long inc = local;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const long long up = __shfl_up_sync(FULL, inc, s);
+            if (lane >= s) inc += up;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_tot[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const long long up = __shfl_up_sync(FULL, w, s);
+                if (lane >= s) w += up;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        long long excl = carry + inc - local + (warp ? warp_tot[warp - 1] : 0);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (i0 + k < n) out[i0 + k] = (int)excl;
+            excl += vals[k];
+        }
+        carry += warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[n] = (int)carry;
+        totals[blockIdx.x] = carry;
+    }
+}
+
+// Row of `n` distinct ints: out[rank(v)] = v.
+__device__ __forceinline__ void warp_rank_sort(const int *src, int *dst, int n, int lane) {
+    for (int e = lane; e < n; e += 32) {
+        const int v = src[e];
+        int rank = 0;
+        for (int k = 0; k < n; ++k) rank += src[k] < v;
+        dst[rank] = v;
+    }
+}
+
+constexpr int NL_WARPS = 4;
+
+// Block = one cell, warp = one real centre of that cell.  FILL=false counts, FILL=true
+// writes the hits (ballot-compacted) and sorts each row by supercell index.
+template <bool FILL>
+__global__ void __launch_bounds__(NL_WARPS * 32)
+k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots,
+            const int *__restrict__ cell_start, int n_real, int *__restrict__ cnt2,
+            int *__restrict__ cnt3, const int *__restrict__ off2, const int *__restrict__ off3,
+            int *__restrict__ scratch2, int *__restrict__ scratch3, int *__restrict__ idx2,
+            int *__restrict__ idx3) {
+    const int cell = blockIdx.x;
+    const int s0 = cell_start[cell], s1 = cell_start[cell + 1];
+    if (s0 == s1) return;
+    const int cz = cell % G.nz, cy = (cell / G.nz) % G.ny, cx = cell / (G.nz * G.ny);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool has3 = B.n_trios > 0;
+    for (int s = s0 + warp; s < s1; s += NL_WARPS) {
+        const Slot c = slots[s];
+        if (c.m >= n_real) continue;        // ghosts are never centres
+        const Vec3 pc = {c.x, c.y, c.z};
+        int n2 = 0, n3 = 0, base2 = 0, base3 = 0;
+        if (FILL) { base2 = off2[c.m]; base3 = off3[c.m]; }
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = cx + dx;
+            if (x < 0 || x >= G.nx) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= G.ny) continue;
+                const int z0 = cz > 0 ? cz - 1 : 0, z1 = cz + 1 < G.nz ? cz + 1 : G.nz - 1;
+                const int row = (x * G.ny + y) * G.nz;
+                const int r0 = cell_start[row + z0], r1 = cell_start[row + z1 + 1];
+                for (int q0 = r0; q0 < r1; q0 += 32) {
+                    const int q = q0 + lane;
+                    bool k2 = false, k3 = false;
+                    int m = 0;
+                    if (q < r1) {
+                        const Slot t = slots[q];
+                        const Vec3 pt = {t.x, t.y, t.z};
+                        const double d = dist_rn(pc, pt);
+                        const int p = pair_index(B.ne, c.spec, t.spec);
+                        k2 = d > B.pair_lo[p] && d < B.pair_hi[p];
+                        k3 = has3 && d > B.r3min && d <= B.r3max;
+                        m = t.m;
+                    }
+                    const unsigned b2 = __ballot_sync(FULL, k2), b3 = __ballot_sync(FULL, k3);
+                    if (FILL) {
+                        if (k2) scratch2[base2 + n2 + __popc(b2 & lt)] = m;
+                        if (k3) scratch3[base3 + n3 + __popc(b3 & lt)] = m;
+                    }
+                    n2 += __popc(b2);
+                    n3 += __popc(b3);
+                }
+            }
+        }
+        if (!FILL) {
+            if (lane == 0) { cnt2[c.m] = n2; cnt3[c.m] = n3; }
+        } else {
+            __syncwarp();
+            warp_rank_sort(scratch2 + base2, idx2 + base2, n2, lane);
+            warp_rank_sort(scratch3 + base3, idx3 + base3, n3, lane);
+        }
+    }
+}
+
+}  // namespace uf3b
+
+using namespace uf3b;
+
+FrameView uf3b_nlist::view() const {
+    FrameView f;
+    f.n = (int)n;
+    f.n_img = n_img;
+    f.pos = pos.p;
+    f.spec = spec.p;
+    f.img_off = img_off.p;
+    f.img_inv = img_inv.p;
+    f.off2 = off2.p; f.idx2 = idx2.p;
+    f.off3 = off3.p; f.idx3 = idx3.p;
+    return f;
+}
+
+extern "C" {
+
+int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *positions,
+                         const int32_t *atomic_numbers, int32_t n_images,
+                         const double *image_offsets, const int32_t *image_abc,
+                         uf3b_nlist **inout, void *stream_) {
+    if (!basis || !inout) return fail(UF3B_ERR_INVALID, "null argument");
+    if (n_atoms < 0 || n_images < 1) return fail(UF3B_ERR_INVALID, "bad n_atoms / n_images");
+    if (n_atoms > 0 && (!positions || !atomic_numbers)) return fail(UF3B_ERR_INVALID, "null positions");
+    if (!image_offsets || !image_abc) return fail(UF3B_ERR_INVALID, "null image table");
+    const long long n_sup = (long long)n_atoms * n_images;
+    if (n_sup >= (1LL << 31) - 64) return fail(UF3B_ERR_CAPACITY, "supercell exceeds int32 indices");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool created = (*inout == nullptr);
+    uf3b_nlist *nl = created ? new uf3b_nlist() : *inout;
+    struct Guard {   // frees a list created by a failing call
+        uf3b_nlist *p; bool armed;
+        ~Guard() { if (armed) delete p; }
+    } guard{nl, created};
+
+    const int n = (int)n_atoms;
+    nl->n = n_atoms;
+    nl->n_img = n_images;
+    nl->total2 = nl->total3 = 0;
+
+    // periodic image table: pair every image with the one of negated coordinates
+    std::vector<int> inv(n_images, 0);
+    {
+        std::map<std::tuple<int, int, int>, int> rank;
+        for (int g = 0; g < n_images; ++g)
+            rank[std::make_tuple(image_abc[3 * g], image_abc[3 * g + 1], image_abc[3 * g + 2])] = g;
+        if (image_abc[0] || image_abc[1] || image_abc[2])
+            return fail(UF3B_ERR_INVALID, "image 0 must be the home cell");
+        for (int g = 0; g < n_images; ++g) {
+            auto it = rank.find(std::make_tuple(-image_abc[3 * g], -image_abc[3 * g + 1], -image_abc[3 * g + 2]));
+            if (it == rank.end()) return fail(UF3B_ERR_INVALID, "image table is not inversion symmetric");
+            inv[g] = it->second;
+        }
+    }
+    UF3B_CUDA(nl->img_off.reserve(3 * (size_t)n_images));
+    UF3B_CUDA(nl->img_inv.reserve(n_images));
+    UF3B_CUDA(nl->off2.reserve((size_t)n + 1));
+    UF3B_CUDA(nl->off3.reserve((size_t)n + 1));
+    UF3B_CUDA(nl->totals.reserve(4));
+    UF3B_CUDA(cudaMemcpyAsync(nl->img_off.p, image_offsets, sizeof(double) * 3 * n_images, cudaMemcpyDefault, stream));
+    UF3B_CUDA(cudaMemcpyAsync(nl->img_inv.p, inv.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, stream));
+    if (n == 0) {
+        UF3B_CUDA(cudaMemsetAsync(nl->off2.p, 0, sizeof(int), stream));
+        UF3B_CUDA(cudaMemsetAsync(nl->off3.p, 0, sizeof(int), stream));
+        UF3B_CUDA(cudaStreamSynchronize(stream));
+        guard.armed = false;
+        *inout = nl;
+        return UF3B_OK;
+    }
+    UF3B_CUDA(nl->pos.reserve(3 * (size_t)n));
+    UF3B_CUDA(nl->z.reserve(n));
+    UF3B_CUDA(nl->spec.reserve(n));
+    UF3B_CUDA(nl->misc.reserve(8));
+    UF3B_CUDA(nl->cnt.reserve(2 * (size_t)n + 2));
+    UF3B_CUDA(cudaMemcpyAsync(nl->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyDefault, stream));
+    UF3B_CUDA(cudaMemcpyAsync(nl->z.p, atomic_numbers, sizeof(int) * n, cudaMemcpyDefault, stream));
+    int *d_err = (int *)(nl->misc.p + 6);
+    UF3B_CUDA(cudaMemsetAsync(d_err, 0, sizeof(double), stream));
+    UF3B_LAUNCH(k_prepare, 1, 1024, 0, stream, n, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
+                nl->spec.p, nl->misc.p, d_err);
+    double h_misc[7];
+    UF3B_CUDA(cudaMemcpyAsync(h_misc, nl->misc.p, sizeof h_misc, cudaMemcpyDeviceToHost, stream));
+    UF3B_CUDA(cudaStreamSynchronize(stream));
+    int h_err;
+    memcpy(&h_err, &h_misc[6], sizeof h_err);
+    if (h_err) return fail(UF3B_ERR_ELEMENT, "configuration holds an element outside the basis");
+    for (int c = 0; c < 6; ++c)
+        if (!std::isfinite(h_misc[c])) return fail(UF3B_ERR_INVALID, "non-finite position");
+
+    // grid over the bounding box of the real atoms padded by the search radius
+    GridParams G;
+    const double pad = basis->tab.r_search * (1.0 + 1e-9);
+    G.edge = pad;
+    G.ox = h_misc[0] - pad; G.oy = h_misc[1] - pad; G.oz = h_misc[2] - pad;
+    G.hx = h_misc[3] + pad; G.hy = h_misc[4] + pad; G.hz = h_misc[5] + pad;
+    long long n_cell;
+    const long long cell_cap = std::max<long long>(1 << 22, 8 * n_sup);
+    for (;;) {
+        G.nx = (int)std::floor((G.hx - G.ox) / G.edge) + 1;
+        G.ny = (int)std::floor((G.hy - G.oy) / G.edge) + 1;
+        G.nz = (int)std::floor((G.hz - G.oz) / G.edge) + 1;
+        n_cell = (long long)G.nx * G.ny * G.nz;
+        if (n_cell <= cell_cap) break;
+        G.edge *= 1.26;     // very sparse configuration: coarser cells stay correct
+    }
+    UF3B_CUDA(nl->cell_of.reserve((size_t)n_sup));
+    UF3B_CUDA(nl->cell_start.reserve((size_t)n_cell + 1));
+    UF3B_CUDA(nl->cell_cursor.reserve((size_t)n_cell));
+    UF3B_CUDA(cudaMemsetAsync(nl->cell_start.p, 0, sizeof(int) * (n_cell + 1), stream));
+    UF3B_CUDA(cudaMemsetAsync(nl->cell_cursor.p, 0, sizeof(int) * n_cell, stream));
+    const int bin_blocks = (int)std::min<long long>((n_sup + 255) / 256, 148 * 16);
+    UF3B_LAUNCH(k_bin_count, bin_blocks, 256, 0, stream, n, n_sup, nl->pos.p, nl->img_off.p, G,
+                nl->cell_of.p, nl->cell_start.p);
+    UF3B_LAUNCH(k_scan, 1, 1024, 0, stream, nl->cell_start.p, nl->cell_start.p, nullptr, nullptr,
+                (int)n_cell, nl->totals.p);
+    // every supercell atom that survives the box test has a slot; n_sup bounds it
+    UF3B_CUDA(nl->slots.reserve((size_t)n_sup));
+    UF3B_LAUNCH(k_bin_fill, bin_blocks, 256, 0, stream, n, n_sup, nl->pos.p, nl->img_off.p,
+                nl->spec.p, nl->cell_of.p, nl->cell_start.p, nl->cell_cursor.p, nl->slots.p);
+
+    int *cnt2 = nl->cnt.p, *cnt3 = nl->cnt.p + n + 1;
+    UF3B_LAUNCH(k_neighbors<false>, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G,
+                nl->slots.p, nl->cell_start.p, n, cnt2, cnt3, nullptr, nullptr, nullptr, nullptr,
+                nullptr, nullptr);
+    UF3B_LAUNCH(k_scan, 2, 1024, 0, stream, cnt2, nl->off2.p, cnt3, nl->off3.p, n, nl->totals.p + 1);
+    long long h_tot[2];
+    UF3B_CUDA(cudaMemcpyAsync(h_tot, nl->totals.p + 1, sizeof h_tot, cudaMemcpyDeviceToHost, stream));
+    UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (h_tot[0] >= (1LL << 31) || h_tot[1] >= (1LL << 31))
+        return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
+    nl->total2 = h_tot[0];
+    nl->total3 = h_tot[1];
+    UF3B_CUDA(nl->idx2.reserve((size_t)h_tot[0] + 1));
+    UF3B_CUDA(nl->idx3.reserve((size_t)h_tot[1] + 1));
+    UF3B_CUDA(nl->scratch.reserve((size_t)(h_tot[0] + h_tot[1]) + 2));
+    UF3B_LAUNCH(k_neighbors<true>, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G,
+                nl->slots.p, nl->cell_start.p, n, nullptr, nullptr, nl->off2.p, nl->off3.p,
+                nl->scratch.p, nl->scratch.p + h_tot[0], nl->idx2.p, nl->idx3.p);
+    guard.armed = false;
+    *inout = nl;
+    return UF3B_OK;
+}
+
+int uf3b_neighbors_count(const uf3b_nlist *nl, int which, int64_t *n_entries) {
+    if (!nl || !n_entries || (which != 2 && which != 3)) return fail(UF3B_ERR_INVALID, "bad argument");
+    *n_entries = which == 2 ? nl->total2 : nl->total3;
+    return UF3B_OK;
+}
+
+int uf3b_neighbors_export(const uf3b_nlist *nl, int which, int64_t *offsets, int64_t *supercell_index) {
+    if (!nl || !offsets || (which != 2 && which != 3)) return fail(UF3B_ERR_INVALID, "bad argument");
+    const int64_t total = which == 2 ? nl->total2 : nl->total3;
+    std::vector<int> off((size_t)nl->n + 1), idx((size_t)total);
+    UF3B_CUDA(cudaDeviceSynchronize());
+    UF3B_CUDA(cudaMemcpy(off.data(), which == 2 ? nl->off2.p : nl->off3.p, sizeof(int) * off.size(), cudaMemcpyDeviceToHost));
+    if (total) {
+        if (!supercell_index) return fail(UF3B_ERR_INVALID, "null index buffer");
+        UF3B_CUDA(cudaMemcpy(idx.data(), which == 2 ? nl->idx2.p : nl->idx3.p, sizeof(int) * idx.size(), cudaMemcpyDeviceToHost));
+    }
+    for (size_t i = 0; i < off.size(); ++i) offsets[i] = off[i];
+    for (size_t i = 0; i < idx.size(); ++i) supercell_index[i] = idx[i];
+    return UF3B_OK;
+}
+
+void uf3b_nlist_destroy(uf3b_nlist *nl) { delete nl; }
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""Owner of the device-side handles (basis tables + one reusable neighbour list).
+
+`Engine` is the only place in the package that calls the C ABI (`include/uf3b.h`).
+`process.BasisFeaturizer` and `calculator.UFCalculator` hold one lazily, drop it when
+pickled (the reference ships featurizers to worker processes, util/parallel.py:182) and
+re-create it in the process / on the GPU where they are next used.
+"""
+import ctypes as C
+
+import numpy as np
+
+from uf3_b200 import _native, geometry
+from uf3_b200.tables import BasisTables
+
+
+def _ptr(arr):
+    return C.c_void_p(arr.ctypes.data)
+
+
+class Engine:
+    def __init__(self, basis, device=None):
+        self._lib = _native.lib()
+        if device is not None:
+            _native.check(self._lib.uf3b_set_device(int(device)))
+        self.tables = BasisTables(basis)
+        self.n_feats = self.tables.n_feats
+        self._basis = C.c_void_p()
+        _native.check(self._lib.uf3b_basis_create(C.byref(self.tables.desc), C.byref(self._basis)))
+        self._nlist = C.c_void_p()
+        self.n_atoms = 0
+        self.has_coefficients = False
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_lib", None) is None:
+            return
+        if self._nlist:
+            self._lib.uf3b_nlist_destroy(self._nlist)
+            self._nlist = C.c_void_p()
+        if self._basis:
+            self._lib.uf3b_basis_destroy(self._basis)
+            self._basis = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ inputs
+    def set_coefficients(self, coefficients):
+        c = np.ascontiguousarray(coefficients, dtype=np.float64)
+        _native.check(self._lib.uf3b_basis_set_coefficients(
+            self._basis, c.ctypes.data_as(C.POINTER(C.c_double)), len(c)))
+        self.has_coefficients = True
+
+    def build_neighbors(self, positions, numbers, cell=None, pbc=None, images=None, stream=None):
+        """Kernel A.  `images` = (abc (n_img,3) int, offsets (n_img,3) float64) overrides the
+        periodic-image table derived from (cell, pbc, r_cut) by `geometry.image_table`."""
+        positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        numbers = np.ascontiguousarray(numbers, dtype=np.int32)
+        if len(numbers) != len(positions):
+            raise ValueError("numbers and positions disagree on n_atoms")
+        if images is None:
+            if cell is None or pbc is None or not np.any(pbc):
+                images = (np.zeros((1, 3), dtype=np.int64), np.zeros((1, 3)))
+            else:
+                images = geometry.image_table(cell, pbc, self.tables.r_cut)
+        abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
+        offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
+        _native.check(self._lib.uf3b_neighbors_build(
+            self._basis, len(positions), _ptr(positions), _ptr(numbers), len(offsets),
+            _ptr(offsets), _ptr(abc), C.byref(self._nlist), stream))
+        self.n_atoms = len(positions)
+        return self
+
+    def build_neighbors_device(self, positions_ptr, numbers_ptr, n_atoms, images, stream=None):
+        """Same with DEVICE pointers for positions (n,3 float64) and numbers (n int32)."""
+        abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
+        offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
+        _native.check(self._lib.uf3b_neighbors_build(
+            self._basis, int(n_atoms), C.c_void_p(positions_ptr), C.c_void_p(numbers_ptr),
+            len(offsets), _ptr(offsets), _ptr(abc), C.byref(self._nlist), stream))
+        self.n_atoms = int(n_atoms)
+        return self
+
+    def neighbor_list(self, which):
+        """CSR (offsets int64 [n+1], supercell indices int64) of list 2 or 3 (parity hook)."""
+        total = C.c_int64()
+        _native.check(self._lib.uf3b_neighbors_count(self._nlist, which, C.byref(total)))
+        offsets = np.zeros(self.n_atoms + 1, dtype=np.int64)
+        idx = np.zeros(max(total.value, 1), dtype=np.int64)
+        _native.check(self._lib.uf3b_neighbors_export(
+            self._nlist, which, offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+            idx.ctypes.data_as(C.POINTER(C.c_int64))))
+        return offsets, idx[:total.value]
+
+    # ------------------------------------------------------------------ kernels B
+    def featurize(self, energy=True, forces=True, out_energy=None, out_forces=None, stream=None):
+        """Feature rows of the configuration last passed to `build_neighbors`.
+
+        Returns (x_energy [F] or None, x_forces [3N, F] or None); force row c*N + a.
+        `out_*` may be preallocated (e.g. pinned) float64 arrays."""
+        n, F = self.n_atoms, self.n_feats
+        xe = xf = None
+        if energy:
+            xe = out_energy if out_energy is not None else np.empty(F)
+        if forces:
+            xf = out_forces if out_forces is not None else np.empty((3 * n, F))
+            if xf.shape != (3 * n, F) or not xf.flags.c_contiguous or xf.dtype != np.float64:
+                raise ValueError("out_forces must be a C-contiguous float64 (3N, F) array")
+        _native.check(self._lib.uf3b_featurize(
+            self._basis, self._nlist, _ptr(xe) if energy else None,
+            _ptr(xf) if (forces and n) else None, F, stream))
+        return xe, xf
+
+    def featurize_device(self, energy_ptr, forces_ptr, ld, stream=None):
+        """Device-pointer form: rows are left in device memory (row stride `ld` doubles)."""
+        _native.check(self._lib.uf3b_featurize(
+            self._basis, self._nlist, C.c_void_p(energy_ptr) if energy_ptr else None,
+            C.c_void_p(forces_ptr) if forces_ptr else None, int(ld), stream))
+
+    def energy_forces(self, energy=True, forces=True, stream=None):
+        n = self.n_atoms
+        e = np.zeros(1) if energy else None
+        f = np.zeros((n, 3)) if forces else None
+        _native.check(self._lib.uf3b_energy_forces(
+            self._basis, self._nlist, _ptr(e) if energy else None,
+            _ptr(f) if (forces and n) else None, None, stream))
+        return (float(e[0]) if energy else None), f
+
+    def energy_forces_device(self, energy_ptr, forces_ptr, stream=None):
+        _native.check(self._lib.uf3b_energy_forces(
+            self._basis, self._nlist, C.c_void_p(energy_ptr) if energy_ptr else None,
+            C.c_void_p(forces_ptr) if forces_ptr else None, None, stream))
+
+    # ------------------------------------------------------------------ instrumentation
+    def launch_count(self):
+        return int(self._lib.uf3b_launch_count())
+
+    def set_timing(self, enabled):
+        self._lib.uf3b_set_timing(1 if enabled else 0)
+
+    def last_kernel_ms(self):
+        return float(self._lib.uf3b_last_kernel_ms())
