@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric: atom-steps/s featurized (2+3-body) on 10k-atom bulk W.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--basis demo|manuscript]
+    python bench.py --impl reference ...       # CPU arm: the oracle port on the host cores
+
+One step = one 10 000-atom frame taken through the whole hot path: neighbour lists
+(Kernel A) + energy row + 3N force rows (Kernel B).  `value` has the frame resident in HBM
+and leaves the rows in HBM; `e2e` goes through the same C-ABI calls with HOST buffers
+(pinned), host->device and device->host copies inside the timed region.  Under torchrun
+every rank featurizes its own frames (frames are independent: weak scaling, no collective
+on the data path); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "bulk bcc W 10x20x25 cells (10000 atoms/frame), sigma=0.05 A, 2+3-body featurization"
+N_POOL = 4          # distinct frames per rank, cycled
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[4:8]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(smax)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_basis(kind):
+    from uf3_b200 import synthetic
+    return synthetic.w_basis(kind)
+
+
+def frame(seed):
+    from uf3_b200 import synthetic
+    return synthetic.bcc_w((10, 20, 25), seed=seed)
+
+
+# --------------------------------------------------------------------------- CPU arms
+def oracle_frames_per_second(basis, n_frames, threads):
+    """Oracle port (oracle/uf3_oracle.c) on `n_frames` full frames, `threads` at a time."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import uf3_oracle as orc
+    from uf3_b200 import geometry
+    packed = orc.PackedBasis(basis)
+    frames = [frame(1000 + i) for i in range(n_frames)]
+    images = geometry.image_table(frames[0][2], frames[0][3], basis.r_cut)
+
+    def work(fr):
+        orc.featurize(packed, fr[0], fr[1], images[1], energy=True, forces=True)
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        for fr in frames:
+            work(fr)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(work, frames))
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """CPU arm.  The reference is pure Python and holds dense O(M^2) matrices (it cannot
+    represent a 10k-atom frame: SURVEY.md fact 2) and cannot travel to the GPU box, so the
+    arm times the C restatement of its algorithm (the oracle port) on all host threads."""
+    if rank != 0:
+        return
+    basis = make_basis(args.basis)
+    cores = os.cpu_count() or 1
+    n_atoms = 10000
+    for _ in range(min(args.warmup, 1)):
+        oracle_frames_per_second(basis, cores, cores)
+    times = [oracle_frames_per_second(basis, cores, cores) for _ in range(args.steps)]
+    total = sum(times)
+    value = cores * n_atoms * args.steps / total
+    line = {
+        "impl": "reference", "metric": "atom-steps/s featurized (2+3-body) on 10k-atom W",
+        "value": value, "unit": "atom-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "basis": args.basis, "n_feats": int(basis.n_feats),
+                   "step": f"{cores} frames of 10000 atoms, one per host thread"},
+        "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} full 10k-atom frames per step (energy row + 3N force "
+                                   "rows), oracle/uf3_oracle.c, one frame per thread"},
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from uf3_b200 import geometry
+    from uf3_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    basis = make_basis(args.basis)
+    eng = Engine(basis, device=local_rank)
+    F = eng.n_feats
+    frames = [frame(rank * N_POOL + i) for i in range(N_POOL)]
+    n_atoms = len(frames[0][0])
+    images = geometry.image_table(frames[0][2], frames[0][3], basis.r_cut)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    d_pos = [torch.from_numpy(fr[0]).to(dev) for fr in frames]
+    d_num = torch.from_numpy(frames[0][1]).to(dev)
+    d_xe = torch.empty(F, dtype=torch.float64, device=dev)
+    d_xf = torch.empty((3 * n_atoms, F), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step_resident(i):
+        eng.build_neighbors_device(d_pos[i % N_POOL].data_ptr(), d_num.data_ptr(), n_atoms, images,
+                                   stream)
+        eng.featurize_device(d_xe.data_ptr(), d_xf.data_ptr(), F, stream)
+
+    h_pos = [torch.from_numpy(fr[0]).pin_memory() for fr in frames]
+    h_num = torch.from_numpy(frames[0][1]).pin_memory()
+    h_xe = torch.empty(F, dtype=torch.float64).pin_memory()
+    h_xf = torch.empty((3 * n_atoms, F), dtype=torch.float64).pin_memory()
+    h_pos_np = [t.numpy() for t in h_pos]
+    h_num_np, h_xe_np, h_xf_np = h_num.numpy(), h_xe.numpy(), h_xf.numpy()
+
+    def step_e2e(i):
+        eng.build_neighbors(h_pos_np[i % N_POOL], h_num_np, images=images, stream=stream)
+        eng.featurize(out_energy=h_xe_np, out_forces=h_xf_np, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(step, steps, warmup):
+        for i in range(warmup):
+            step(i)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        launches0 = eng.launch_count()
+        for k in range(steps):
+            flush.zero_()                      # L2 flush, outside the per-step event bracket
+            ev[k][0].record()
+            step(warmup + k)
+            ev[k][1].record()
+        barrier()
+        launches = eng.launch_count() - launches0
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches = timed(step_resident, args.steps, args.warmup)
+    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # dominant kernel (k_featurize), timed alone with CUDA events on its own stream
+    eng.set_timing(True)
+    kernel_ms = []
+    for i in range(5):
+        flush.zero_()
+        step_resident(i)
+        kernel_ms.append(eng.last_kernel_ms())
+    eng.set_timing(False)
+    k_ms = statistics.mean(kernel_ms[1:])
+    e2, e3 = eng.neighbor_count(2), eng.neighbor_count(3)
+    # algorithmic bytes of one k_featurize launch (DESIGN.md "Kernel B"): positions + species,
+    # both CSR lists, and the 3N x F force rows + energy row written once.
+    alg_bytes = n_atoms * 28 + 4 * (e2 + e3) + 8 * (n_atoms + 1) + 24 * n_atoms * F + 8 * F
+    peak, peak_src = load_peaks()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+
+    value = world * n_atoms * args.steps / (total_ms * 1e-3)
+    e2e_value = world * n_atoms * args.steps / (e2e_ms * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fp64_peak = eng.probe_fp64_tflops()
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu_frames = 4
+        t_cpu = oracle_frames_per_second(basis, n_cpu_frames, 1)
+        cpu = {"value": n_cpu_frames * n_atoms / t_cpu, "unit": "atom-steps/s", "cores": 1,
+               "kind": "port",
+               "sample": f"{n_cpu_frames} full 10k-atom frames (energy row + 3N force rows), "
+                         "oracle/uf3_oracle.c, single thread"}
+    line = {
+        "metric": "atom-steps/s featurized (2+3-body) on 10k-atom W",
+        "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "basis": args.basis, "n_feats": F,
+                   "frames_per_rank_pool": N_POOL, "pairs_per_atom": e2 / n_atoms,
+                   "list3_per_atom": e3 / n_atoms,
+                   "step": "neighbour lists + energy row + 3N force rows of one frame per rank",
+                   "l2": "flushed between steps (256 MiB memset outside the per-step event bracket)"},
+        "e2e": {"value": e2e_value, "unit": "atom-steps/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": n_atoms * 28 + images[1].nbytes + images[0].size * 4,
+                "d2h_bytes_per_step": (3 * n_atoms + 1) * F * 8},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_featurize", "achieved": achieved, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes},
+        "roofline_fp64": {"peak_tflops": fp64_peak, "peak_source": "uf3b_probe_fp64_tflops (DFMA chains)",
+                          "note": "3-body rows are FP64-bound, see DESIGN.md"},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--basis", default="demo", choices=["demo", "manuscript"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

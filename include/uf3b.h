@@ -158,6 +158,9 @@ int64_t uf3b_launch_count(void);
  * measured with CUDA events on the call's stream; enable with uf3b_set_timing(1). */
 int uf3b_set_timing(int enabled);
 double uf3b_last_kernel_ms(void);
+/* Measured non-tensor float64 FMA rate of the current device (dependent DFMA chains):
+ * the second roof the 3-body kernels are reported against in bench.py. */
+int uf3b_probe_fp64_tflops(double *tflops);
 
 #ifdef __cplusplus
 }

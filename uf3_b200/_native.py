@@ -69,6 +69,7 @@ SIGNATURES = {
     "uf3b_launch_count": (C.c_int64, []),
     "uf3b_set_timing": (C.c_int, [C.c_int]),
     "uf3b_last_kernel_ms": (C.c_double, []),
+    "uf3b_probe_fp64_tflops": (C.c_int, [_f64p]),
 }
 
 _lib = None

@@ -231,6 +231,9 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     T.bin_col = (const int *)(base + o_bin_col);
     T.bin_w = (const double *)(base + o_bin_w);
     T.z_to_spec = (const int *)(base + o_z);
+    T.unit_weights = 1;
+    for (int k = 0; k < n_bins; ++k)
+        if (bin_col[k] >= 0 && bin_w[k] != 1.0) T.unit_weights = 0;
     T.coeff = b->coeff;
     T.c_grid = b->c_grid;
     b->n_bins = n_bins;

@@ -94,6 +94,8 @@ struct BasisTab {
     const double *coeff;      // flat model coefficients [n_feats]   (inference only)
     const double *c_grid;     // decompressed 3-body coefficient grids, bin layout
     const int *z_to_spec;     // [128] atomic number -> element index or -1
+    int unit_weights;         // every kept bin folds with weight exactly 1 (always true for
+                              // tables produced from compress_3B; lets kernels skip bin_w)
 };
 
 // One binned supercell atom (32 B so that a run of cells is one aligned bulk copy).
@@ -134,6 +136,7 @@ struct uf3b_basis {
     uf3b::DevBuf<double> partials;
     uf3b::DevBuf<double> stage;
     uf3b::DevBuf<double> stage_e;
+    uf3b::DevBuf<double> gacc;     // global-memory accumulators for very wide rows
 };
 
 struct uf3b_nlist {

@@ -24,15 +24,21 @@
 
 namespace uf3b {
 
+// One triangle as seen by the accumulating atom.  Header words first so that both are
+// 16-byte aligned broadcast loads in phase B.
 struct __align__(16) TriRec {
-    double v[3][4], dv[3][4];
-    double A[3], B[3], C[3];
     int base;              // bin index of (il, im, in), trio offset included
     int mn, nn;            // bin strides of l and m
-    int dlm, dmn, dln;     // il-im, im-in, il-in (mirror classes of symmetric trios)
     int col0;              // first feature column of the trio
-    int flags;             // bit0 valid, bit1 centre role, bits 8+: symmetry order
+    int pack;              // PK_* flags | symmetry << 8; 0 = record contributes nothing
+    int dlm, dmn;          // il-im, im-in (mirror classes of symmetric trios)
+    int pad0;
+    double v[3][4], dv[3][4];
+    double A[3], B[3], C[3];
+    double pad1;
 };
+static_assert(sizeof(TriRec) % 16 == 0, "TriRec must keep 16-byte alignment in arrays");
+constexpr int PK_VALID = 1, PK_CENTRE = 2;
 
 struct __align__(16) PairRec {
     double v[4], dv[4];
@@ -42,10 +48,15 @@ struct __align__(16) PairRec {
 };
 
 constexpr int CHUNK = 32;
+constexpr size_t DUMMY_BYTES = 32 * 32;     // one 32-byte sink per lane for masked-off updates
 constexpr size_t WARP_SCRATCH = CHUNK * sizeof(TriRec) + sizeof(RoleViews);
 
-__host__ __device__ inline size_t featurize_warp_bytes(int n_feats) {
-    return (((size_t)4 * n_feats * sizeof(double) + 15) & ~size_t(15)) + ((WARP_SCRATCH + 15) & ~size_t(15));
+// Per-warp shared memory: [accumulators (unless they live in global memory)][sinks][scratch]
+__host__ __device__ inline size_t featurize_acc_bytes(int n_feats, bool global_acc) {
+    return (global_acc ? 0 : (((size_t)4 * n_feats * sizeof(double) + 15) & ~size_t(15))) + DUMMY_BYTES;
+}
+__host__ __device__ inline size_t featurize_warp_bytes(int n_feats, bool global_acc) {
+    return featurize_acc_bytes(n_feats, global_acc) + ((WARP_SCRATCH + 15) & ~size_t(15));
 }
 
 __device__ __forceinline__ void store_record(TriRec *rec, const Triangle &T, const BasisTab &B, int role) {
@@ -58,83 +69,105 @@ __device__ __forceinline__ void store_record(TriRec *rec, const Triangle &T, con
     rec->mn = T.dim_m * T.dim_n;
     rec->nn = T.dim_n;
     rec->base = __ldg(B.trio_goff + T.trio) + (T.il * T.dim_m + T.im) * T.dim_n + T.in;
+    rec->col0 = __ldg(B.trio_col + T.trio);
     rec->dlm = T.il - T.im;
     rec->dmn = T.im - T.in;
-    rec->dln = T.il - T.in;
-    rec->col0 = __ldg(B.trio_col + T.trio);
-    rec->flags = 1 | (role == 0 ? 2 : 0) | (__ldg(B.trio_sym + T.trio) << 8);
+    int sym = __ldg(B.trio_sym + T.trio);
+    sym = sym < 1 ? 1 : (sym > 3 ? 3 : sym);
+    rec->pack = PK_VALID | (role == 0 ? PK_CENTRE : 0) | (sym << 8);
 }
 
-// Phase B: scatter `count` records into the warp's accumulators.
+// acc[col] += add for one bin, or the lane's private sink when the bin is masked off.
+__device__ __forceinline__ void rmw2(double2 *p0, double2 *p1, double e0, const double a0[3],
+                                     double e1, const double a1[3]) {
+    double2 x0 = p0[0], y0 = p0[1], x1 = p1[0], y1 = p1[1];
+    x0.x += e0; x0.y += a0[0]; y0.x += a0[1]; y0.y += a0[2];
+    p0[0] = x0; p0[1] = y0;
+    // p1 may equal p0 only when both are the sink, whose content is never read back
+    x1.x += e1; x1.y += a1[0]; y1.x += a1[1]; y1.y += a1[2];
+    p1[0] = x1; p1[1] = y1;
+}
+
+// Phase B: scatter `count` records into the warp's accumulators.  Lane = (p, q, r-pair) of
+// the triangle's 4x4x4 block of non-zero basis products, two bins per lane.  Bins that fold
+// onto the same compressed column under the trio's permutation symmetry are applied in
+// separate passes; lanes that are masked off in a pass (trimmed / dropped bin, other
+// mirror class) update a private sink so every pass is branch-free.
 __device__ __forceinline__ void scatter_records(const BasisTab &B, const TriRec *recs, int count,
-                                                double *acc, int lane, bool want_e, bool want_f) {
-    const int p = lane >> 3, q = (lane >> 1) & 3, rh = lane & 1;
+                                                double *acc, double *sink, int lane, bool want_e) {
+    const int p = lane >> 3, q = (lane >> 1) & 3, r = (lane & 1) * 2;
+    double2 *const snk = reinterpret_cast<double2 *>(sink);
     for (int t = 0; t < count; ++t) {
         const TriRec *rec = recs + t;
-        const int flags = rec->flags;
-        if (!(flags & 1)) continue;
-        const bool centre = (flags & 2) != 0;
-        const int sym = flags >> 8;
+        const int4 h1 = *reinterpret_cast<const int4 *>(&rec->pack);      // pack, dlm, dmn, -
+        if (!(h1.x & PK_VALID)) continue;
+        const int4 h0 = *reinterpret_cast<const int4 *>(&rec->base);      // base, mn, nn, col0
+        const bool centre = (h1.x & PK_CENTRE) != 0;
+        const int sym = h1.x >> 8;
         const double vl = rec->v[0][p], dvl = rec->dv[0][p];
         const double vm = rec->v[1][q], dvm = rec->dv[1][q];
-        const double c_ = vl * vm;
-        double q1[3], q2[3];
-        if (want_f) {
-            const double a_ = dvl * vm, b_ = vl * dvm;
+        const double2 vn = *reinterpret_cast<const double2 *>(&rec->v[2][r]);
+        const double2 dvn = *reinterpret_cast<const double2 *>(&rec->dv[2][r]);
+        const double a_ = dvl * vm, b_ = vl * dvm, c_ = vl * vm;
+        double add0[3], add1[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                q1[c] = a_ * rec->A[c] + b_ * rec->B[c];
-                q2[c] = c_ * rec->C[c];
-            }
+        for (int c = 0; c < 3; ++c) {
+            const double q1 = a_ * rec->A[c] + b_ * rec->B[c];
+            const double q2 = c_ * rec->C[c];
+            add0[c] = vn.x * q1 + dvn.x * q2;
+            add1[c] = vn.y * q1 + dvn.y * q2;
         }
-        const int bin_pq = rec->base + p * rec->mn + q * rec->nn;
-        const int col0 = rec->col0;
+        double e0 = (centre && want_e) ? c_ * vn.x : 0.0;
+        double e1 = (centre && want_e) ? c_ * vn.y : 0.0;
+        const int bin = h0.x + p * h0.y + q * h0.z + r;
+        const int col_a = __ldg(B.bin_col + bin), col_b = __ldg(B.bin_col + bin + 1);
+        if (!B.unit_weights) {
+            const double w0 = __ldg(B.bin_w + bin), w1 = __ldg(B.bin_w + bin + 1);
+            e0 *= w0; e1 *= w1;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = 2 * rh + rr;
-            const double vn = rec->v[2][r], dvn = rec->dv[2][r];
-            const int bin = bin_pq + r;
-            const int col = __ldg(B.bin_col + bin);
-            int cls = 0, n_cls = 1;
-            if (sym == 2) {
-                cls = (p + rec->dlm) > q;
-                n_cls = 2;
-            } else if (sym >= 3) {      // stable-sort class of (il+p, im+q, in+r)
-                cls = ((p + rec->dlm) > q) | (((q + rec->dmn) > r) << 1) | (((p + rec->dln) > r) << 2);
-                n_cls = 8;
-            }
-            double add[4] = {0.0, 0.0, 0.0, 0.0};
-            if (col >= 0) {
-                const double w = __ldg(B.bin_w + bin);
-                if (centre && want_e) add[0] = w * (c_ * vn);
-                if (want_f) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) add[1 + c] = w * (vn * q1[c] + dvn * q2[c]);
-                }
-            }
-            double *dst = acc + 4 * (size_t)(col0 + (col >= 0 ? col : 0));
-            for (int ph = 0; ph < n_cls; ++ph) {
-                if (col >= 0 && cls == ph) {
-                    if (centre && want_e) dst[0] += add[0];
-                    if (want_f) { dst[1] += add[1]; dst[2] += add[2]; dst[3] += add[3]; }
-                }
+            for (int c = 0; c < 3; ++c) { add0[c] *= w0; add1[c] *= w1; }
+        }
+        double2 *const d0 = col_a >= 0 ? reinterpret_cast<double2 *>(acc + 4 * (h0.w + col_a)) : snk;
+        double2 *const d1 = col_b >= 0 ? reinterpret_cast<double2 *>(acc + 4 * (h0.w + col_b)) : snk;
+        if (sym == 1) {
+            rmw2(d0, d1, e0, add0, e1, add1);
+            __syncwarp();
+        } else if (sym == 2) {
+            // mirror class l > m: (l,m,n) and (m,l,n) share a column, never within one pass
+            const bool upper = (p + h1.y) > q;
+            rmw2(upper ? snk : d0, upper ? snk : d1, e0, add0, e1, add1);
+            __syncwarp();
+            rmw2(upper ? d0 : snk, upper ? d1 : snk, e0, add0, e1, add1);
+            __syncwarp();
+        } else {
+            // stable-sort class of (il+p, im+q, in+r): equal classes never share a column
+            const int x = p + h1.y + h1.z, y = q + h1.z;          // relative to in
+            const int cls0 = (x > y) | ((y > r) << 1) | ((x > r) << 2);
+            const int cls1 = (x > y) | ((y > r + 1) << 1) | ((x > r + 1) << 2);
+            for (int ph = 0; ph < 8; ++ph) {
+                rmw2(cls0 == ph ? d0 : snk, cls1 == ph ? d1 : snk, e0, add0, e1, add1);
                 __syncwarp();
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(256)
+// GLOBAL_ACC: the per-warp accumulators [4 * n_feats] live in a global scratch buffer
+// (L1/L2 resident) instead of shared memory — the path for bases whose rows do not fit
+// (e.g. 18 trio interactions of a ternary system, F ~ 7000).
+template <bool GLOBAL_ACC>
+__global__ void __launch_bounds__(256, 2)
 k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long long ld,
-            double *__restrict__ partials, int want_e_, int want_f_) {
+            double *__restrict__ partials, double *gacc, int want_e_, int want_f_) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int gw = blockIdx.x * nw + warp, n_gw = gridDim.x * nw;
     const int F = B.n_feats;
     const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
-    unsigned char *mine = smem + (size_t)warp * featurize_warp_bytes(F);
-    double *acc = (double *)mine;
-    unsigned char *scratch = mine + (((size_t)4 * F * sizeof(double) + 15) & ~size_t(15));
+    unsigned char *mine = smem + (size_t)warp * featurize_warp_bytes(F, GLOBAL_ACC);
+    double *acc = GLOBAL_ACC ? gacc + (size_t)gw * 4 * F : (double *)mine;
+    double *sink = (double *)(mine + featurize_acc_bytes(F, GLOBAL_ACC) - DUMMY_BYTES) + 4 * lane;
+    unsigned char *scratch = mine + featurize_acc_bytes(F, GLOBAL_ACC);
     TriRec *recs = (TriRec *)scratch;
     PairRec *prec = (PairRec *)scratch;
     RoleViews *views = (RoleViews *)(scratch + CHUNK * sizeof(TriRec));
@@ -210,7 +243,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
             const int n_tri = n3a * (n3a - 1) / 2;
             for (int t0 = 0; t0 < n_tri; t0 += CHUNK) {
                 const int t = t0 + lane;
-                recs[lane].flags = 0;
+                recs[lane].pack = 0;
                 if (t < n_tri) {
                     int qj, qk;
                     unrank_pair(t, qj, qk);
@@ -220,7 +253,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                         store_record(recs + lane, T, B, 0);
                 }
                 __syncwarp();
-                scatter_records(B, recs, min(CHUNK, n_tri - t0), acc, lane, want_e, want_f);
+                scatter_records(B, recs, min(CHUNK, n_tri - t0), acc, sink, lane, want_e);
                 __syncwarp();
             }
             // (ii) `a` as a neighbour of each centre in its list (force rows only)
@@ -229,7 +262,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                     const int total = publish_views(B, f, a, vbase, n3a, lane, views);
                     for (int it0 = 0; it0 < total; it0 += CHUNK) {
                         const int it = it0 + lane;
-                        recs[lane].flags = 0;
+                        recs[lane].pack = 0;
                         if (it < total) {
                             const int v = find_view(views, it);
                             const int ci = views->centre[v], apr = views->a_prime[v];
@@ -244,7 +277,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                             }
                         }
                         __syncwarp();
-                        scatter_records(B, recs, min(CHUNK, total - it0), acc, lane, false, true);
+                        scatter_records(B, recs, min(CHUNK, total - it0), acc, sink, lane, false);
                         __syncwarp();
                     }
                 }
@@ -313,20 +346,19 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     }
 
     // launch shape: as many warps per block as fit, grid sized to the SM count
-    const size_t per_warp = featurize_warp_bytes(F);
     int dev = 0, smem_max = 0;
     UF3B_CUDA(cudaGetDevice(&dev));
     UF3B_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (per_warp > (size_t)smem_max)
-        return fail(UF3B_ERR_CAPACITY, "n_feats = %d needs %zu B of shared memory per warp (limit %d)",
-                    F, per_warp, smem_max);
-    int warps = 8;
+    // accumulators in shared memory while at least two warps fit a block, else in global memory
+    const bool global_acc = 2 * featurize_warp_bytes(F, false) > (size_t)smem_max;
+    const size_t per_warp = featurize_warp_bytes(F, global_acc);
+    int warps = global_acc ? 4 : 8;
     while (warps > 1 && (size_t)warps * per_warp > (size_t)smem_max / 2) warps >>= 1;
-    while ((size_t)warps * per_warp > (size_t)smem_max) warps >>= 1;
     const size_t smem = (size_t)warps * per_warp;
-    UF3B_CUDA(cudaFuncSetAttribute(k_featurize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kernel = global_acc ? k_featurize<true> : k_featurize<false>;
+    UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_featurize, warps * 32, smem));
+    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count() * per_sm;
     const int need = (n + warps - 1) / warps;
@@ -355,8 +387,9 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         UF3B_CUDA(cudaEventCreate(&ev1));
         UF3B_CUDA(cudaEventRecord(ev0, stream));
     }
-    UF3B_LAUNCH(k_featurize, grid, warps * 32, smem, stream, basis->tab, view, d_xf, d_ld,
-                basis->partials.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
+    if (global_acc) UF3B_CUDA(basis->gacc.reserve((size_t)n_gw * 4 * F));
+    UF3B_LAUNCH(kernel, grid, warps * 32, smem, stream, basis->tab, view, d_xf, d_ld,
+                basis->partials.p, basis->gacc.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (x_energy)
         UF3B_LAUNCH(k_energy_row, F, 256, 0, stream, basis->partials.p, n_gw, F, basis->tab.ne,

@@ -152,3 +152,49 @@ void uf3b_gram_destroy(uf3b_gram *gm) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ FP64 peak probe
+// Dependent-chain DFMA loop, 8 independent chains per thread: measures the chip's
+// non-tensor float64 FMA rate, the second roof the 3-body kernels are reported against
+// (MEASURED_PEAKS.json carries no FP64 figure).
+namespace uf3b {
+__global__ void __launch_bounds__(256) k_fp64_probe(double *out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = fma(x[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 123.456) out[0] = s;    // keeps the loop alive
+}
+}  // namespace uf3b
+
+extern "C" int uf3b_probe_fp64_tflops(double *tflops) {
+    if (!tflops) return fail(UF3B_ERR_INVALID, "null argument");
+    double *d_out = nullptr;
+    UF3B_CUDA(cudaMalloc((void **)&d_out, sizeof(double)));
+    const int iters = 1 << 15, blocks = sm_count() * 8;
+    cudaEvent_t e0, e1;
+    UF3B_CUDA(cudaEventCreate(&e0));
+    UF3B_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        UF3B_CUDA(cudaEventRecord(e0, 0));
+        UF3B_LAUNCH(k_fp64_probe, blocks, 256, 0, 0, d_out, iters, 0.999999, 1e-6);
+        UF3B_CUDA(cudaEventRecord(e1, 0));
+        UF3B_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        UF3B_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    const double flop = 2.0 * 8.0 * (double)iters * 256.0 * blocks;
+    *tflops = flop / (best * 1e-3) / 1e12;
+    return UF3B_OK;
+}

@@ -24,6 +24,7 @@ struct Triangle {
     int trio;                   // interaction index  centre*n_pairs + pair(j,k)
     int il, im, in;             // first basis index per leg
     int dim_m, dim_n;           // grid extents of legs m and n
+    int lo[3], cnt[3];          // untrimmed part [lo, lo+cnt) of each leg's 4 basis functions
 };
 
 // role: 0 = `a` is the centre, 1 = `a` is the neighbour with supercell index mj,
@@ -59,6 +60,16 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
     T.trio = t;
     T.dim_m = nkm - 4;
     T.dim_n = nkn - 4;
+    {   // basis indices kept by the trims: [n_lead, n_basis - n_trail)  (angles.py:554)
+        const int first[3] = {T.il, T.im, T.in}, nb[3] = {nkl - 4, nkm - 4, nkn - 4};
+#pragma unroll
+        for (int leg = 0; leg < 3; ++leg) {
+            const int lo = max(0, n_lead - first[leg]), hi = min(4, nb[leg] - n_trail - first[leg]);
+            T.lo[leg] = lo;
+            T.cnt[leg] = max(0, hi - lo);
+        }
+        if (T.cnt[0] == 0 || T.cnt[1] == 0 || T.cnt[2] == 0) return false;
+    }
     // direction cosines (distances.py:354-363): u_ab = (x_b - x_a) / r_ab
     const double il_ = 1.0 / dij, im_ = 1.0 / dik, in_ = 1.0 / djk;
     const double uij[3] = {(pj.x - pc.x) * il_, (pj.y - pc.y) * il_, (pj.z - pc.z) * il_};

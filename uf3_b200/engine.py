@@ -84,6 +84,12 @@ class Engine:
         self.n_atoms = int(n_atoms)
         return self
 
+    def neighbor_count(self, which):
+        """Number of entries in list 2 or 3 of the current configuration."""
+        total = C.c_int64()
+        _native.check(self._lib.uf3b_neighbors_count(self._nlist, which, C.byref(total)))
+        return int(total.value)
+
     def neighbor_list(self, which):
         """CSR (offsets int64 [n+1], supercell indices int64) of list 2 or 3 (parity hook)."""
         total = C.c_int64()
@@ -143,3 +149,8 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self._lib.uf3b_last_kernel_ms())
+
+    def probe_fp64_tflops(self):
+        out = C.c_double()
+        _native.check(self._lib.uf3b_probe_fp64_tflops(C.byref(out)))
+        return float(out.value)
