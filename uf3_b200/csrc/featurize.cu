@@ -17,6 +17,8 @@
 //           block of non-zero basis products and adds them into the compressed column
 //           of each bin.  Bins that fold onto the same column under the trio's
 //           permutation symmetry are applied in separate phases.
+#include <type_traits>
+
 #include "common.cuh"
 #include "geom.cuh"
 #include "spline.cuh"
@@ -24,21 +26,21 @@
 
 namespace uf3b {
 
-// One triangle as seen by the accumulating atom.  Header words first so that both are
-// 16-byte aligned broadcast loads in phase B.
+// One triangle as seen by the accumulating atom.  Four header quads first (broadcast
+// 16-byte loads in phase B, no bit unpacking), then the leg values and role vectors.
 struct __align__(16) TriRec {
-    int base;              // bin index of (il, im, in), trio offset included
-    int mn, nn;            // bin strides of l and m
-    int col0;              // first feature column of the trio
-    int pack;              // PK_* flags | symmetry << 8; 0 = record contributes nothing
-    int dlm, dmn;          // il-im, im-in (mirror classes of symmetric trios)
-    int pad0;
+    int base, mn, nn, col0;        // bin index of (il,im,in) incl. trio offset; bin strides
+                                   // of l and m; first feature column of the trio
+    int flags, sym, dlm, dmn;      // RF_*; symmetry order; il-im, im-in (mirror classes)
+    int n_act, p0, q0, r0;         // untrimmed bins: count and first (p, q, r)
+    int nq, nr, mq, mr;            // extents of q and r and their fixed-point reciprocals
     double v[3][4], dv[3][4];
     double A[3], B[3], C[3];
-    double pad1;
+    double pad;
 };
 static_assert(sizeof(TriRec) % 16 == 0, "TriRec must keep 16-byte alignment in arrays");
-constexpr int PK_VALID = 1, PK_CENTRE = 2;
+constexpr int RF_VALID = 1, RF_CENTRE = 2;
+constexpr unsigned REC_V = 64, REC_DV = 64 + 96, REC_ABC = 64 + 192;   // byte offsets
 
 struct __align__(16) PairRec {
     double v[4], dv[4];
@@ -48,12 +50,11 @@ struct __align__(16) PairRec {
 };
 
 constexpr int CHUNK = 32;
-constexpr size_t DUMMY_BYTES = 32 * 32;     // one 32-byte sink per lane for masked-off updates
 constexpr size_t WARP_SCRATCH = CHUNK * sizeof(TriRec) + sizeof(RoleViews);
 
-// Per-warp shared memory: [accumulators (unless they live in global memory)][sinks][scratch]
+// Per-warp shared memory: [accumulators (unless they live in global memory)][scratch]
 __host__ __device__ inline size_t featurize_acc_bytes(int n_feats, bool global_acc) {
-    return (global_acc ? 0 : (((size_t)4 * n_feats * sizeof(double) + 15) & ~size_t(15))) + DUMMY_BYTES;
+    return global_acc ? 0 : (((size_t)4 * n_feats * sizeof(double) + 15) & ~size_t(15));
 }
 __host__ __device__ inline size_t featurize_warp_bytes(int n_feats, bool global_acc) {
     return featurize_acc_bytes(n_feats, global_acc) + ((WARP_SCRATCH + 15) & ~size_t(15));
@@ -72,81 +73,137 @@ __device__ __forceinline__ void store_record(TriRec *rec, const Triangle &T, con
     rec->col0 = __ldg(B.trio_col + T.trio);
     rec->dlm = T.il - T.im;
     rec->dmn = T.im - T.in;
-    int sym = __ldg(B.trio_sym + T.trio);
-    sym = sym < 1 ? 1 : (sym > 3 ? 3 : sym);
-    rec->pack = PK_VALID | (role == 0 ? PK_CENTRE : 0) | (sym << 8);
+    const int sym = __ldg(B.trio_sym + T.trio);
+    rec->sym = sym < 1 ? 1 : (sym > 3 ? 3 : sym);
+    // floor(b / n) for b < 64, n in 1..4 is (b * magic[n]) >> 8
+    const int nq = T.cnt[1], nr = T.cnt[2];
+    rec->nq = nq;
+    rec->nr = nr;
+    rec->mq = nq == 3 ? 86 : (256 >> (nq >> 1));
+    rec->mr = nr == 3 ? 86 : (256 >> (nr >> 1));
+    rec->n_act = T.cnt[0] * nq * nr;
+    rec->p0 = T.lo[0];
+    rec->q0 = T.lo[1];
+    rec->r0 = T.lo[2];
+    rec->flags = RF_VALID | (role == 0 ? RF_CENTRE : 0);
 }
 
-// acc[col] += add for one bin, or the lane's private sink when the bin is masked off.
-__device__ __forceinline__ void rmw2(double2 *p0, double2 *p1, double e0, const double a0[3],
-                                     double e1, const double a1[3]) {
-    double2 x0 = p0[0], y0 = p0[1], x1 = p1[0], y1 = p1[1];
-    x0.x += e0; x0.y += a0[0]; y0.x += a0[1]; y0.y += a0[2];
-    p0[0] = x0; p0[1] = y0;
-    // p1 may equal p0 only when both are the sink, whose content is never read back
-    x1.x += e1; x1.y += a1[0]; y1.x += a1[1]; y1.y += a1[2];
-    p1[0] = x1; p1[1] = y1;
-}
+// Where a warp's accumulators [column][e, fx, fy, fz] live.
+struct SharedAcc {
+    unsigned base;       // shared-window byte address
+    __device__ __forceinline__ void add(int col, double e, double x, double y, double z) const {
+        const unsigned a = base + 32u * (unsigned)col;
+        double2 u = lds128(a), w = lds128(a + 16);
+        u.x += e; u.y += x; w.x += y; w.y += z;
+        sts128(a, u);
+        sts128(a + 16, w);
+    }
+};
+struct GlobalAcc {
+    double *base;
+    __device__ __forceinline__ void add(int col, double e, double x, double y, double z) const {
+        double2 *d = reinterpret_cast<double2 *>(base + 4 * (size_t)col);
+        double2 u = d[0], w = d[1];
+        u.x += e; u.y += x; w.x += y; w.y += z;
+        d[0] = u;
+        d[1] = w;
+    }
+};
 
-// Phase B: scatter `count` records into the warp's accumulators.  Lane = (p, q, r-pair) of
-// the triangle's 4x4x4 block of non-zero basis products, two bins per lane.  Bins that fold
-// onto the same compressed column under the trio's permutation symmetry are applied in
-// separate passes; lanes that are masked off in a pass (trimmed / dropped bin, other
-// mirror class) update a private sink so every pass is branch-free.
-__device__ __forceinline__ void scatter_records(const BasisTab &B, const TriRec *recs, int count,
-                                                double *acc, double *sink, int lane, bool want_e) {
-    const int p = lane >> 3, q = (lane >> 1) & 3, r = (lane & 1) * 2;
-    double2 *const snk = reinterpret_cast<double2 *>(sink);
+// Phase B: scatter `count` records into the warp's accumulators.  A record whose untrimmed
+// part of the 4x4x4 block of basis products holds at most 32 bins gets one bin per lane
+// (bins enumerated by fixed-point division); otherwise lane = (p, q, r-pair) with two bins
+// per lane.  Bins that fold onto the same compressed column under the trio's permutation
+// symmetry are applied in separate passes, and only lanes with a kept bin of the pass
+// touch the accumulators.
+template <class Acc>
+__device__ __forceinline__ void scatter_records(const BasisTab &B, unsigned recs, int count,
+                                                const Acc acc, int lane, bool want_e) {
     for (int t = 0; t < count; ++t) {
-        const TriRec *rec = recs + t;
-        const int4 h1 = *reinterpret_cast<const int4 *>(&rec->pack);      // pack, dlm, dmn, -
-        if (!(h1.x & PK_VALID)) continue;
-        const int4 h0 = *reinterpret_cast<const int4 *>(&rec->base);      // base, mn, nn, col0
-        const bool centre = (h1.x & PK_CENTRE) != 0;
-        const int sym = h1.x >> 8;
-        const double vl = rec->v[0][p], dvl = rec->dv[0][p];
-        const double vm = rec->v[1][q], dvm = rec->dv[1][q];
-        const double2 vn = *reinterpret_cast<const double2 *>(&rec->v[2][r]);
-        const double2 dvn = *reinterpret_cast<const double2 *>(&rec->dv[2][r]);
-        const double a_ = dvl * vm, b_ = vl * dvm, c_ = vl * vm;
-        double add0[3], add1[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double q1 = a_ * rec->A[c] + b_ * rec->B[c];
-            const double q2 = c_ * rec->C[c];
-            add0[c] = vn.x * q1 + dvn.x * q2;
-            add1[c] = vn.y * q1 + dvn.y * q2;
-        }
-        double e0 = (centre && want_e) ? c_ * vn.x : 0.0;
-        double e1 = (centre && want_e) ? c_ * vn.y : 0.0;
-        const int bin = h0.x + p * h0.y + q * h0.z + r;
-        const int col_a = __ldg(B.bin_col + bin), col_b = __ldg(B.bin_col + bin + 1);
-        if (!B.unit_weights) {
-            const double w0 = __ldg(B.bin_w + bin), w1 = __ldg(B.bin_w + bin + 1);
-            e0 *= w0; e1 *= w1;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { add0[c] *= w0; add1[c] *= w1; }
-        }
-        double2 *const d0 = col_a >= 0 ? reinterpret_cast<double2 *>(acc + 4 * (h0.w + col_a)) : snk;
-        double2 *const d1 = col_b >= 0 ? reinterpret_cast<double2 *>(acc + 4 * (h0.w + col_b)) : snk;
-        if (sym == 1) {
-            rmw2(d0, d1, e0, add0, e1, add1);
-            __syncwarp();
-        } else if (sym == 2) {
-            // mirror class l > m: (l,m,n) and (m,l,n) share a column, never within one pass
-            const bool upper = (p + h1.y) > q;
-            rmw2(upper ? snk : d0, upper ? snk : d1, e0, add0, e1, add1);
-            __syncwarp();
-            rmw2(upper ? d0 : snk, upper ? d1 : snk, e0, add0, e1, add1);
-            __syncwarp();
+        const unsigned rec = recs + (unsigned)t * (unsigned)sizeof(TriRec);
+        const int4 h1 = lds128i(rec + 16);      // flags, sym, dlm, dmn
+        if (!(h1.x & RF_VALID)) continue;
+        const int4 h0 = lds128i(rec);           // base, mn, nn, col0
+        const int4 h2 = lds128i(rec + 32);      // n_act, p0, q0, r0
+        const bool centre = (h1.x & RF_CENTRE) != 0 && want_e;
+        const int sym = h1.y;
+        int p, q, r;
+        const bool wide = h2.x > 32;
+        if (!wide) {
+            const int4 h3 = lds128i(rec + 48);  // nq, nr, mq, mr
+            const int t1 = (lane * h3.w) >> 8;
+            r = h2.w + lane - t1 * h3.y;
+            const int t2 = (t1 * h3.z) >> 8;
+            q = h2.z + t1 - t2 * h3.x;
+            p = h2.y + t2;
         } else {
-            // stable-sort class of (il+p, im+q, in+r): equal classes never share a column
-            const int x = p + h1.y + h1.z, y = q + h1.z;          // relative to in
+            p = lane >> 3;
+            q = (lane >> 1) & 3;
+            r = (lane & 1) * 2;
+        }
+        const int bin = h0.x + p * h0.y + q * h0.z + r;
+        const bool in0 = wide || lane < h2.x;
+        const int col_a = in0 ? __ldg(B.bin_col + bin) : -1;
+        const int col_b = wide ? __ldg(B.bin_col + bin + 1) : -1;
+        const bool live0 = col_a >= 0, live1 = col_b >= 0;
+        double e0 = 0.0, e1 = 0.0, a0[3], a1[3];
+        if (live0 || live1) {
+            const double vl = lds64(rec + REC_V + 8 * p), dvl = lds64(rec + REC_DV + 8 * p);
+            const double vm = lds64(rec + REC_V + 32 + 8 * q), dvm = lds64(rec + REC_DV + 32 + 8 * q);
+            const double ga = dvl * vm, gb = vl * dvm, gc = vl * vm;
+            const double2 ab0 = lds128(rec + REC_ABC), ab1 = lds128(rec + REC_ABC + 16);
+            const double2 ab2 = lds128(rec + REC_ABC + 32), ab3 = lds128(rec + REC_ABC + 48);
+            const double c2 = lds64(rec + REC_ABC + 64);
+            // A = (ab0.x, ab0.y, ab1.x)  B = (ab1.y, ab2.x, ab2.y)  C = (ab3.x, ab3.y, c2)
+            const double q1x = ga * ab0.x + gb * ab1.y, q2x = gc * ab3.x;
+            const double q1y = ga * ab0.y + gb * ab2.x, q2y = gc * ab3.y;
+            const double q1z = ga * ab1.x + gb * ab2.y, q2z = gc * c2;
+            if (!wide) {
+                const double vn = lds64(rec + REC_V + 64 + 8 * r), dvn = lds64(rec + REC_DV + 64 + 8 * r);
+                e0 = centre ? gc * vn : 0.0;
+                a0[0] = vn * q1x + dvn * q2x;
+                a0[1] = vn * q1y + dvn * q2y;
+                a0[2] = vn * q1z + dvn * q2z;
+                a1[0] = a1[1] = a1[2] = 0.0;
+            } else {
+                const double2 vn = lds128(rec + REC_V + 64 + 8 * r), dvn = lds128(rec + REC_DV + 64 + 8 * r);
+                e0 = centre ? gc * vn.x : 0.0;
+                e1 = centre ? gc * vn.y : 0.0;
+                a0[0] = vn.x * q1x + dvn.x * q2x;
+                a0[1] = vn.x * q1y + dvn.x * q2y;
+                a0[2] = vn.x * q1z + dvn.x * q2z;
+                a1[0] = vn.y * q1x + dvn.y * q2x;
+                a1[1] = vn.y * q1y + dvn.y * q2y;
+                a1[2] = vn.y * q1z + dvn.y * q2z;
+            }
+            if (!B.unit_weights) {
+                const double w0 = live0 ? __ldg(B.bin_w + bin) : 0.0;
+                const double w1 = live1 ? __ldg(B.bin_w + bin + 1) : 0.0;
+                e0 *= w0; e1 *= w1;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { a0[c] *= w0; a1[c] *= w1; }
+            }
+        }
+        auto pass = [&](bool mine0, bool mine1) {
+            if (mine0) acc.add(h0.w + col_a, e0, a0[0], a0[1], a0[2]);
+            if (mine1) acc.add(h0.w + col_b, e1, a1[0], a1[1], a1[2]);
+            __syncwarp();
+        };
+        if (sym == 1) {
+            pass(live0, live1);
+        } else if (sym == 2) {
+            // (l,m,n) and (m,l,n) share a column: l <= m first, then l > m
+            const bool upper = (p + h1.z) > q;
+            pass(live0 && !upper, live1 && !upper);
+            if (__any_sync(FULL, (live0 || live1) && upper)) pass(live0 && upper, live1 && upper);
+        } else {
+            // stable-sort class of (il+p, im+q, in+r): bins of one class never share a column
+            const int x = p + h1.z + h1.w, y = q + h1.w;      // l, m relative to `in`
             const int cls0 = (x > y) | ((y > r) << 1) | ((x > r) << 2);
             const int cls1 = (x > y) | ((y > r + 1) << 1) | ((x > r + 1) << 2);
             for (int ph = 0; ph < 8; ++ph) {
-                rmw2(cls0 == ph ? d0 : snk, cls1 == ph ? d1 : snk, e0, add0, e1, add1);
-                __syncwarp();
+                const bool m0 = live0 && cls0 == ph, m1 = live1 && cls1 == ph;
+                if (__any_sync(FULL, m0 || m1)) pass(m0, m1);
             }
         }
     }
@@ -166,9 +223,11 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
     const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
     unsigned char *mine = smem + (size_t)warp * featurize_warp_bytes(F, GLOBAL_ACC);
     double *acc = GLOBAL_ACC ? gacc + (size_t)gw * 4 * F : (double *)mine;
-    double *sink = (double *)(mine + featurize_acc_bytes(F, GLOBAL_ACC) - DUMMY_BYTES) + 4 * lane;
     unsigned char *scratch = mine + featurize_acc_bytes(F, GLOBAL_ACC);
     TriRec *recs = (TriRec *)scratch;
+    const unsigned recs_s = pin(smem_addr(recs));
+    typename std::conditional<GLOBAL_ACC, GlobalAcc, SharedAcc>::type acc_rw;
+    if constexpr (GLOBAL_ACC) acc_rw.base = acc; else acc_rw.base = pin(smem_addr(acc));
     PairRec *prec = (PairRec *)scratch;
     RoleViews *views = (RoleViews *)(scratch + CHUNK * sizeof(TriRec));
 
@@ -243,7 +302,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
             const int n_tri = n3a * (n3a - 1) / 2;
             for (int t0 = 0; t0 < n_tri; t0 += CHUNK) {
                 const int t = t0 + lane;
-                recs[lane].pack = 0;
+                recs[lane].flags = 0;
                 if (t < n_tri) {
                     int qj, qk;
                     unrank_pair(t, qj, qk);
@@ -253,7 +312,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                         store_record(recs + lane, T, B, 0);
                 }
                 __syncwarp();
-                scatter_records(B, recs, min(CHUNK, n_tri - t0), acc, sink, lane, want_e);
+                scatter_records(B, recs_s, min(CHUNK, n_tri - t0), acc_rw, lane, want_e);
                 __syncwarp();
             }
             // (ii) `a` as a neighbour of each centre in its list (force rows only)
@@ -262,7 +321,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                     const int total = publish_views(B, f, a, vbase, n3a, lane, views);
                     for (int it0 = 0; it0 < total; it0 += CHUNK) {
                         const int it = it0 + lane;
-                        recs[lane].pack = 0;
+                        recs[lane].flags = 0;
                         if (it < total) {
                             const int v = find_view(views, it);
                             const int ci = views->centre[v], apr = views->a_prime[v];
@@ -277,7 +336,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                             }
                         }
                         __syncwarp();
-                        scatter_records(B, recs, min(CHUNK, total - it0), acc, sink, lane, false);
+                        scatter_records(B, recs_s, min(CHUNK, total - it0), acc_rw, lane, false);
                         __syncwarp();
                     }
                 }

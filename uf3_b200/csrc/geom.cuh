@@ -41,6 +41,37 @@ __device__ __forceinline__ double dist_rn(const Vec3 &p, const Vec3 &q) {
     return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
 }
 
+// ---- shared-memory access by 32-bit shared-window address.  The featurize kernel keeps
+// its per-warp bases in registers through `pin` (ptxas otherwise rematerialises the
+// generic->shared conversion, ~12 instructions, at every use in the hot loop); the
+// accessors are volatile so that read-modify-write sequences keep their program order.
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ unsigned pin(unsigned v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ double lds64(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds128(unsigned a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int4 lds128i(unsigned a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
