@@ -1,0 +1,185 @@
+"""GPU tests of the reference-facing classes (BasisFeaturizer, UFCalculator, GramAccumulator)
+against fixtures written by the running reference and against the oracle."""
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from uf3_b200 import geometry, least_squares as ls, synthetic
+from uf3_b200.atoms import Atoms
+from uf3_b200.calculator import UFCalculator
+from uf3_b200.process import BasisFeaturizer
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["ref_steel_pbc", "ref_h2o_trimA", "ref_ch4_trimB", "syn_nexe64_pair"])
+def test_evaluate_configuration_rows(name):
+    """Row keys, order and values of process.py:293-367 (reference test:
+    tests/test_representation.py:605-648 for the Fe-C cell)."""
+    case = gu.Case(name)
+    feat = BasisFeaturizer(case.basis())
+    n = len(case.numbers)
+    forces = np.arange(3.0 * n).reshape(3, n)
+    rows = feat.evaluate_configuration(case.atoms(), name="cfg", energy=-1.5, forces=forces)
+    assert len(rows) == 1 + 3 * n
+    keys = list(rows)
+    assert keys[0] == ("cfg", "energy") and keys[1] == ("cfg", "fx_0") and keys[-1] == ("cfg", f"fz_{n - 1}")
+    assert rows[("cfg", "energy")][0] == -1.5
+    assert np.allclose(rows[("cfg", "energy")][1:], case["x_energy"], rtol=1e-5, atol=1e-8)
+    got = np.stack([rows[("cfg", f"{c}_{a}")] for c in ("fx", "fy", "fz") for a in range(n)])
+    assert np.array_equal(got[:, 0], forces.reshape(-1))
+    assert np.allclose(got[:, 1:], case["x_forces"], rtol=1e-5, atol=1e-8)
+    assert len(feat.columns) == got.shape[1]
+    unnamed = feat.evaluate_configuration(case.atoms(), energy=0.0)
+    assert list(unnamed) == ["energy"]
+
+
+def test_partial_featurizers_and_supercell_argument():
+    case = gu.Case("syn_w16_demo")
+    basis = case.basis()
+    feat = BasisFeaturizer(basis)
+    atoms = case.atoms()
+    sup = geometry.get_supercell(atoms, r_cut=basis.r_cut)
+    n = len(atoms)
+    e2, e3 = feat.featurize_energy_2B(atoms, sup), feat.featurize_energy_3B(atoms, sup)
+    assert np.allclose(np.concatenate([[n], e2, e3]), case["x_energy"], rtol=1e-5, atol=1e-8)
+    f2, f3 = feat.featurize_force_2B(atoms, sup), feat.featurize_force_3B(atoms, sup)
+    assert f2.shape == (n, 3, 18) and f3.shape == (n, 3, 54)
+    want = case["x_forces"].reshape(3, n, -1).transpose(1, 0, 2)
+    assert np.allclose(f2, want[:, :, 1:19], rtol=1e-5, atol=1e-8)
+    assert np.allclose(f3, want[:, :, 19:], rtol=1e-5, atol=1e-8)
+    # as in the reference, no supercell argument means no periodic images
+    isolated = Atoms(numbers=case.numbers, positions=case.positions)
+    assert np.allclose(feat.featurize_energy_2B(atoms), feat.featurize_energy_2B(isolated))
+
+
+def test_unknown_element_warns_and_returns_empty():
+    feat = BasisFeaturizer(synthetic.w_basis("demo"))
+    geom = Atoms("WFe", positions=[[0, 0, 0], [2.5, 0, 0]])
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        assert feat.evaluate_configuration(geom, name="bad", energy=0.0) == {}
+    assert any(issubclass(w.category, RuntimeWarning) for w in caught)
+
+
+def test_featurizer_pickles_and_dataframe():
+    import pandas as pd
+    case = gu.Case("syn_w16_demo")
+    feat = BasisFeaturizer(case.basis())
+    feat.evaluate_configuration(case.atoms(), energy=0.0)
+    clone = pickle.loads(pickle.dumps(feat))
+    assert clone._engine is None
+    n = len(case.numbers)
+    df = pd.DataFrame({"geometry": [case.atoms(), case.atoms()], "energy": [1.0, 2.0],
+                       "fx": [np.zeros(n)] * 2, "fy": [np.zeros(n)] * 2, "fz": [np.zeros(n)] * 2},
+                      index=["a", "b"])
+    table = clone.evaluate(df)
+    assert table.shape == (2 * (1 + 3 * n), len(clone.columns))
+    assert table.index[0] == ("a", "energy")
+    assert np.allclose(table.loc[("b", "energy")].to_numpy()[1:], case["x_energy"], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", gu.case_names("calculator"))
+def test_calculator_matches_reference(name):
+    """Known answers of tests/test_calculator.py:12-114 and synthetic frames."""
+    case = gu.Case(name)
+    model = ls.WeightedLinearModel(case.basis())
+    model.coefficients = np.array(case["coefficients"])
+    calc = UFCalculator(model)
+    atoms = case.atoms()
+    atoms.calc = calc
+    assert "W" in calc.solutions or "Ne" in calc.solutions
+    assert set(calc.pair_potentials) == set(case.basis().interactions_map[2])
+    e = atoms.get_potential_energy()
+    f = atoms.get_forces()
+    assert abs(e - float(case["energy"])) <= 1e-6 * max(abs(float(case["energy"])), 1e-12)
+    assert gu.rel_err(f, case["forces"]) <= 1e-6
+    assert calc.results["energy"] == e and calc.results["free_energy"] == e
+
+
+def test_numerical_stress_is_energy_derivative():
+    case = gu.Case("calc_w8_pbc")
+    model = ls.WeightedLinearModel(case.basis())
+    model.coefficients = np.array(case["coefficients"])
+    calc = UFCalculator(model)
+    atoms = case.atoms()
+    stress = calc._get_stress(atoms)
+    assert stress.shape == (6,) and np.all(np.isfinite(stress))
+    d, vol = 1e-5, atoms.get_volume()
+    strained = []
+    for sign in (1, -1):
+        trial = atoms.copy()
+        trial.set_cell(atoms.get_cell() @ np.diag([1 + sign * d, 1, 1]), scale_atoms=True)
+        strained.append(calc.get_potential_energy(trial))
+    assert np.isclose(stress[0], (strained[0] - strained[1]) / (2 * d * vol), rtol=1e-3, atol=1e-6)
+
+
+def test_forces_are_minus_energy_gradient():
+    case = gu.Case("calc_syn_w54_model23")
+    model = ls.WeightedLinearModel(case.basis())
+    model.coefficients = np.array(case["coefficients"])
+    calc = UFCalculator(model)
+    atoms = case.atoms()
+    forces = calc.get_forces(atoms)
+    h = 1e-5
+    for a, c in ((0, 0), (7, 1), (53, 2)):
+        plus, minus = atoms.copy(), atoms.copy()
+        plus.positions[a, c] += h
+        minus.positions[a, c] -= h
+        num = -(calc.get_potential_energy(plus) - calc.get_potential_energy(minus)) / (2 * h)
+        assert np.isclose(forces[a, c], num, rtol=1e-5, atol=1e-6)
+    assert np.abs(forces.sum(axis=0)).max() < 1e-8      # Newton's third law
+
+
+def test_device_gram_equals_host_gram_and_fit():
+    import torch
+    case = gu.Case("syn_w128_demo")
+    basis = case.basis()
+    feat = BasisFeaturizer(basis)
+    n, F = len(case.numbers), basis.n_feats
+    eng = feat.engine
+    eng.build_neighbors(case.positions, case.numbers, images=geometry.image_table(case.cell, case.pbc, basis.r_cut))
+    rows = torch.empty((3 * n, F), dtype=torch.float64, device="cuda")
+    xe = np.empty(F)
+    eng._featurize_mixed(xe, rows.data_ptr(), F)
+    rng = np.random.default_rng(1)
+    y_f = rng.normal(size=3 * n)
+    dev = ls.GramAccumulator(F)
+    dev.add_energy_row(xe, -3.0, n)
+    dev.add_force_rows_device(rows.data_ptr(), y_f, 3 * n, F)
+    host = ls.GramStats(F)
+    host.add_energy_row(case["x_energy"], -3.0, n)
+    host.add_force_rows(case["x_forces"], y_f)
+    a, b = dev.export(), host.export()
+    scale = np.abs(b["gram_f"]).max()
+    assert np.abs(a["gram_f"] - b["gram_f"]).max() <= 1e-9 * scale
+    assert np.allclose(a["gram_f"], a["gram_f"].T)
+    assert np.abs(a["ord_f"] - b["ord_f"]).max() <= 1e-9 * np.abs(b["ord_f"]).max()
+    assert np.allclose(a["gram_e"], b["gram_e"], rtol=1e-9, atol=1e-12)
+    kw = dict(ridge_1b=1e-4, ridge_2b=1e-4, ridge_3b=1e-4, curvature_2b=1e-4)
+    m_dev, m_host = ls.WeightedLinearModel(basis, **kw), ls.WeightedLinearModel(basis, **kw)
+    m_dev.fit_from_accumulator(dev)
+    m_host.fit_from_accumulator(host)
+    assert np.allclose(m_dev.coefficients, m_host.coefficients, rtol=1e-6, atol=1e-7)
+    dev.close()
+
+
+def test_accumulate_frames_sharded():
+    """uf3_b200.distributed.accumulate_frames on one GPU: the two shards add up to the whole."""
+    from uf3_b200 import distributed
+    cases = [gu.Case(n) for n in ("syn_w16_demo", "syn_w54_demo", "syn_w36_slab")]
+    feat = BasisFeaturizer(cases[0].basis())
+    rng = np.random.default_rng(2)
+    frames = [(c.atoms(), float(rng.normal()), rng.normal(size=(3, len(c.numbers)))) for c in cases]
+    whole = distributed.accumulate_frames(feat, frames).to_vector()
+    parts = sum(distributed.accumulate_frames(feat, frames, rank=r, world_size=2).to_vector() for r in range(2))
+    assert np.allclose(parts, whole, rtol=1e-10, atol=1e-10)
+    host = ls.GramStats(feat.engine.n_feats)
+    for c, (_, e, f) in zip(cases, frames):
+        host.add_energy_row(c["x_energy"], e, len(c.numbers))
+        host.add_force_rows(c["x_forces"], f.reshape(-1))
+    ref = host.to_vector()
+    assert np.abs(whole - ref).max() <= 1e-8 * np.abs(ref).max()

@@ -1,0 +1,68 @@
+"""Normal-equation bookkeeping (CPU): frozen columns, E/F weighting, and the flattened
+Gram statistics that multi-GPU fits all-reduce.  The reference behaviour restated here is
+regression/least_squares.py:248-353, :666-771, :817-890, :1147-1168."""
+import numpy as np
+
+import golden_util as gu
+from uf3_b200 import least_squares as ls
+
+
+def _rows(name="syn_w54_demo", seed=0):
+    case = gu.Case(name)
+    rng = np.random.default_rng(seed)
+    coeff = rng.normal(size=case["x_energy"].shape[0])
+    x_e = np.stack([case["x_energy"], case["x_energy"] * 1.01 + 0.1])
+    n_atoms = len(case.numbers)
+    x_f = case["x_forces"]
+    y_e = x_e @ coeff + rng.normal(0, 1e-3, len(x_e))
+    y_f = x_f @ coeff + rng.normal(0, 1e-3, len(x_f))
+    return case, n_atoms, x_e, y_e, x_f, y_f
+
+
+def test_freeze_and_revert_columns():
+    x = np.arange(20.0).reshape(4, 5)
+    y = np.arange(4.0)
+    mask = ls.get_freezing_mask(5, np.array([1, 3]))
+    assert mask.tolist() == [0, 2, 4]
+    xm, ym = ls.freeze_columns(x, y, mask, np.array([2.0, -1.0]), np.array([1, 3]))
+    assert xm.shape == (4, 3) and np.allclose(ym, y - 2 * x[:, 1] + x[:, 3])
+    full = ls.revert_frozen_coefficients(np.array([1.0, 2.0, 3.0]), 5, mask, np.array([9.0, 8.0]), np.array([1, 3]))
+    assert full.tolist() == [1, 9, 2, 8, 3]
+
+
+def test_e_f_weights():
+    assert ls.calc_E_F_weights(4, 9, 0.0, 2.0) == (1.0, 1 / 3)
+    w_e, w_f = ls.calc_E_F_weights(4, 9, 0.5, 2.0)
+    assert np.isclose(w_e, 1 / 2 / 0.5) and np.isclose(w_f, 1 / 3 / 2.0)
+
+
+def test_fit_from_statistics_equals_fit_from_rows():
+    case, n_atoms, x_e, y_e, x_f, y_f = _rows()
+    basis = case.basis()
+    direct = ls.WeightedLinearModel(basis, ridge_1b=1e-4, ridge_2b=1e-4, ridge_3b=1e-4, curvature_2b=1e-4)
+    # dataframe_to_tuples divides energy rows and targets by the atom count (:697-700)
+    direct.fit(x_e / n_atoms, y_e / n_atoms, x_f, y_f, weight=0.7)
+    stats = ls.GramStats(basis.n_feats)
+    for row, target in zip(x_e, y_e):
+        stats.add_energy_row(row, target, n_atoms)
+    half = len(x_f) // 2
+    stats.add_force_rows(x_f[:half], y_f[:half])
+    stats.add_force_rows(x_f[half:], y_f[half:])
+    via_stats = ls.WeightedLinearModel(basis, ridge_1b=1e-4, ridge_2b=1e-4, ridge_3b=1e-4, curvature_2b=1e-4)
+    via_stats.fit_from_accumulator(stats, weight=0.7)
+    assert np.allclose(via_stats.coefficients, direct.coefficients, rtol=1e-6, atol=1e-7)
+    assert np.all(via_stats.coefficients[basis.col_idx] == 0)
+    # flatten / restore is loss-free
+    clone = ls.GramStats(basis.n_feats)
+    clone.from_vector(stats.to_vector())
+    assert np.array_equal(clone.to_vector(), stats.to_vector())
+    assert len(stats.to_vector()) == 2 * basis.n_feats ** 2 + 2 * basis.n_feats + 6
+
+
+def test_energy_only_fit():
+    case, n_atoms, x_e, y_e, _, _ = _rows()
+    basis = case.basis()
+    model = ls.WeightedLinearModel(basis, ridge_2b=1e-6, ridge_3b=1e-6, ridge_1b=1e-6)
+    model.fit(x_e / n_atoms, y_e / n_atoms)
+    assert model.coefficients.shape == (basis.n_feats,)
+    assert np.isfinite(model.coefficients).all()

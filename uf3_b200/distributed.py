@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing: frames shard over ranks, one all-reduce of the normal equations.
+
+The reference parallelises featurization over frames with a process pool and merges
+pandas DataFrames (`process.py:196-254`, `util/parallel.py:167-251`).  Frames are
+independent, so here frame f goes to rank f mod world_size, every rank accumulates its
+own Gram statistics (`least_squares.GramStats`, 2 F^2 + 2 F + 6 doubles) and a single
+`all_reduce(SUM)` over NCCL (GPU ranks) or gloo (CPU tests) replaces `gather_and_merge`.
+There is no collective on the featurization path itself.
+"""
+import numpy as np
+
+
+def shard(items, rank, world_size):
+    """Round-robin shard of a sequence: rank r gets items r, r + world, ..."""
+    return list(items)[rank::world_size]
+
+
+def all_reduce_stats(stats, group=None):
+    """Sum `GramStats` over all ranks in place (no-op without an initialised group)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats
+    vec = torch.from_numpy(stats.to_vector())
+    if dist.get_backend(group) == "nccl":
+        vec = vec.cuda()
+    dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    stats.from_vector(vec.cpu().numpy())
+    return stats
+
+
+def accumulate_frames(featurizer, frames, stats=None, rank=0, world_size=1):
+    """Featurize this rank's share of `frames` on its GPU and fold the rows into Gram
+    statistics without moving force rows off the device.
+
+    frames: sequence of (geom, energy, forces) with forces shaped (3, N) or None."""
+    import torch
+    from uf3_b200.atoms import frame_arrays
+    from uf3_b200 import geometry
+    from uf3_b200.least_squares import GramAccumulator
+
+    eng = featurizer.engine
+    F = eng.n_feats
+    if stats is None:
+        stats = GramAccumulator(F)
+    stream = torch.cuda.current_stream().cuda_stream
+    rows = None
+    for geom, energy, forces in shard(frames, rank, world_size):
+        positions, numbers, cell, pbc = frame_arrays(geom)
+        images = geometry.image_table(cell, pbc, featurizer.r_cut) if np.any(pbc) else None
+        eng.build_neighbors(positions, numbers, images=images, stream=stream)
+        n = len(positions)
+        want_f = forces is not None and featurizer.fit_forces and n > 0
+        if want_f and (rows is None or rows.shape[0] < 3 * n):
+            rows = torch.empty((3 * n, F), dtype=torch.float64, device="cuda")
+        xe = np.empty(F)
+        eng._featurize_mixed(xe, rows.data_ptr() if want_f else None, F, stream)
+        if energy is not None:
+            stats.add_energy_row(xe, energy, n)
+        if want_f:
+            stats.add_force_rows_device(rows.data_ptr(), np.asarray(forces, dtype=np.float64).reshape(-1),
+                                        3 * n, F, stream)
+    return stats

@@ -126,6 +126,12 @@ class Engine:
             self._basis, self._nlist, C.c_void_p(energy_ptr) if energy_ptr else None,
             C.c_void_p(forces_ptr) if forces_ptr else None, int(ld), stream))
 
+    def _featurize_mixed(self, out_energy, forces_ptr, ld, stream=None):
+        """Energy row into a HOST array, force rows (if any) left at a DEVICE address."""
+        _native.check(self._lib.uf3b_featurize(
+            self._basis, self._nlist, _ptr(out_energy),
+            C.c_void_p(forces_ptr) if forces_ptr else None, int(ld), stream))
+
     def energy_forces(self, energy=True, forces=True, stream=None):
         n = self.n_atoms
         e = np.zeros(1) if energy else None

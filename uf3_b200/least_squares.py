@@ -1,0 +1,387 @@
+"""`WeightedLinearModel` — model container and normal-equation fit.
+
+API mirror of `/root/reference/uf3/regression/least_squares.py` for the parts the hot
+path touches: loading / saving fitted models (`from_json`, `load`, `as_dict`, :185-216,
+:528-621), the frozen-column bookkeeping (:817-890) and the weighted Gram solve
+(`fit`, `fit_with_gram`, `combine_weighted_gram`, :248-353).  The Gram matrices can come
+from host arrays (as in the reference) or straight from the device accumulator
+(`GramAccumulator`, fed by `uf3b_gram_accumulate` on rows that never leave the GPU) —
+the regularised solve itself is a p x p problem (p <= ~900) and stays on the host
+LAPACK, exactly as the reference does it (`np.linalg.solve`, :763-771).
+"""
+import ctypes as C
+import warnings
+from typing import Collection, Dict
+
+import numpy as np
+
+from uf3_b200 import bspline, composition, json_io
+
+
+# ---------------------------------------------------------------- helpers
+def get_freezing_mask(n_feats, col_idx):
+    return np.setdiff1d(np.arange(n_feats), col_idx)
+
+
+def freeze_columns(x, y, mask, frozen_c, col_idx):
+    """Drop the frozen columns of x and move their fixed contribution into y."""
+    x = np.asarray(x)
+    y = np.subtract(y, np.dot(x[:, col_idx], frozen_c))
+    return x[:, mask], y
+
+
+def freeze_regularizer(regularizer, mask):
+    return regularizer[:, mask]
+
+
+def revert_frozen_coefficients(solution, n_coeff, mask, frozen_c, frozen_idx):
+    full = np.zeros(n_coeff, dtype=np.asarray(solution).dtype)
+    full[np.asarray(mask, dtype=int)] = solution
+    if len(frozen_idx):
+        full[np.asarray(frozen_idx, dtype=int)] = frozen_c
+    return full
+
+
+def moore_penrose_components(x, y):
+    x = np.asarray(x)
+    return np.dot(x.T, x), np.dot(x.T, y)
+
+
+def batched_moore_penrose(x, y, batch_size=2500):
+    n_samples, n_features = np.shape(x)
+    n_batches = int(n_samples / batch_size)
+    if n_batches <= 1:
+        return moore_penrose_components(x, y)
+    gram = np.zeros((n_features, n_features))
+    ordinate = np.zeros(n_features)
+    for batch in np.array_split(np.arange(len(y)), n_batches):
+        g, o = moore_penrose_components(x[batch], y[batch])
+        gram += g
+        ordinate += o
+    return gram, ordinate
+
+
+def lu_factorization(a, b):
+    return np.linalg.solve(a, b)
+
+
+def calc_E_F_weights(n_e, n_f, std_e, std_f):
+    """Weights of the energy / force blocks (least_squares.py:1147-1168)."""
+    if std_e == 0:
+        return 1.0, 1 / np.sqrt(n_f)
+    return 1 / np.sqrt(n_e) / std_e, 1 / np.sqrt(n_f) / std_f
+
+
+def arrange_coefficients(coefficients, bspline_config):
+    """Flat coefficient vector -> {element: float, pair: vector, trio: vector}."""
+    pieces = np.array_split(coefficients, np.cumsum(bspline_config.partition_sizes)[:-1])
+    elements = bspline_config.element_list
+    solutions = {el: piece[0] for el, piece in zip(elements, pieces[:len(elements)])}
+    rest = pieces[len(elements):]
+    j = 0
+    for degree in range(2, bspline_config.degree + 1):
+        for interaction in bspline_config.interactions_map[degree]:
+            solutions[interaction] = rest[j]
+            j += 1
+    return solutions
+
+
+def rmse_metric(predicted, actual):
+    return float(np.sqrt(np.mean(np.subtract(predicted, actual) ** 2)))
+
+
+def mae_metric(predicted, actual):
+    return float(np.mean(np.abs(np.subtract(predicted, actual))))
+
+
+# ---------------------------------------------------------------- model
+class WeightedLinearModel:
+    def __init__(self, bspline_config, regularizer=None, data_coverage=None, **params):
+        self.coefficients = None
+        self.regularizer = regularizer
+        self.bspline_config = bspline_config
+        n_basis = int(np.sum(bspline_config.get_feature_partition_sizes()))
+        if data_coverage is not None:
+            if len(data_coverage) != n_basis:
+                raise ValueError(f"Incorrect data_coverage shape: {len(data_coverage)} != {n_basis}")
+            self.data_coverage = np.asarray(data_coverage)
+        else:
+            self.data_coverage = np.zeros(n_basis, dtype=bool)
+        if self.regularizer is None:
+            self.set_params(**params)
+
+    def set_params(self, **params):
+        if "bspline_config" in params:
+            self.bspline_config = params["bspline_config"]
+        if "regularizer" in params:
+            self.regularizer = params["regularizer"]
+        elif self.regularizer is None:
+            strengths = {k: v for k, v in params.items()
+                         if isinstance(v, (int, float, np.floating))}
+            self.regularizer = self.bspline_config.get_regularization_matrix(**strengths)
+
+    # ------------------------------------------------------------ I/O
+    @staticmethod
+    def from_config(config):
+        return WeightedLinearModel.from_dict(config)
+
+    @staticmethod
+    def from_dict(config):
+        basis = bspline.BSplineBasis.from_dict(config)
+        model = WeightedLinearModel(basis, regularizer=config.get("regularizer"),
+                                    data_coverage=config.get("data_coverage"))
+        model.load(solution=config)
+        return model
+
+    @staticmethod
+    def from_json(filename):
+        return WeightedLinearModel.from_dict(json_io.load_interaction_map(filename))
+
+    def as_dict(self):
+        solution = arrange_coefficients(self.coefficients, self.bspline_config)
+        for trio in self.bspline_config.interactions_map.get(3, []):
+            solution[trio] = self.bspline_config.decompress_3B(solution[trio], trio)
+        return dict(coefficients=solution, knots=self.bspline_config.knots_map,
+                    data_coverage=self.data_coverage, **self.bspline_config.as_dict())
+
+    dump = as_dict
+
+    def to_json(self, filename):
+        json_io.dump_interaction_map(self.as_dict(), filename=filename, write=True)
+
+    def load(self, solution: Dict = None, filename: str = None):
+        """Flatten {interaction: coefficients} into `self.coefficients`; 3-body entries may
+        be full (L, M, N) grids, which are folded with `compress_3B(fitting=False)`."""
+        if filename is not None:
+            if solution is not None:
+                warnings.warn("Provided solutions ignored; loading file.")
+            solution = json_io.load_interaction_map(filename)
+        elif solution is None:
+            raise ValueError("Neither solution nor filename were provided.")
+        if "coefficients" in solution:
+            solution = solution["coefficients"]
+        elif "solution" in solution:
+            warnings.warn("'solution' should be renamed to 'coefficients'")
+            solution = solution["solution"]
+        solution = dict(solution)
+        for key in list(solution):
+            if isinstance(key, tuple):
+                solution.setdefault(composition.sort_interaction_symbols(key), solution[key])
+        basis = self.bspline_config
+        sizes = basis.get_interaction_partitions()[0]
+        flat = [[solution[el]] for el in basis.element_list]
+        for pair in basis.interactions_map[2]:
+            if pair not in solution:
+                warnings.warn(f"{pair} not provided.")
+                solution[pair] = np.zeros(sizes[pair])
+            if len(solution[pair]) != sizes[pair]:
+                raise ValueError(f"Incorrect shape: {pair}, {len(solution[pair])} != {sizes[pair]}")
+            flat.append(np.asarray(solution[pair], dtype=float))
+        for trio in (basis.interactions_map.get(3, []) if basis.degree > 2 else []):
+            if trio not in solution:
+                raise ValueError(f"{trio} not provided.")
+            component = np.array(solution[trio])
+            if component.ndim > 1:
+                component = basis.compress_3B(component, trio, fitting=False)
+            if len(component) != sizes[trio]:
+                raise ValueError(f"Incorrect shape: {trio}, {len(component)} != {sizes[trio]}")
+            flat.append(np.asarray(component, dtype=float))
+        flat = np.concatenate(flat)
+        if len(flat) != int(np.sum(basis.partition_sizes)):
+            raise ValueError(f"Incorrect coefficients: {len(flat)} provided, "
+                             f"{int(np.sum(basis.partition_sizes))} expected.")
+        self.coefficients = flat
+
+    # ------------------------------------------------------------ bookkeeping
+    @property
+    def n_feats(self):
+        return self.bspline_config.n_feats
+
+    @property
+    def frozen_c(self):
+        return self.bspline_config.frozen_c
+
+    @property
+    def col_idx(self):
+        return self.bspline_config.col_idx
+
+    @property
+    def mask(self):
+        return get_freezing_mask(self.n_feats, self.col_idx)
+
+    def __repr__(self):
+        return "\n".join(["WeightedLinearModel:", f"    Fit: {self.coefficients is not None}",
+                          repr(self.bspline_config)])
+
+    # ------------------------------------------------------------ fit
+    def fit_with_gram(self, gram, ordinate):
+        """Solve (G + R^T R) c = b on the unfrozen columns (least_squares.py:248-272)."""
+        coverage = revert_frozen_coefficients(np.sum(gram, axis=0) != 0, self.n_feats, self.mask,
+                                              self.frozen_c, self.col_idx)
+        self.data_coverage = np.logical_or(self.data_coverage, coverage)
+        reg = freeze_regularizer(self.regularizer, self.mask)
+        solution = lu_factorization(gram + np.dot(reg.T, reg), ordinate)
+        self.coefficients = revert_frozen_coefficients(solution, self.n_feats, self.mask,
+                                                       self.frozen_c, self.col_idx)
+
+    def combine_weighted_gram(self, gram_e, gram_f, ord_e, ord_f, energy_weight, force_weight, weight):
+        gram = weight * energy_weight ** 2 * gram_e + (1 - weight) * force_weight ** 2 * gram_f
+        ordinate = weight * energy_weight ** 2 * ord_e + (1 - weight) * force_weight ** 2 * ord_f
+        return gram, ordinate
+
+    def fit(self, x_e, y_e, x_f=None, y_f=None, weight=0.5, batch_size=2500):
+        x_e, y_e = freeze_columns(x_e, y_e, self.mask, self.frozen_c, self.col_idx)
+        gram, ordinate = batched_moore_penrose(x_e, y_e, batch_size=batch_size)
+        if x_f is not None:
+            w_e, w_f = calc_E_F_weights(len(y_e), len(y_f), np.std(y_e), np.std(y_f))
+            x_f, y_f = freeze_columns(x_f, y_f, self.mask, self.frozen_c, self.col_idx)
+            gram_f, ord_f = batched_moore_penrose(x_f, y_f, batch_size=batch_size)
+            gram, ordinate = self.combine_weighted_gram(gram, gram_f, ordinate, ord_f, w_e, w_f, weight)
+        self.fit_with_gram(gram, ordinate)
+
+    def fit_from_accumulator(self, acc, weight=0.5):
+        """Fit from full-width Gram statistics gathered on the device (`GramAccumulator`,
+        all-reduced over ranks by `uf3_b200.distributed`).  Equivalent to `fit` on the
+        stacked rows: frozen columns are eliminated from the Gram blocks instead of from X."""
+        stats = acc.export()
+        mask, col, c0 = self.mask, np.asarray(self.col_idx, dtype=int), np.asarray(self.frozen_c)
+
+        def reduce(gram, ordinate):
+            # (X_m)^T X_m and (X_m)^T (y - X_c c0)
+            return gram[np.ix_(mask, mask)], ordinate[mask] - gram[np.ix_(mask, col)] @ c0
+
+        gram, ordinate = reduce(stats["gram_e"], stats["ord_e"])
+        if stats["n_f"] > 0:
+            gram_f, ord_f = reduce(stats["gram_f"], stats["ord_f"])
+            # the reference takes np.std AFTER folding the frozen contribution into y;
+            # frozen coefficients are zero (bspline.py:577-635), so y is unchanged
+            w_e, w_f = calc_E_F_weights(stats["n_e"], stats["n_f"], stats["std_e"], stats["std_f"])
+            gram, ordinate = self.combine_weighted_gram(gram, gram_f, ordinate, ord_f, w_e, w_f, weight)
+        self.fit_with_gram(gram, ordinate)
+
+    def predict(self, x):
+        return np.dot(x, self.coefficients)
+
+    def score(self, x, y):
+        return rmse_metric(self.predict(x), y)
+
+
+# ---------------------------------------------------------------- Gram statistics
+class GramStats:
+    """Normal-equation statistics of a stream of feature rows (host side).
+
+    Holds G_e, b_e (energy rows), G_f, b_f (force rows) at FULL feature width and the
+    running count / sum / sum of squares of the targets that replace the reference's
+    `VarianceRecorder` (least_squares.py:19-53).  Energy rows and their targets are
+    divided by the atom count on entry, as `dataframe_to_tuples` does (:697-700).
+    `to_vector` / `from_vector` flatten everything into one float64 array of
+    2 F^2 + 2 F + 6 values, so a fit sharded over many ranks costs ONE all-reduce."""
+
+    def __init__(self, n_feats):
+        n = self.n_feats = int(n_feats)
+        self.gram_e, self.gram_f = np.zeros((n, n)), np.zeros((n, n))
+        self.ord_e, self.ord_f = np.zeros(n), np.zeros(n)
+        self.moments = np.zeros(6)      # n_e, sum_e, sumsq_e, n_f, sum_f, sumsq_f
+
+    def _count(self, y, is_force):
+        k = 3 if is_force else 0
+        self.moments[k:k + 3] += (len(y), float(np.sum(y)), float(np.dot(y, y)))
+
+    def add_energy_row(self, x_energy, energy, n_atoms):
+        x = np.asarray(x_energy, dtype=np.float64) / n_atoms
+        y = float(energy) / n_atoms
+        self.gram_e += np.outer(x, x)
+        self.ord_e += x * y
+        self._count(np.array([y]), False)
+
+    def add_force_rows(self, x_forces, y_forces):
+        x = np.asarray(x_forces, dtype=np.float64)
+        y = np.asarray(y_forces, dtype=np.float64).reshape(-1)
+        self.gram_f += x.T @ x
+        self.ord_f += x.T @ y
+        self._count(y, True)
+
+    def _blocks(self):
+        return self.gram_e, self.gram_f, self.ord_e, self.ord_f
+
+    def to_vector(self):
+        gram_e, gram_f, ord_e, ord_f = self._blocks()
+        return np.concatenate([gram_e.ravel(), gram_f.ravel(), ord_e, ord_f, self.moments])
+
+    def from_vector(self, vec):
+        """Replace the state by a flattened one (e.g. the all-reduced sum over ranks)."""
+        n, g = self.n_feats, self.n_feats ** 2
+        vec = np.asarray(vec, dtype=np.float64)
+        if vec.shape != (2 * g + 2 * n + 6,):
+            raise ValueError("flattened Gram statistics have the wrong length")
+        self._reset_device()
+        self.gram_e, self.gram_f = vec[:g].reshape(n, n).copy(), vec[g:2 * g].reshape(n, n).copy()
+        self.ord_e, self.ord_f = vec[2 * g:2 * g + n].copy(), vec[2 * g + n:2 * g + 2 * n].copy()
+        self.moments = vec[2 * g + 2 * n:].copy()
+
+    def _reset_device(self):
+        pass
+
+    def export(self):
+        gram_e, gram_f, ord_e, ord_f = self._blocks()
+        n_e, s_e, ss_e, n_f, s_f, ss_f = self.moments
+
+        def std(count, total, squares):
+            if count < 1:
+                return 0.0
+            return float(np.sqrt(max(squares / count - (total / count) ** 2, 0.0)))
+
+        return dict(gram_e=gram_e, gram_f=gram_f, ord_e=ord_e, ord_f=ord_f,
+                    n_e=int(round(n_e)), n_f=int(round(n_f)),
+                    std_e=std(n_e, s_e, ss_e), std_f=std(n_f, s_f, ss_f))
+
+
+class GramAccumulator(GramStats):
+    """`GramStats` whose force block is accumulated ON THE DEVICE (C ABI `uf3b_gram_*`)
+    from rows that the featurize kernel left in HBM: a frame's 3N x F force rows (110 MB
+    for 10k atoms with the 456-column basis) are never copied to the host.  The energy
+    row is one vector per frame and is added on the host."""
+
+    def __init__(self, n_feats):
+        super().__init__(n_feats)
+        from uf3_b200 import _native
+        self._native = _native
+        self._lib = _native.lib()
+        self._handle = C.c_void_p()
+        _native.check(self._lib.uf3b_gram_create(self.n_feats, C.byref(self._handle)))
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.uf3b_gram_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_force_rows_device(self, x_ptr, y_forces, rows, ld, stream=None):
+        """x_ptr: device address of `rows` x n_feats float64 rows (row stride ld doubles);
+        y_forces: host targets in the same row order (fx_0.., fy_0.., fz_0..)."""
+        y = np.ascontiguousarray(y_forces, dtype=np.float64).reshape(-1)
+        if len(y) != rows:
+            raise ValueError("one target per force row is required")
+        self._native.check(self._lib.uf3b_gram_accumulate(
+            self._handle, C.c_void_p(x_ptr), C.c_void_p(y.ctypes.data), int(rows), int(ld), 1, stream))
+        self._count(y, True)
+
+    def _device_force_block(self):
+        n = self.n_feats
+        gram, ordinate = np.zeros((n, n)), np.zeros(n)
+        self._native.check(self._lib.uf3b_gram_export(
+            self._handle, 1, C.c_void_p(gram.ctypes.data), C.c_void_p(ordinate.ctypes.data)))
+        return gram, ordinate
+
+    def _blocks(self):
+        gram_d, ord_d = self._device_force_block()
+        return self.gram_e, self.gram_f + gram_d, self.ord_e, self.ord_f + ord_d
+
+    def _reset_device(self):
+        self.close()
+        self._native.check(self._lib.uf3b_gram_create(self.n_feats, C.byref(self._handle)))
