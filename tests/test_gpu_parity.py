@@ -168,3 +168,80 @@ def test_unknown_element_is_an_error():
     with pytest.raises(_native.ElementError):
         eng.build_neighbors(np.zeros((2, 3)), np.array([74, 26]))
     eng.close()
+
+
+# ----------------------------------------------------------------- BASELINE.json full sizes
+def test_headline_frame_10k_atoms_matches_oracle():
+    """configs[1]: bulk W, 10 000 atoms, 2+3-body rows.  The reference cannot hold this size;
+    the oracle (pinned on the goldens above) does it in a few seconds."""
+    from uf3_b200 import synthetic
+    basis = synthetic.w_basis("demo")
+    pos, numbers, cell, pbc = synthetic.bcc_w((10, 20, 25), seed=0)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    packed = orc.PackedBasis(basis)
+    eng = Engine(basis)
+    eng.build_neighbors(pos, numbers, images=images)
+    for which in (2, 3):
+        off, idx = eng.neighbor_list(which)
+        want_off, want_idx = orc.neighbor_lists(packed, pos, numbers, images[1], which)
+        assert np.array_equal(off, want_off) and np.array_equal(idx, want_idx)
+    xe, xf = eng.featurize()
+    want_e, want_f = orc.featurize(packed, pos, numbers, images[1])
+    assert gu.rel_err(xe, want_e) <= REL and gu.rel_err(xf, want_f) <= REL
+    # size-independent properties: translation invariance (rows of each component sum to 0
+    # over atoms) and the energy row's pair block counts every ordered pair once per column set
+    n = len(pos)
+    assert np.abs(xf.reshape(3, n, -1).sum(axis=1)).max() <= 1e-9 * np.abs(xf).max() * n
+    assert xe[0] == n
+    # run-to-run bit reproducibility (no atomics on the row path)
+    xe2, xf2 = eng.featurize()
+    assert np.array_equal(xe, xe2) and np.array_equal(xf, xf2)
+    eng.close()
+
+
+def test_nexe_50k_inference_matches_oracle():
+    """configs[2]: Ne/Xe binary, 50 000 atoms, 2-body energy + forces."""
+    from uf3_b200 import synthetic
+    basis = synthetic.nexe_basis()
+    pos, numbers, cell, pbc = synthetic.nexe((25, 25, 10), seed=0)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    coeff = np.array(gu.Case("calc_syn_nexe64_pair")["coefficients"])
+    packed = orc.PackedBasis(basis)
+    want_e, want_f = orc.energy_forces(basis, packed, coeff, pos, numbers, images[1])
+    eng = Engine(basis)
+    eng.set_coefficients(coeff)
+    eng.build_neighbors(pos, numbers, images=images)
+    e, f = eng.energy_forces()
+    assert abs(e - want_e) <= REL * abs(want_e)
+    assert gu.rel_err(f, want_f) <= REL
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * np.abs(f).max() * len(pos)
+    eng.close()
+
+
+def test_w_20k_energy_forces_match_oracle_and_100k_properties():
+    """configs[4]: W at MD sizes with the shipped 2+3-body model; oracle at 20 000 atoms,
+    momentum conservation and image-shift invariance at 100 000."""
+    from uf3_b200 import synthetic
+    case = gu.Case("calc_syn_w54_model23")
+    basis = case.basis()
+    coeff = np.array(case["coefficients"])
+    packed = orc.PackedBasis(basis)
+    eng = Engine(basis)
+    eng.set_coefficients(coeff)
+    pos, numbers, cell, pbc = synthetic.bcc_w((20, 20, 25), a=3.206, sigma=0.15, seed=3)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    want_e, want_f = orc.energy_forces(basis, packed, coeff, pos, numbers, images[1])
+    eng.build_neighbors(pos, numbers, images=images)
+    e, f = eng.energy_forces()
+    assert abs(e - want_e) <= REL * abs(want_e) and gu.rel_err(f, want_f) <= REL
+    pos, numbers, cell, pbc = synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    eng.build_neighbors(pos, numbers, images=images)
+    e, f = eng.energy_forces()
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * np.abs(f).max() * len(pos)
+    shifted = pos.copy()
+    shifted[::7] += cell[0]                   # move every 7th atom into the next periodic image
+    eng.build_neighbors(shifted, numbers, images=images)
+    e2, f2 = eng.energy_forces()
+    assert abs(e2 - e) <= 1e-9 * abs(e) and gu.rel_err(f2, f) <= 1e-8
+    eng.close()
