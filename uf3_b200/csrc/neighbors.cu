@@ -179,9 +179,35 @@ __device__ __forceinline__ void warp_rank_sort(const int *src, int *dst, int n, 
 }
 
 constexpr int NL_WARPS = 4;
+constexpr int NL_TILE = 1024;     // slots staged per block (32 KB); larger tiles fall back to global reads
 
-// Block = one cell, warp = one real centre of that cell.  FILL=false counts, FILL=true
-// writes the hits (ballot-compacted) and sorts each row by supercell index.
+// ---- TMA bulk copy (cp.async.bulk, completion counted on an mbarrier)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// Block = one cell, warp = one real centre of that cell.  The slots of the 3x3x3 block of
+// cells around it are 9 contiguous z-runs in the binned array; one thread stages them into
+// shared memory with 9 TMA bulk copies tracked by an mbarrier, and every warp then sweeps
+// the staged tile 32 candidates at a time.  FILL=false counts, FILL=true writes the hits
+// (ballot-compacted) and sorts each row by supercell index.
 template <bool FILL>
 __global__ void __launch_bounds__(NL_WARPS * 32)
 k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots,
@@ -189,11 +215,54 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
             int *__restrict__ cnt3, const int *__restrict__ off2, const int *__restrict__ off3,
             int *__restrict__ scratch2, int *__restrict__ scratch3, int *__restrict__ idx2,
             int *__restrict__ idx3) {
+    __shared__ __align__(128) Slot tile[NL_TILE];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ int run_lo[9], run_n[9], n_cand;
     const int cell = blockIdx.x;
     const int s0 = cell_start[cell], s1 = cell_start[cell + 1];
     if (s0 == s1) return;
-    const int cz = cell % G.nz, cy = (cell / G.nz) % G.ny, cx = cell / (G.nz * G.ny);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // any real atom in this cell?  (ghost-only cells of the padding do no work)
+    int real_here = 0;
+    for (int s = s0 + (int)threadIdx.x; s < s1; s += NL_WARPS * 32) real_here |= slots[s].m < n_real;
+    if (!__syncthreads_or(real_here)) return;
+
+    const int cz = cell % G.nz, cy = (cell / G.nz) % G.ny, cx = cell / (G.nz * G.ny);
+    if (threadIdx.x == 0) {
+        int total = 0, k = 0;
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy, ++k) {
+                const int x = cx + dx, y = cy + dy;
+                int lo = 0, cnt = 0;
+                if (x >= 0 && x < G.nx && y >= 0 && y < G.ny) {
+                    const int z0 = cz > 0 ? cz - 1 : 0, z1 = cz + 1 < G.nz ? cz + 1 : G.nz - 1;
+                    const int row = (x * G.ny + y) * G.nz;
+                    lo = cell_start[row + z0];
+                    cnt = cell_start[row + z1 + 1] - lo;
+                }
+                run_lo[k] = lo;
+                run_n[k] = cnt;
+                total += cnt;
+            }
+        n_cand = total;
+        if (total <= NL_TILE) {
+            const unsigned b = smem_addr(&bar);
+            mbar_init(b, 1);
+            mbar_expect_tx(b, (unsigned)total * (unsigned)sizeof(Slot));
+            unsigned dst = smem_addr(tile);
+            for (int r = 0; r < 9; ++r)
+                if (run_n[r] > 0) {
+                    const unsigned bytes = (unsigned)run_n[r] * (unsigned)sizeof(Slot);
+                    bulk_copy_g2s(dst, slots + run_lo[r], bytes, b);
+                    dst += bytes;
+                }
+        }
+    }
+    __syncthreads();
+    const int total = n_cand;
+    const bool staged = total <= NL_TILE;
+    if (staged) mbar_wait(smem_addr(&bar), 0);
+
     const unsigned lt = (1u << lane) - 1u;
     const bool has3 = B.n_trios > 0;
     for (int s = s0 + warp; s < s1; s += NL_WARPS) {
@@ -202,37 +271,33 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
         const Vec3 pc = {c.x, c.y, c.z};
         int n2 = 0, n3 = 0, base2 = 0, base3 = 0;
         if (FILL) { base2 = off2[c.m]; base3 = off3[c.m]; }
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int x = cx + dx;
-            if (x < 0 || x >= G.nx) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int y = cy + dy;
-                if (y < 0 || y >= G.ny) continue;
-                const int z0 = cz > 0 ? cz - 1 : 0, z1 = cz + 1 < G.nz ? cz + 1 : G.nz - 1;
-                const int row = (x * G.ny + y) * G.nz;
-                const int r0 = cell_start[row + z0], r1 = cell_start[row + z1 + 1];
-                for (int q0 = r0; q0 < r1; q0 += 32) {
-                    const int q = q0 + lane;
-                    bool k2 = false, k3 = false;
-                    int m = 0;
-                    if (q < r1) {
-                        const Slot t = slots[q];
-                        const Vec3 pt = {t.x, t.y, t.z};
-                        const double d = dist_rn(pc, pt);
-                        const int p = pair_index(B.ne, c.spec, t.spec);
-                        k2 = d > B.pair_lo[p] && d < B.pair_hi[p];
-                        k3 = has3 && d > B.r3min && d <= B.r3max;
-                        m = t.m;
-                    }
-                    const unsigned b2 = __ballot_sync(FULL, k2), b3 = __ballot_sync(FULL, k3);
-                    if (FILL) {
-                        if (k2) scratch2[base2 + n2 + __popc(b2 & lt)] = m;
-                        if (k3) scratch3[base3 + n3 + __popc(b3 & lt)] = m;
-                    }
-                    n2 += __popc(b2);
-                    n3 += __popc(b3);
+        auto visit = [&](const Slot *cand, int count) {
+            for (int q0 = 0; q0 < count; q0 += 32) {
+                const int q = q0 + lane;
+                bool k2 = false, k3 = false;
+                int m = 0;
+                if (q < count) {
+                    const Slot t = cand[q];
+                    const Vec3 pt = {t.x, t.y, t.z};
+                    const double d = dist_rn(pc, pt);
+                    const int p = pair_index(B.ne, c.spec, t.spec);
+                    k2 = d > B.pair_lo[p] && d < B.pair_hi[p];
+                    k3 = has3 && d > B.r3min && d <= B.r3max;
+                    m = t.m;
                 }
+                const unsigned b2 = __ballot_sync(FULL, k2), b3 = __ballot_sync(FULL, k3);
+                if (FILL) {
+                    if (k2) scratch2[base2 + n2 + __popc(b2 & lt)] = m;
+                    if (k3) scratch3[base3 + n3 + __popc(b3 & lt)] = m;
+                }
+                n2 += __popc(b2);
+                n3 += __popc(b3);
             }
+        };
+        if (staged) {
+            visit(tile, total);
+        } else {
+            for (int r = 0; r < 9; ++r) visit(slots + run_lo[r], run_n[r]);
         }
         if (!FILL) {
             if (lane == 0) { cnt2[c.m] = n2; cnt3[c.m] = n3; }
