@@ -147,6 +147,22 @@ def test_energy_forces_match_oracle_mid_size():
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["syn_w54_demo", "syn_w36_slab", "ref_ar3_default"])
+def test_register_tile_and_scatter_paths_agree(name, monkeypatch):
+    """Unary bases with a small untrimmed 3-body grid take the register-tile path of
+    k_featurize; UF3B_NO_TILE forces the general shared-memory scatter path."""
+    case = gu.Case(name)
+    _, eng, _ = _engine_for(case)
+    xe_tile, xf_tile = eng.featurize()
+    eng.close()
+    monkeypatch.setenv("UF3B_NO_TILE", "1")
+    _, eng, _ = _engine_for(case)
+    xe_scatter, xf_scatter = eng.featurize()
+    eng.close()
+    assert gu.rel_err(xe_tile, xe_scatter) <= 1e-12 and gu.rel_err(xf_tile, xf_scatter) <= 1e-12
+    assert gu.rel_err(xf_scatter, case["x_forces"]) <= REL
+
+
 def test_empty_and_single_atom():
     basis = gu.Case("syn_w16_demo").basis()
     eng = Engine(basis)

@@ -7,6 +7,7 @@
 // (forcefield/calculator.py:490-573).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -240,6 +241,10 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     b->n_feats = d->n_feats;
     b->h_trio_goff = trio_goff;
     b->h_trio_col = trio_col;
+    b->h_trio_sym = trio_sym;
+    b->h_trio_dims.resize(3 * n_trios);
+    for (int k = 0; k < 3 * n_trios; ++k) b->h_trio_dims[k] = trio_nk[k] - 4;
+    b->no_tile = getenv("UF3B_NO_TILE") != nullptr;
     b->h_bin_col = bin_col;
     b->h_bin_w = bin_w;
     b->h_numbers = numbers;

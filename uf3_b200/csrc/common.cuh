@@ -129,7 +129,8 @@ struct uf3b_basis {
     int n_feats = 0;
     bool has_coeff = false;
     int device = 0;
-    std::vector<int> h_trio_goff, h_bin_col, h_trio_col;
+    std::vector<int> h_trio_goff, h_bin_col, h_trio_col, h_trio_sym, h_trio_dims;   // dims: [3*t + leg]
+    bool no_tile = false;          // force the general scatter path (tests / profiling)
     std::vector<double> h_bin_w;
     std::vector<int> h_numbers;
     // scratch for energy partial sums and force-row staging (grow-only)

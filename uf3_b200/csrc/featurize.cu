@@ -34,13 +34,14 @@ struct __align__(16) TriRec {
     int flags, sym, dlm, dmn;      // RF_*; symmetry order; il-im, im-in (mirror classes)
     int n_act, p0, q0, r0;         // untrimmed bins: count and first (p, q, r)
     int nq, nr, mq, mr;            // extents of q and r and their fixed-point reciprocals
+    int il, im, in, pad0;          // first basis index of each leg (register-tile path)
     double v[3][4], dv[3][4];
     double A[3], B[3], C[3];
     double pad;
 };
 static_assert(sizeof(TriRec) % 16 == 0, "TriRec must keep 16-byte alignment in arrays");
 constexpr int RF_VALID = 1, RF_CENTRE = 2;
-constexpr unsigned REC_V = 64, REC_DV = 64 + 96, REC_ABC = 64 + 192;   // byte offsets
+constexpr unsigned REC_V = 80, REC_DV = 80 + 96, REC_ABC = 80 + 192;   // byte offsets
 
 struct __align__(16) PairRec {
     double v[4], dv[4];
@@ -73,6 +74,9 @@ __device__ __forceinline__ void store_record(TriRec *rec, const Triangle &T, con
     rec->col0 = __ldg(B.trio_col + T.trio);
     rec->dlm = T.il - T.im;
     rec->dmn = T.im - T.in;
+    rec->il = T.il;
+    rec->im = T.im;
+    rec->in = T.in;
     const int sym = __ldg(B.trio_sym + T.trio);
     rec->sym = sym < 1 ? 1 : (sym > 3 ? 3 : sym);
     // floor(b / n) for b < 64, n in 1..4 is (b * magic[n]) >> 8
@@ -209,12 +213,112 @@ __device__ __forceinline__ void scatter_records(const BasisTab &B, unsigned recs
     }
 }
 
+// ---------------------------------------------------------------- register-tile path
+// For a unary basis whose UNTRIMMED 3-body grid is small (the default and demo UF3 bases:
+// 3 x 3 x 9 cells after the trims), the per-atom grid is kept in registers instead of being
+// updated in shared memory per triangle: lane owns up to KP (m, n) cells of the untrimmed
+// (m, n) plane and, for each, one accumulator quad per untrimmed l (at most RT_LA).  A
+// record then costs a handful of broadcast loads and FMAs per lane, with no read-modify-
+// write, no symmetry passes and no synchronisation; the grid is folded into the compressed
+// columns (bin_col, mirror passes) once per atom.
+constexpr int RT_LA = 4;
+
+struct TileGeom {
+    int l0, m0, n0;        // first untrimmed basis index per leg
+    int la, ma, na;        // untrimmed extents
+    int dim_m, dim_n;      // full grid extents of legs m, n
+    int goff, col0, sym;
+};
+
+template <int KP>
+struct Tile {
+    double acc[KP][RT_LA][4];
+    int m[KP], n[KP];      // owned (m, n) cells (absolute basis indices), m < 0: none
+
+    __device__ __forceinline__ void init(const TileGeom &g, int lane) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int cell = lane + 32 * k;
+            const bool ok = cell < g.ma * g.na;
+            m[k] = ok ? g.m0 + cell / g.na : -1000;
+            n[k] = ok ? g.n0 + cell % g.na : -1000;
+#pragma unroll
+            for (int l = 0; l < RT_LA; ++l)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[k][l][c] = 0.0;
+        }
+    }
+
+    // add `count` records (phase B of the register-tile path)
+    __device__ __forceinline__ void accumulate(const TileGeom &g, unsigned recs, int count, bool want_e) {
+        for (int t = 0; t < count; ++t) {
+            const unsigned rec = recs + (unsigned)t * (unsigned)sizeof(TriRec);
+            const int4 h1 = lds128i(rec + 16);      // flags, sym, dlm, dmn
+            if (!(h1.x & RF_VALID)) continue;
+            const int4 h4 = lds128i(rec + 64);      // il, im, in
+            const bool centre = (h1.x & RF_CENTRE) != 0 && want_e;
+            const double2 ab0 = lds128(rec + REC_ABC), ab1 = lds128(rec + REC_ABC + 16);
+            const double2 ab2 = lds128(rec + REC_ABC + 32), ab3 = lds128(rec + REC_ABC + 48);
+            const double c2 = lds64(rec + REC_ABC + 64);
+            // A = (ab0.x, ab0.y, ab1.x)  B = (ab1.y, ab2.x, ab2.y)  C = (ab3.x, ab3.y, c2)
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const unsigned q = (unsigned)(m[k] - h4.y), r = (unsigned)(n[k] - h4.z);
+                if (q < 4u && r < 4u) {
+                    const double vm = lds64(rec + REC_V + 32 + 8 * q), dvm = lds64(rec + REC_DV + 32 + 8 * q);
+                    const double vn = lds64(rec + REC_V + 64 + 8 * r), dvn = lds64(rec + REC_DV + 64 + 8 * r);
+                    const double t1 = vm * vn, t2 = dvm * vn, t3 = vm * dvn;
+#pragma unroll
+                    for (int l = 0; l < RT_LA; ++l) {
+                        const unsigned pp = (unsigned)(g.l0 + l - h4.x);      // warp-uniform
+                        if (l < g.la && pp < 4u) {
+                            const double vl = lds64(rec + REC_V + 8 * pp), dvl = lds64(rec + REC_DV + 8 * pp);
+                            const double ga = dvl * t1, gb = vl * t2, gc = vl * t3;
+                            if (centre) acc[k][l][0] += vl * t1;
+                            acc[k][l][1] += ga * ab0.x + gb * ab1.y + gc * ab3.x;
+                            acc[k][l][2] += ga * ab0.y + gb * ab2.x + gc * ab3.y;
+                            acc[k][l][3] += ga * ab1.x + gb * ab2.y + gc * c2;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // fold the grid into the compressed columns (once per atom) and clear the force parts
+    template <class Acc>
+    __device__ __forceinline__ void flush(const BasisTab &B, const TileGeom &g, const Acc out) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+#pragma unroll
+            for (int l = 0; l < RT_LA; ++l) {
+                const int ll = g.l0 + l;
+                int col = -1;
+                if (l < g.la && m[k] >= 0) col = __ldg(B.bin_col + g.goff + (ll * g.dim_m + m[k]) * g.dim_n + n[k]);
+                const bool live = col >= 0;
+                // stable-sort class of (l, m, n): equal classes never share a column
+                int cls = 0;
+                if (g.sym >= 2) cls = ll > m[k];
+                if (g.sym == 3) cls |= ((m[k] > n[k]) << 1) | ((ll > n[k]) << 2);
+                const int n_cls = g.sym == 1 ? 1 : (g.sym == 2 ? 2 : 8);
+                for (int ph = 0; ph < n_cls; ++ph) {
+                    if (live && cls == ph)
+                        out.add(g.col0 + col, acc[k][l][0], acc[k][l][1], acc[k][l][2], acc[k][l][3]);
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[k][l][c] = 0.0;
+            }
+    }
+};
+
 // GLOBAL_ACC: the per-warp accumulators [4 * n_feats] live in a global scratch buffer
 // (L1/L2 resident) instead of shared memory — the path for bases whose rows do not fit
 // (e.g. 18 trio interactions of a ternary system, F ~ 7000).
-template <bool GLOBAL_ACC>
+// KP > 0 selects the register-tile path with KP (m, n) cells per lane.
+template <bool GLOBAL_ACC, int KP>
 __global__ void __launch_bounds__(256, 2)
-k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long long ld,
+k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__restrict__ xf, long long ld,
             double *__restrict__ partials, double *gacc, int want_e_, int want_f_) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -233,6 +337,8 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
 
     for (int k = lane; k < 4 * F; k += 32) acc[k] = 0.0;
     __syncwarp();
+    Tile<(KP > 0 ? KP : 1)> tile;
+    if constexpr (KP > 0) tile.init(tg, lane);
 
     for (int a = gw; a < f.n; a += n_gw) {
         const int sa = __ldg(f.spec + a);
@@ -312,7 +418,8 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                         store_record(recs + lane, T, B, 0);
                 }
                 __syncwarp();
-                scatter_records(B, recs_s, min(CHUNK, n_tri - t0), acc_rw, lane, want_e);
+                if constexpr (KP > 0) tile.accumulate(tg, recs_s, min(CHUNK, n_tri - t0), want_e);
+                else scatter_records(B, recs_s, min(CHUNK, n_tri - t0), acc_rw, lane, want_e);
                 __syncwarp();
             }
             // (ii) `a` as a neighbour of each centre in its list (force rows only)
@@ -336,7 +443,8 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
                             }
                         }
                         __syncwarp();
-                        scatter_records(B, recs_s, min(CHUNK, total - it0), acc_rw, lane, false);
+                        if constexpr (KP > 0) tile.accumulate(tg, recs_s, min(CHUNK, total - it0), false);
+                        else scatter_records(B, recs_s, min(CHUNK, total - it0), acc_rw, lane, false);
                         __syncwarp();
                     }
                 }
@@ -344,6 +452,7 @@ k_featurize(const BasisTab B, const FrameView f, double *__restrict__ xf, long l
         }
 
         // ------------------------------------------------ rows fx_a, fy_a, fz_a
+        if constexpr (KP > 0) tile.flush(B, tg, acc_rw);
         __syncwarp();
         if (want_f) {
             for (int col = lane; col < F; col += 32) {
@@ -414,7 +523,22 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     int warps = global_acc ? 4 : 8;
     while (warps > 1 && (size_t)warps * per_warp > (size_t)smem_max / 2) warps >>= 1;
     const size_t smem = (size_t)warps * per_warp;
-    auto kernel = global_acc ? k_featurize<true> : k_featurize<false>;
+    // register-tile path: unary basis, unit folding weights, small untrimmed 3-body grid
+    TileGeom tg = {};
+    int kp = 0;
+    if (!global_acc && basis->tab.n_trios == 1 && basis->tab.unit_weights && !basis->no_tile) {
+        const int lead = basis->tab.lead3, trail = basis->tab.trail3;
+        const int L = basis->h_trio_dims[0], M = basis->h_trio_dims[1], N = basis->h_trio_dims[2];
+        tg.l0 = tg.m0 = tg.n0 = lead;
+        tg.la = L - lead - trail; tg.ma = M - lead - trail; tg.na = N - lead - trail;
+        tg.dim_m = M; tg.dim_n = N;
+        tg.goff = 0; tg.col0 = basis->h_trio_col[0]; tg.sym = basis->h_trio_sym[0];
+        if (tg.la >= 1 && tg.la <= RT_LA && tg.ma >= 1 && tg.na >= 1 && tg.ma * tg.na <= 64
+            && tg.sym >= 1 && tg.sym <= 3)
+            kp = tg.ma * tg.na <= 32 ? 1 : 2;
+    }
+    auto kernel = global_acc ? k_featurize<true, 0>
+                             : (kp == 1 ? k_featurize<false, 1> : (kp == 2 ? k_featurize<false, 2> : k_featurize<false, 0>));
     UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
@@ -447,7 +571,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         UF3B_CUDA(cudaEventRecord(ev0, stream));
     }
     if (global_acc) UF3B_CUDA(basis->gacc.reserve((size_t)n_gw * 4 * F));
-    UF3B_LAUNCH(kernel, grid, warps * 32, smem, stream, basis->tab, view, d_xf, d_ld,
+    UF3B_LAUNCH(kernel, grid, warps * 32, smem, stream, basis->tab, view, tg, d_xf, d_ld,
                 basis->partials.p, basis->gacc.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (x_energy)
