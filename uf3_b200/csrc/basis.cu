@@ -81,7 +81,7 @@ int uf3b_host_eval_basis(const double *knots, int32_t n_knots, double r, double 
     if (!knots || n_knots < 8 || !v || !dv) return fail(UF3B_ERR_INVALID, "bad knot vector");
     std::vector<double> poly;
     build_pieces(knots, n_knots, poly);
-    return eval_leg(knots, n_knots, poly.data(), r, 0, 0, v, dv);
+    return eval_leg(knots, n_knots, knot_scale(knots, n_knots), poly.data(), r, 0, 0, v, dv);
 }
 
 int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
@@ -106,7 +106,7 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
 
     // ---- pairs
     std::vector<int> pair_nk(n_pairs), pair_koff(n_pairs), pair_poff(n_pairs), pair_col(n_pairs);
-    std::vector<double> pair_lo(n_pairs), pair_hi(n_pairs), knots2, poly2;
+    std::vector<double> pair_lo(n_pairs), pair_hi(n_pairs), knots2, poly2, pair_scale(n_pairs);
     double r_search = 0.0;
     {
         int koff = 0;
@@ -122,6 +122,7 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
                 knots2.push_back(t);
             }
             build_pieces(d->pair_knots + koff, nk, poly2);
+            pair_scale[p] = knot_scale(d->pair_knots + koff, nk);
             koff += nk;
             pair_lo[p] = d->pair_r_min[p] > 0.0 ? d->pair_r_min[p] : 0.0;   // distances.py:60
             pair_hi[p] = d->pair_r_max[p];
@@ -135,7 +136,7 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     // ---- trios
     std::vector<int> trio_nk(3 * n_trios), trio_koff(3 * n_trios), trio_poff(3 * n_trios);
     std::vector<int> trio_col(n_trios), trio_goff(n_trios), trio_sym(n_trios);
-    std::vector<double> knots3, poly3;
+    std::vector<double> knots3, poly3, trio_scale(3 * n_trios);
     std::vector<int> bin_col;
     std::vector<double> bin_w;
     double r3min = 0.0, r3max = 0.0;
@@ -161,6 +162,7 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
                     if (leg < 2 && v > r3max) r3max = v;                            // angles.py:322
                 }
                 build_pieces(d->trio_knots + koff, nk, poly3);
+                trio_scale[3 * t + leg] = knot_scale(d->trio_knots + koff, nk);
                 koff += nk;
                 grid *= nk - 4;
             }
@@ -196,6 +198,7 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     const size_t o_knots3 = pk.add(knots3), o_poly3 = pk.add(poly3);
     const size_t o_bin_col = pk.add(bin_col), o_bin_w = pk.add(bin_w);
     const size_t o_z = pk.add(z_to_spec);
+    const size_t o_pair_scale = pk.add(pair_scale), o_trio_scale = pk.add(trio_scale);
 
     uf3b_basis *b = new uf3b_basis();
     cudaGetDevice(&b->device);
@@ -232,6 +235,8 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     T.bin_col = (const int *)(base + o_bin_col);
     T.bin_w = (const double *)(base + o_bin_w);
     T.z_to_spec = (const int *)(base + o_z);
+    T.pair_scale = (const double *)(base + o_pair_scale);
+    T.trio_scale = (const double *)(base + o_trio_scale);
     T.unit_weights = 1;
     for (int k = 0; k < n_bins; ++k)
         if (bin_col[k] >= 0 && bin_w[k] != 1.0) T.unit_weights = 0;

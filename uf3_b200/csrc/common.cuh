@@ -85,10 +85,10 @@ struct BasisTab {
     double r_search;          // max over pair r_max and r3max (cell edge)
     const int *pair_nk, *pair_koff, *pair_poff, *pair_col;
     const double *pair_lo, *pair_hi;   // strict bounds max(r_min,0) < d < r_max
-    const double *knots2, *poly2;
+    const double *knots2, *poly2, *pair_scale;   // scale: intervals per unit length
     const int *trio_nk, *trio_koff, *trio_poff;   // [3*t + leg]
     const int *trio_col, *trio_goff, *trio_sym;   // [t]
-    const double *knots3, *poly3;
+    const double *knots3, *poly3, *trio_scale;   // [3*t + leg]
     const int *bin_col;       // full grid bin -> compressed column (or -1), trio-major
     const double *bin_w;      // folding weight of the bin
     const double *coeff;      // flat model coefficients [n_feats]   (inference only)

@@ -71,7 +71,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *__restrict__ forces
             const double d = dist_rn(pa, pj);
             const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
             double v[4], dv[4];
-            const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr),
+            const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
                                      B.poly2 + __ldg(B.pair_poff + pr), d, 0, 0, v, dv);
             if (idx < 0) continue;
             const double *c = B.coeff + __ldg(B.pair_col + pr) + idx;

@@ -217,31 +217,62 @@ __device__ __forceinline__ void scatter_records(const BasisTab &B, unsigned recs
 // For a unary basis whose UNTRIMMED 3-body grid is small (the default and demo UF3 bases:
 // 3 x 3 x 9 cells after the trims), the per-atom grid is kept in registers instead of being
 // updated in shared memory per triangle: lane owns up to KP (m, n) cells of the untrimmed
-// (m, n) plane and, for each, one accumulator quad per untrimmed l (at most RT_LA).  A
-// record then costs a handful of broadcast loads and FMAs per lane, with no read-modify-
-// write, no symmetry passes and no synchronisation; the grid is folded into the compressed
-// columns (bin_col, mirror passes) once per atom.
+// (m, n) plane and, for each, one accumulator quad per untrimmed l (at most RT_LA).
+// Phase A writes every leg's four values DENSELY by absolute basis index (zero outside the
+// triangle's block), so phase B is branch-free: fixed per-lane offsets, a few broadcast
+// loads and FMAs per record, no read-modify-write, no symmetry passes, no synchronisation.
+// The grid is folded into the compressed columns (bin_col, mirror passes) once per atom.
 constexpr int RT_LA = 4;
+constexpr unsigned TR_ABC = 16, TR_VL = 96, TR_DVL = 128, TR_LEGS = 160;   // tile record bytes
+static_assert(TR_LEGS + 16 * 12 <= sizeof(TriRec), "tile record must fit the scratch slot");
 
 struct TileGeom {
     int l0, m0, n0;        // first untrimmed basis index per leg
-    int la, ma, na;        // untrimmed extents
+    int la, ma, na;        // untrimmed extents (la <= RT_LA, ma + na <= 12, ma * na <= 64)
     int dim_m, dim_n;      // full grid extents of legs m, n
     int goff, col0, sym;
 };
 
+// Tile record: [flags][A B C][vl[4] dvl[4]][vm[ma] dvm[ma] vn[na] dvn[na]], dense by
+// (basis index - first untrimmed index).
+__device__ __forceinline__ void store_tile_record(unsigned char *rec, const Triangle &T,
+                                                  const TileGeom &g, int role) {
+    double *legs = reinterpret_cast<double *>(rec + TR_VL);
+    {   // clear the dense leg arrays, 16 bytes at a time
+        double2 *z = reinterpret_cast<double2 *>(legs);
+        const int n16 = 4 + g.ma + g.na;
+        for (int k = 0; k < n16; ++k) z[k] = make_double2(0.0, 0.0);
+    }
+    double *abc = reinterpret_cast<double *>(rec + TR_ABC);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { abc[c] = T.A[c]; abc[3 + c] = T.B[c]; abc[6 + c] = T.C[c]; }
+    double *vm = legs + 8, *dvm = vm + g.ma, *vn = dvm + g.ma, *dvn = vn + g.na;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int l = T.il + p - g.l0, m = T.im + p - g.m0, n = T.in + p - g.n0;
+        if (l >= 0 && l < g.la) { legs[l] = T.v[0][p]; legs[4 + l] = T.dv[0][p]; }
+        if (m >= 0 && m < g.ma) { vm[m] = T.v[1][p]; dvm[m] = T.dv[1][p]; }
+        if (n >= 0 && n < g.na) { vn[n] = T.v[2][p]; dvn[n] = T.dv[2][p]; }
+    }
+    *reinterpret_cast<int *>(rec) = RF_VALID | (role == 0 ? RF_CENTRE : 0);
+}
+
 template <int KP>
 struct Tile {
     double acc[KP][RT_LA][4];
-    int m[KP], n[KP];      // owned (m, n) cells (absolute basis indices), m < 0: none
+    int m[KP], n[KP];          // owned (m, n) cells (absolute basis indices), m < 0: none
+    unsigned off_m[KP], off_n[KP];   // byte offsets of vm[m - m0], vn[n - n0] in a tile record
 
     __device__ __forceinline__ void init(const TileGeom &g, int lane) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             const int cell = lane + 32 * k;
             const bool ok = cell < g.ma * g.na;
-            m[k] = ok ? g.m0 + cell / g.na : -1000;
-            n[k] = ok ? g.n0 + cell % g.na : -1000;
+            const int mi = ok ? cell / g.na : 0, ni = ok ? cell % g.na : 0;
+            m[k] = ok ? g.m0 + mi : -1000;
+            n[k] = ok ? g.n0 + ni : -1000;
+            off_m[k] = TR_LEGS + 8u * (unsigned)mi;
+            off_n[k] = TR_LEGS + 8u * (unsigned)(2 * g.ma + ni);
 #pragma unroll
             for (int l = 0; l < RT_LA; ++l)
 #pragma unroll
@@ -251,41 +282,40 @@ struct Tile {
 
     // add `count` records (phase B of the register-tile path)
     __device__ __forceinline__ void accumulate(const TileGeom &g, unsigned recs, int count, bool want_e) {
+        const unsigned d_m = 8u * (unsigned)g.ma, d_n = 8u * (unsigned)g.na;
         for (int t = 0; t < count; ++t) {
             const unsigned rec = recs + (unsigned)t * (unsigned)sizeof(TriRec);
-            const int4 h1 = lds128i(rec + 16);      // flags, sym, dlm, dmn
-            if (!(h1.x & RF_VALID)) continue;
-            const int4 h4 = lds128i(rec + 64);      // il, im, in
-            const bool centre = (h1.x & RF_CENTRE) != 0 && want_e;
-            const double2 ab0 = lds128(rec + REC_ABC), ab1 = lds128(rec + REC_ABC + 16);
-            const double2 ab2 = lds128(rec + REC_ABC + 32), ab3 = lds128(rec + REC_ABC + 48);
-            const double c2 = lds64(rec + REC_ABC + 64);
+            const int4 h = lds128i(rec);
+            if (!(h.x & RF_VALID)) continue;
+            const double escale = ((h.x & RF_CENTRE) != 0 && want_e) ? 1.0 : 0.0;
+            const double2 ab0 = lds128(rec + TR_ABC), ab1 = lds128(rec + TR_ABC + 16);
+            const double2 ab2 = lds128(rec + TR_ABC + 32), ab3 = lds128(rec + TR_ABC + 48);
+            const double c2 = lds64(rec + TR_ABC + 64);
             // A = (ab0.x, ab0.y, ab1.x)  B = (ab1.y, ab2.x, ab2.y)  C = (ab3.x, ab3.y, c2)
+            const double2 vl01 = lds128(rec + TR_VL), vl23 = lds128(rec + TR_VL + 16);
+            const double2 dl01 = lds128(rec + TR_DVL), dl23 = lds128(rec + TR_DVL + 16);
+            const double vl[4] = {vl01.x, vl01.y, vl23.x, vl23.y};
+            const double dvl[4] = {dl01.x, dl01.y, dl23.x, dl23.y};
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-                const unsigned q = (unsigned)(m[k] - h4.y), r = (unsigned)(n[k] - h4.z);
-                if (q < 4u && r < 4u) {
-                    const double vm = lds64(rec + REC_V + 32 + 8 * q), dvm = lds64(rec + REC_DV + 32 + 8 * q);
-                    const double vn = lds64(rec + REC_V + 64 + 8 * r), dvn = lds64(rec + REC_DV + 64 + 8 * r);
-                    const double t1 = vm * vn, t2 = dvm * vn, t3 = vm * dvn;
+                const double vm = lds64(rec + off_m[k]), dvm = lds64(rec + off_m[k] + d_m);
+                const double vn = lds64(rec + off_n[k]), dvn = lds64(rec + off_n[k] + d_n);
+                const double t1 = vm * vn, t2 = dvm * vn, t3 = vm * dvn, t1e = t1 * escale;
 #pragma unroll
-                    for (int l = 0; l < RT_LA; ++l) {
-                        const unsigned pp = (unsigned)(g.l0 + l - h4.x);      // warp-uniform
-                        if (l < g.la && pp < 4u) {
-                            const double vl = lds64(rec + REC_V + 8 * pp), dvl = lds64(rec + REC_DV + 8 * pp);
-                            const double ga = dvl * t1, gb = vl * t2, gc = vl * t3;
-                            if (centre) acc[k][l][0] += vl * t1;
-                            acc[k][l][1] += ga * ab0.x + gb * ab1.y + gc * ab3.x;
-                            acc[k][l][2] += ga * ab0.y + gb * ab2.x + gc * ab3.y;
-                            acc[k][l][3] += ga * ab1.x + gb * ab2.y + gc * c2;
-                        }
+                for (int l = 0; l < RT_LA; ++l) {
+                    if (l < g.la) {           // warp-uniform
+                        const double ga = dvl[l] * t1, gb = vl[l] * t2, gc = vl[l] * t3;
+                        acc[k][l][0] = fma(vl[l], t1e, acc[k][l][0]);
+                        acc[k][l][1] = fma(gc, ab3.x, fma(gb, ab1.y, fma(ga, ab0.x, acc[k][l][1])));
+                        acc[k][l][2] = fma(gc, ab3.y, fma(gb, ab2.x, fma(ga, ab0.y, acc[k][l][2])));
+                        acc[k][l][3] = fma(gc, c2, fma(gb, ab2.y, fma(ga, ab1.x, acc[k][l][3])));
                     }
                 }
             }
         }
     }
 
-    // fold the grid into the compressed columns (once per atom) and clear the force parts
+    // fold the grid into the compressed columns (once per atom) and clear it
     template <class Acc>
     __device__ __forceinline__ void flush(const BasisTab &B, const TileGeom &g, const Acc out) {
 #pragma unroll
@@ -356,7 +386,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
                     const Vec3 pj = super_position(f, __ldg(f.idx2 + e), aj);
                     const double d = dist_rn(pa, pj);
                     const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
-                    const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr),
+                    const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
                                              B.poly2 + __ldg(B.pair_poff + pr), d, B.lead2, B.trail2,
                                              rec.v, rec.dv);
                     if (idx >= 0) {
@@ -408,14 +438,15 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
             const int n_tri = n3a * (n3a - 1) / 2;
             for (int t0 = 0; t0 < n_tri; t0 += CHUNK) {
                 const int t = t0 + lane;
-                recs[lane].flags = 0;
+                if constexpr (KP > 0) recs[lane].base = 0; else recs[lane].flags = 0;
                 if (t < n_tri) {
                     int qj, qk;
                     unrank_pair(t, qj, qk);
                     Triangle T;
                     if (eval_triangle(B, f, pa, sa, __ldg(f.idx3 + row0 + qj), __ldg(f.idx3 + row0 + qk),
                                       0, B.lead3, B.trail3, T))
-                        store_record(recs + lane, T, B, 0);
+                        if constexpr (KP > 0) store_tile_record((unsigned char *)(recs + lane), T, tg, 0);
+                        else store_record(recs + lane, T, B, 0);
                 }
                 __syncwarp();
                 if constexpr (KP > 0) tile.accumulate(tg, recs_s, min(CHUNK, n_tri - t0), want_e);
@@ -428,7 +459,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
                     const int total = publish_views(B, f, a, vbase, n3a, lane, views);
                     for (int it0 = 0; it0 < total; it0 += CHUNK) {
                         const int it = it0 + lane;
-                        recs[lane].flags = 0;
+                        if constexpr (KP > 0) recs[lane].base = 0; else recs[lane].flags = 0;
                         if (it < total) {
                             const int v = find_view(views, it);
                             const int ci = views->centre[v], apr = views->a_prime[v];
@@ -439,7 +470,8 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
                                 if (eval_triangle(B, f, real_position(f, ci), __ldg(f.spec + ci),
                                                   first ? apr : mk, first ? mk : apr, first ? 1 : 2,
                                                   B.lead3, B.trail3, T))
-                                    store_record(recs + lane, T, B, first ? 1 : 2);
+                                    if constexpr (KP > 0) store_tile_record((unsigned char *)(recs + lane), T, tg, first ? 1 : 2);
+                                    else store_record(recs + lane, T, B, first ? 1 : 2);
                             }
                         }
                         __syncwarp();
@@ -534,7 +566,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         tg.dim_m = M; tg.dim_n = N;
         tg.goff = 0; tg.col0 = basis->h_trio_col[0]; tg.sym = basis->h_trio_sym[0];
         if (tg.la >= 1 && tg.la <= RT_LA && tg.ma >= 1 && tg.na >= 1 && tg.ma * tg.na <= 64
-            && tg.sym >= 1 && tg.sym <= 3)
+            && tg.ma + tg.na <= 12 && tg.sym >= 1 && tg.sym <= 3)
             kp = tg.ma * tg.na <= 32 ? 1 : 2;
     }
     auto kernel = global_acc ? k_featurize<true, 0>

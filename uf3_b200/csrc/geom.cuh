@@ -41,6 +41,16 @@ __device__ __forceinline__ double dist_rn(const Vec3 &p, const Vec3 &q) {
     return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
 }
 
+// 1/d for a finite, normal d > 0 (an interatomic distance): single-precision seed and two
+// Newton steps, relative error < 1e-15 — used for direction cosines only, never for a
+// cutoff decision.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r = (double)__frcp_rn((float)d);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    return r;
+}
+
 // ---- shared-memory access by 32-bit shared-window address.  The featurize kernel keeps
 // its per-warp bases in registers through `pin` (ptxas otherwise rematerialises the
 // generic->shared conversion, ~12 instructions, at every use in the hot loop); the

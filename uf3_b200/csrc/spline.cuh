@@ -21,11 +21,12 @@ namespace uf3b {
 #endif
 
 // Interval i with t[i] < r <= t[i+1], 3 <= i <= nk-5, or -1.
-UF3B_HD int find_interval(const double *t, int nk, double r) {
+// `scale` = (nk - 7) / (t[nk-4] - t[3]) (intervals per unit length, precomputed).
+UF3B_HD int find_interval(const double *t, int nk, double scale, double r) {
     const double t_first = t[3], t_last = t[nk - 4];
     if (!(r > t_first) || !(r <= t_last)) return -1;
     // uniform-spacing guess, verified against the real knots
-    int i = 3 + (int)((r - t_first) * (double)(nk - 7) / (t_last - t_first));
+    int i = 3 + (int)((r - t_first) * scale);
     if (i > nk - 5) i = nk - 5;
     if (t[i] < r && r <= t[i + 1]) return i;
     int lo = 3, hi = nk - 4;    // invariant: t[lo] < r <= t[hi]
@@ -37,11 +38,18 @@ UF3B_HD int find_interval(const double *t, int nk, double r) {
 }
 
 // Values and first derivatives of basis functions i-3..i at r (piece = poly + 16*(i-3)).
+// Pieces are 32-byte aligned (16 doubles each in a 32-byte aligned table).
 UF3B_HD void eval_piece(const double *piece, double u, double v[4], double dv[4]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+#if defined(__CUDA_ARCH__)
+        const double2 lo = __ldg(reinterpret_cast<const double2 *>(piece) + 2 * q);
+        const double2 hi = __ldg(reinterpret_cast<const double2 *>(piece) + 2 * q + 1);
+        const double c0 = lo.x, c1 = lo.y, c2 = hi.x, c3 = hi.y;
+#else
         const double c0 = piece[4 * q + 0], c1 = piece[4 * q + 1];
         const double c2 = piece[4 * q + 2], c3 = piece[4 * q + 3];
+#endif
         v[q] = ((c3 * u + c2) * u + c1) * u + c0;
         dv[q] = (3.0 * c3 * u + 2.0 * c2) * u + c1;
     }
@@ -49,9 +57,9 @@ UF3B_HD void eval_piece(const double *piece, double u, double v[4], double dv[4]
 
 // Full leg evaluation with trims (angles.py:554-565, bspline.py:840): returns the
 // first basis index or -1; basis indices outside [n_lead, n_basis - n_trail) give 0.
-UF3B_HD int eval_leg(const double *t, int nk, const double *poly, double r, int n_lead,
+UF3B_HD int eval_leg(const double *t, int nk, double scale, const double *poly, double r, int n_lead,
                      int n_trail, double v[4], double dv[4]) {
-    const int i = find_interval(t, nk, r);
+    const int i = find_interval(t, nk, scale, r);
     if (i < 0) return -1;
     eval_piece(poly + 16 * (i - 3), r - t[i], v, dv);
     const int idx = i - 3, nb = nk - 4;
@@ -61,6 +69,11 @@ UF3B_HD int eval_leg(const double *t, int nk, const double *poly, double r, int 
         if (bi < n_lead || bi >= nb - n_trail) { v[q] = 0.0; dv[q] = 0.0; }
     }
     return idx;
+}
+
+inline double knot_scale(const double *t, int nk) {
+    const double span = t[nk - 4] - t[3];
+    return span > 0.0 ? (double)(nk - 7) / span : 0.0;
 }
 
 // Host: polynomial pieces of a knot vector (Cox-de Boor on polynomials in u).

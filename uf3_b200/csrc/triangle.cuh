@@ -53,9 +53,9 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
     if (!(dij >= tl[0] && dij <= tl[nkl - 1])) return false;      // angles.py:502-508
     if (!(dik >= tm[0] && dik <= tm[nkm - 1])) return false;
     if (!(djk >= tn[0] && djk <= tn[nkn - 1])) return false;
-    T.il = eval_leg(tl, nkl, B.poly3 + __ldg(B.trio_poff + 3 * t), dij, n_lead, n_trail, T.v[0], T.dv[0]);
-    T.im = eval_leg(tm, nkm, B.poly3 + __ldg(B.trio_poff + 3 * t + 1), dik, n_lead, n_trail, T.v[1], T.dv[1]);
-    T.in = eval_leg(tn, nkn, B.poly3 + __ldg(B.trio_poff + 3 * t + 2), djk, n_lead, n_trail, T.v[2], T.dv[2]);
+    T.il = eval_leg(tl, nkl, __ldg(B.trio_scale + 3 * t), B.poly3 + __ldg(B.trio_poff + 3 * t), dij, n_lead, n_trail, T.v[0], T.dv[0]);
+    T.im = eval_leg(tm, nkm, __ldg(B.trio_scale + 3 * t + 1), B.poly3 + __ldg(B.trio_poff + 3 * t + 1), dik, n_lead, n_trail, T.v[1], T.dv[1]);
+    T.in = eval_leg(tn, nkn, __ldg(B.trio_scale + 3 * t + 2), B.poly3 + __ldg(B.trio_poff + 3 * t + 2), djk, n_lead, n_trail, T.v[2], T.dv[2]);
     if (T.il < 0 || T.im < 0 || T.in < 0) return false;           // r exactly on the first knot
     T.trio = t;
     T.dim_m = nkm - 4;
@@ -71,7 +71,7 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
         if (T.cnt[0] == 0 || T.cnt[1] == 0 || T.cnt[2] == 0) return false;
     }
     // direction cosines (distances.py:354-363): u_ab = (x_b - x_a) / r_ab
-    const double il_ = 1.0 / dij, im_ = 1.0 / dik, in_ = 1.0 / djk;
+    const double il_ = fast_rcp(dij), im_ = fast_rcp(dik), in_ = fast_rcp(djk);
     const double uij[3] = {(pj.x - pc.x) * il_, (pj.y - pc.y) * il_, (pj.z - pc.z) * il_};
     const double uik[3] = {(pk.x - pc.x) * im_, (pk.y - pc.y) * im_, (pk.z - pc.z) * im_};
     const double ujk[3] = {(pk.x - pj.x) * in_, (pk.y - pj.y) * in_, (pk.z - pj.z) * in_};
