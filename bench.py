@@ -156,6 +156,85 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------- inference configs
+def inference_extras(torch, dev, stream, steps=20):
+    """BASELINE.json configs[2] and configs[4] at one GPU: energy + forces per step through
+    the C ABI (neighbour lists + evaluator), inputs resident / via host buffers.  Reported
+    beside the headline; not part of `value`."""
+    import glob
+    from uf3_b200 import bspline, composition, geometry, synthetic
+    from uf3_b200.engine import Engine
+
+    def model23():
+        # the shipped W 2+3-body model (examples/tungsten_extxyz/model_2and3.json), carried
+        # as a test fixture because /root/reference does not exist on the GPU box
+        data = np.load(os.path.join(ROOT, "tests", "golden", "calc_syn_w54_model23.npz"))
+        cfg = json.loads(str(data["config"]))
+        knots = {}
+        for key, val in cfg["kwargs"]["knots_map"].items():
+            parts = tuple(key.split("-"))
+            knots[parts] = np.array(val) if len(parts) == 2 else [np.array(v) for v in val]
+        chem = composition.ChemicalSystem(cfg["element_list"], degree=cfg["degree"])
+        lead = {int(k): v for k, v in cfg["kwargs"]["leading_trim"].items()}
+        trail = {int(k): v for k, v in cfg["kwargs"]["trailing_trim"].items()}
+        basis = bspline.BSplineBasis(chem, knots_map=knots, leading_trim=lead, trailing_trim=trail)
+        return basis, np.array(data["coefficients"])
+
+    def nexe_model():
+        data = np.load(os.path.join(ROOT, "tests", "golden", "calc_syn_nexe64_pair.npz"))
+        return synthetic.nexe_basis(), np.array(data["coefficients"])
+
+    out = {}
+    for tag, (basis, coeff), fr in (
+            ("nexe_50k_energy_forces", nexe_model(), synthetic.nexe((25, 25, 10), seed=0)),
+            ("w_100k_md_step_energy_forces", model23(), synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0))):
+        eng = Engine(basis, device=dev.index)
+        eng.set_coefficients(coeff)
+        pos, numbers, cell, pbc = fr
+        n = len(pos)
+        images = geometry.image_table(cell, pbc, basis.r_cut)
+        d_pos = torch.from_numpy(pos).to(dev)
+        d_num = torch.from_numpy(numbers).to(dev)
+        d_e = torch.zeros(1, dtype=torch.float64, device=dev)
+        d_f = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+        h_pos = torch.from_numpy(pos).pin_memory().numpy()
+
+        def resident():
+            eng.build_neighbors_device(d_pos.data_ptr(), d_num.data_ptr(), n, images, stream)
+            eng.energy_forces_device(d_e.data_ptr(), d_f.data_ptr(), stream)
+
+        def host():
+            eng.build_neighbors(h_pos, numbers, images=images, stream=stream)
+            eng.energy_forces(stream=stream)
+
+        res = {}
+        for name, fn in (("resident", resident), ("e2e", host)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"ms_per_step": ms, "atom_steps_per_s": n / (ms * 1e-3)}
+        eng.set_timing(True)
+        resident()
+        res["k_energy_forces_ms"] = eng.last_kernel_ms()
+        eng.set_timing(False)
+        res["n_atoms"] = n
+        res["n_feats"] = int(basis.n_feats)
+        res["pairs_per_atom"] = eng.neighbor_count(2) / n
+        # algorithmic bytes of the evaluator launch: positions + species + both CSR lists + forces
+        alg = n * 28 + 4 * (eng.neighbor_count(2) + eng.neighbor_count(3)) + 8 * (n + 1) + 24 * n + 8
+        res["hbm_GBps_algorithmic"] = alg / (res["k_energy_forces_ms"] * 1e-3) / 1e9
+        out[tag] = res
+        eng.close()
+    return out
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -257,6 +336,9 @@ def run_ours(args, rank, world, local_rank):
         return
 
     fp64_peak = eng.probe_fp64_tflops()
+    extra = None
+    if world == 1 and args.extra:
+        extra = inference_extras(torch, dev, stream)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_cpu_frames = 4
@@ -286,6 +368,7 @@ def run_ours(args, rank, world, local_rank):
                           "note": "3-body rows are FP64-bound, see DESIGN.md"},
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -300,6 +383,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--basis", default="demo", choices=["demo", "manuscript"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
+    ap.add_argument("--extra", action="store_true", help="also time the inference configs (Ne/Xe 50k, W 100k)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -81,6 +81,25 @@ def test_energy_forces_match_reference(name):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["calc_w8_pbc", "calc_syn_w128_model23", "calc_w_trimer"])
+def test_owner_computes_force_scheme(name, monkeypatch):
+    """UF3B_DETERMINISTIC_FORCES selects the atomics-free scheme of k_energy_forces: same
+    parity bar, and bit-identical forces run to run."""
+    monkeypatch.setenv("UF3B_DETERMINISTIC_FORCES", "1")
+    case = gu.Case(name)
+    _, eng, _ = _engine_for(case)
+    eng.set_coefficients(case["coefficients"])
+    e, f = eng.energy_forces()
+    e2, f2 = eng.energy_forces()
+    assert abs(e - float(case["energy"])) <= REL * abs(float(case["energy"]))
+    assert gu.rel_err(f, case["forces"]) <= REL
+    assert e == e2 and np.array_equal(f, f2)
+    monkeypatch.delenv("UF3B_DETERMINISTIC_FORCES")
+    _, f_newton = eng.energy_forces()
+    assert gu.rel_err(f_newton, f) <= 1e-12
+    eng.close()
+
+
 def test_reference_known_answers():
     """tests/test_calculator.py:40-50, :109-114 of the reference (values as printed there)."""
     case = gu.Case("calc_w_dimer_free")

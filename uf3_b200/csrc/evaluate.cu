@@ -8,6 +8,15 @@
 // coefficient grid, and the atom's force is reduced across the warp with shuffles.
 // As in the reference, no trimming is applied at evaluation time: trimmed basis
 // functions carry zero coefficients (calculator.py:207,286,565-571).
+//
+// Two force schemes share the code.  NEWTON (default): every triangle is evaluated once,
+// by its centre, and the reactions on the two neighbours are added to their parent atoms
+// with float64 atomics (red.global.add.f64) — a third of the work; the summation order of
+// those atomics varies from run to run at the 1e-16 level.  Owner-computes
+// (UF3B_DETERMINISTIC_FORCES=1): each atom also visits the triangles of the centres in
+// its list and adds only its own share — no atomics, bit-reproducible, 3x the triangles.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "geom.cuh"
 #include "spline.cuh"
@@ -16,11 +25,12 @@
 namespace uf3b {
 
 // value and the three leg-partials of  sum_pqr C[il+p, im+q, in+r] Bl_p Bm_q Bn_r
-__device__ __forceinline__ void contract(const double *__restrict__ grid, const Triangle &T,
+template <class Ptr>
+__device__ __forceinline__ void contract(Ptr grid, const Triangle &T,
                                          double &val, double &gl, double &gm, double &gn) {
     val = gl = gm = gn = 0.0;
     const int mn = T.dim_m * T.dim_n;
-    const double *base = grid + (T.il * T.dim_m + T.im) * T.dim_n + T.in;
+    const double *base = grid + (T.il * T.dim_m + T.im) * T.dim_n + T.in;   // global or shared
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         double u0 = 0.0, u1 = 0.0, u2 = 0.0;
@@ -30,7 +40,7 @@ __device__ __forceinline__ void contract(const double *__restrict__ grid, const 
             double t0 = 0.0, t1 = 0.0;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const double c = __ldg(row + r);
+                const double c = row[r];
                 t0 += c * T.v[2][r];
                 t1 += c * T.dv[2][r];
             }
@@ -47,10 +57,19 @@ __device__ __forceinline__ void contract(const double *__restrict__ grid, const 
 
 constexpr int EV_WARPS = 4;
 
-__global__ void __launch_bounds__(EV_WARPS * 32)
-k_energy_forces(const BasisTab B, const FrameView f, double *__restrict__ forces,
-                double *__restrict__ e_partials, int want_e_, int want_f_) {
+// grid_in_smem: the decompressed coefficient grids (n_grid doubles) are staged in shared
+// memory once per block.
+template <bool NEWTON>
+__global__ void __launch_bounds__(EV_WARPS * 32, 4)
+k_energy_forces(const BasisTab B, const FrameView f, double *forces,
+                double *__restrict__ e_partials, int want_e_, int want_f_, int n_grid, int grid_in_smem) {
     __shared__ RoleViews s_views[EV_WARPS];
+    extern __shared__ __align__(16) double s_grid[];
+    if (grid_in_smem) {
+        for (int k = threadIdx.x; k < n_grid; k += blockDim.x) s_grid[k] = B.c_grid[k];
+        __syncthreads();
+    }
+    const double *c_grid = grid_in_smem ? s_grid : B.c_grid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * EV_WARPS + warp, n_gw = gridDim.x * EV_WARPS;
     const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
@@ -101,13 +120,25 @@ k_energy_forces(const BasisTab B, const FrameView f, double *__restrict__ forces
                                    0, 0, T))
                     continue;
                 double val, gl, gm, gn;
-                contract(B.c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
+                contract(c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
                 e_acc += val;
                 fx += gl * T.A[0] + gm * T.B[0];
                 fy += gl * T.A[1] + gm * T.B[1];
                 fz += gl * T.A[2] + gm * T.B[2];
+                if (NEWTON && want_f) {
+                    // reactions: F_j = -gl u_ij + gn u_jk, F_k = -gm u_ik - gn u_jk, added to
+                    // the parent atoms of j and k; (A, B) hold (u_ij, u_ik), u_jk is rebuilt
+                    // from the positions the triangle was evaluated at
+                    double *fj = forces + 3 * (size_t)T.atom_j, *fk = forces + 3 * (size_t)T.atom_k;
+                    atomicAdd(fj + 0, -gl * T.A[0] + gn * T.ujk[0]);
+                    atomicAdd(fj + 1, -gl * T.A[1] + gn * T.ujk[1]);
+                    atomicAdd(fj + 2, -gl * T.A[2] + gn * T.ujk[2]);
+                    atomicAdd(fk + 0, -gm * T.B[0] - gn * T.ujk[0]);
+                    atomicAdd(fk + 1, -gm * T.B[1] - gn * T.ujk[1]);
+                    atomicAdd(fk + 2, -gm * T.B[2] - gn * T.ujk[2]);
+                }
             }
-            if (want_f) {
+            if (!NEWTON && want_f) {
                 for (int vbase = 0; vbase < n3a; vbase += 32) {
                     const int total = publish_views(B, f, a, vbase, n3a, lane, views);
                     for (int it = lane; it < total; it += 32) {
@@ -121,7 +152,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *__restrict__ forces
                                            first ? mk : apr, first ? 1 : 2, 0, 0, T))
                             continue;
                         double val, gl, gm, gn;
-                        contract(B.c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
+                        contract(c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
                         fx += gl * T.A[0] + gm * T.B[0] + gn * T.C[0];
                         fy += gl * T.A[1] + gm * T.B[1] + gn * T.C[1];
                         fz += gl * T.A[2] + gm * T.B[2] + gn * T.C[2];
@@ -135,9 +166,15 @@ k_energy_forces(const BasisTab B, const FrameView f, double *__restrict__ forces
             fy = warp_sum(fy);
             fz = warp_sum(fz);
             if (lane == 0) {
-                forces[3 * (size_t)a + 0] = fx;
-                forces[3 * (size_t)a + 1] = fy;
-                forces[3 * (size_t)a + 2] = fz;
+                if (NEWTON) {       // other centres add their reactions to this atom concurrently
+                    atomicAdd(forces + 3 * (size_t)a + 0, fx);
+                    atomicAdd(forces + 3 * (size_t)a + 1, fy);
+                    atomicAdd(forces + 3 * (size_t)a + 2, fz);
+                } else {
+                    forces[3 * (size_t)a + 0] = fx;
+                    forces[3 * (size_t)a + 1] = fy;
+                    forces[3 * (size_t)a + 2] = fz;
+                }
             }
         }
     }
@@ -183,8 +220,15 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
         }
         return UF3B_OK;
     }
+    const bool deterministic = getenv("UF3B_DETERMINISTIC_FORCES") != nullptr;
+    const bool newton = !deterministic && basis->tab.n_trios > 0;
+    auto kernel = newton ? k_energy_forces<true> : k_energy_forces<false>;
+    const int n_grid = basis->n_bins;
+    const size_t grid_bytes = sizeof(double) * (size_t)n_grid;
+    const int grid_in_smem = (n_grid > 0 && grid_bytes <= 48 * 1024) ? 1 : 0;
+    const size_t smem = grid_in_smem ? grid_bytes : 0;
     int per_sm = 1;
-    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_energy_forces, EV_WARPS * 32, 0));
+    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EV_WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count() * per_sm;
     const int need = (n + EV_WARPS - 1) / EV_WARPS;
@@ -208,8 +252,9 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
         UF3B_CUDA(cudaEventCreate(&ev1));
         UF3B_CUDA(cudaEventRecord(ev0, stream));
     }
-    UF3B_LAUNCH(k_energy_forces, grid, EV_WARPS * 32, 0, stream, basis->tab, view, d_f,
-                basis->partials.p, energy ? 1 : 0, forces ? 1 : 0);
+    if (newton && forces) UF3B_CUDA(cudaMemsetAsync(d_f, 0, sizeof(double) * 3 * (size_t)n, stream));
+    UF3B_LAUNCH(kernel, grid, EV_WARPS * 32, smem, stream, basis->tab, view, d_f,
+                basis->partials.p, energy ? 1 : 0, forces ? 1 : 0, n_grid, grid_in_smem);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (energy) UF3B_LAUNCH(k_energy_sum, 1, 256, 0, stream, basis->partials.p, n_gw, d_e);
     bool need_sync = g_timing;

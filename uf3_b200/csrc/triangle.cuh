@@ -25,6 +25,8 @@ struct Triangle {
     int il, im, in;             // first basis index per leg
     int dim_m, dim_n;           // grid extents of legs m and n
     int lo[3], cnt[3];          // untrimmed part [lo, lo+cnt) of each leg's 4 basis functions
+    double ujk[3];              // unit vector j -> k (after the atomic-number reordering)
+    int atom_j, atom_k;         // parent atoms of j and k (after the reordering)
 };
 
 // role: 0 = `a` is the centre, 1 = `a` is the neighbour with supercell index mj,
@@ -41,6 +43,7 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
         Vec3 tp = pj; pj = pk; pk = tp;
         double td = dij; dij = dik; dik = td;
         int ts = sj; sj = sk; sk = ts;
+        ts = aj; aj = ak; ak = ts;
         role = role == 1 ? 2 : (role == 2 ? 1 : 0);
     }
     const int t = sc * B.n_pairs + pair_index(B.ne, sj, sk);
@@ -75,8 +78,11 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
     const double uij[3] = {(pj.x - pc.x) * il_, (pj.y - pc.y) * il_, (pj.z - pc.z) * il_};
     const double uik[3] = {(pk.x - pc.x) * im_, (pk.y - pc.y) * im_, (pk.z - pc.z) * im_};
     const double ujk[3] = {(pk.x - pj.x) * in_, (pk.y - pj.y) * in_, (pk.z - pj.z) * in_};
+    T.atom_j = aj;
+    T.atom_k = ak;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        T.ujk[c] = ujk[c];
         // angles.py:282-285 then force_grids -= grids (:229-231), per participating atom
         T.A[c] = role == 0 ? uij[c] : (role == 1 ? -uij[c] : 0.0);
         T.B[c] = role == 0 ? uik[c] : (role == 2 ? -uik[c] : 0.0);
