@@ -150,6 +150,6 @@ struct uf3b_nlist {
     uf3b::DevBuf<int> cell_of, cell_start, cell_cursor;
     uf3b::DevBuf<uf3b::Slot> slots;
     uf3b::DevBuf<double> misc;     // bbox (6) on device
-    uf3b::DevBuf<long long> totals;
+    uf3b::DevBuf<long long> totals, tile_sums;
     uf3b::FrameView view() const;
 };

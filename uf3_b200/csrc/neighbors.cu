@@ -27,7 +27,27 @@ struct GridParams {
     int nx, ny, nz;
 };
 
-// species lookup + bounding box of the real atoms (one block).
+__device__ __forceinline__ void atomic_min_f64(double *addr, double v) {
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *p, assumed;
+    do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) <= v) break;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *p, assumed;
+    do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) >= v) break;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+
+// species lookup + bounding box of the real atoms.  bbox must hold (+inf x3, -inf x3) on
+// entry; every block folds its partial box in with six atomics.
 __global__ void __launch_bounds__(1024) k_prepare(int n, const int *__restrict__ z,
                                                   const int *__restrict__ z_to_spec,
                                                   const double *__restrict__ pos,
@@ -36,7 +56,7 @@ __global__ void __launch_bounds__(1024) k_prepare(int n, const int *__restrict__
     __shared__ double red[6][32];
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     int bad = 0;
-    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
         const int zz = z[a];
         const int s = (zz >= 0 && zz < 128) ? z_to_spec[zz] : -1;
         spec[a] = s < 0 ? 0 : s;
@@ -65,7 +85,7 @@ __global__ void __launch_bounds__(1024) k_prepare(int n, const int *__restrict__
                 l = fmin(l, __shfl_xor_sync(FULL, l, s));
                 h = fmax(h, __shfl_xor_sync(FULL, h, s));
             }
-            if (lane == 0) { bbox[c] = l; bbox[3 + c] = h; }
+            if (lane == 0) { atomic_min_f64(bbox + c, l); atomic_max_f64(bbox + 3 + c, h); }
         }
     }
 }
@@ -166,6 +186,92 @@ __global__ void __launch_bounds__(1024) k_scan(const int *in0, int *out0, const 
         out[n] = (int)carry;
         totals[blockIdx.x] = carry;
     }
+}
+
+// Three-kernel scan for long arrays (blockIdx.y selects the array): tile-local exclusive
+// scans + tile totals, a one-block scan of the totals, then the tile offsets are added.
+constexpr int SCAN_TILE = 1024 * SCAN_ITEMS;
+__global__ void __launch_bounds__(1024) k_scan_local(const int *in0, int *out0, const int *in1, int *out1,
+                                                     int n, long long *tile_sums, int n_tiles) {
+    const int *in = blockIdx.y ? in1 : in0;
+    int *out = blockIdx.y ? out1 : out0;
+    __shared__ long long warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i0 = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int vals[SCAN_ITEMS];
+    long long local = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        vals[k] = (i0 + k < n) ? in[i0 + k] : 0;
+        local += vals[k];
+    }
+    long long inc = local;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const long long up = __shfl_up_sync(FULL, inc, s);
+        if (lane >= s) inc += up;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = warp_tot[lane];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const long long up = __shfl_up_sync(FULL, w, s);
+            if (lane >= s) w += up;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    long long excl = inc - local + (warp ? warp_tot[warp - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (i0 + k < n) out[i0 + k] = (int)excl;
+        excl += vals[k];
+    }
+    if (threadIdx.x == 0) tile_sums[(size_t)blockIdx.y * n_tiles + blockIdx.x] = warp_tot[31];
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(long long *tile_sums, int n_tiles, int *out0, int *out1,
+                                                     int n, long long *totals) {
+    long long *sums = tile_sums + (size_t)blockIdx.x * n_tiles;
+    int *out = blockIdx.x ? out1 : out0;
+    __shared__ long long warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long v = (int)threadIdx.x < n_tiles ? sums[threadIdx.x] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const long long up = __shfl_up_sync(FULL, inc, s);
+        if (lane >= s) inc += up;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = warp_tot[lane];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const long long up = __shfl_up_sync(FULL, w, s);
+            if (lane >= s) w += up;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n_tiles) sums[threadIdx.x] = inc - v + (warp ? warp_tot[warp - 1] : 0);
+    if (threadIdx.x == 0) {
+        out[n] = (int)warp_tot[31];
+        totals[blockIdx.x] = warp_tot[31];
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(int *out0, int *out1, int n, const long long *tile_sums,
+                                                   int n_tiles) {
+    int *out = blockIdx.y ? out1 : out0;
+    const long long off = tile_sums[(size_t)blockIdx.y * n_tiles + blockIdx.x];
+    const long long i0 = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (i0 + k < n) out[i0 + k] += (int)off;
 }
 
 // Row of `n` distinct ints: out[rank(v)] = v.
@@ -313,6 +419,22 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
 
 using namespace uf3b;
 
+// Exclusive scan of one or two int arrays of length n on `stream` (out[n] = total).
+static int scan_arrays(uf3b_nlist *nl, int n_arrays, const int *in0, int *out0, const int *in1, int *out1,
+                       int n, long long *totals, cudaStream_t stream) {
+    const int n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (n_tiles <= 1 || n_tiles > 1024) {
+        UF3B_LAUNCH(k_scan, n_arrays, 1024, 0, stream, in0, out0, in1, out1, n, totals);
+        return UF3B_OK;
+    }
+    UF3B_CUDA(nl->tile_sums.reserve(2 * (size_t)n_tiles));
+    UF3B_LAUNCH(k_scan_local, dim3(n_tiles, n_arrays), 1024, 0, stream, in0, out0, in1, out1, n,
+                nl->tile_sums.p, n_tiles);
+    UF3B_LAUNCH(k_scan_tiles, n_arrays, 1024, 0, stream, nl->tile_sums.p, n_tiles, out0, out1, n, totals);
+    UF3B_LAUNCH(k_scan_add, dim3(n_tiles, n_arrays), 1024, 0, stream, out0, out1, n, nl->tile_sums.p, n_tiles);
+    return UF3B_OK;
+}
+
 FrameView uf3b_nlist::view() const {
     FrameView f;
     f.n = (int)n;
@@ -388,8 +510,10 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     UF3B_CUDA(cudaMemcpyAsync(nl->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyDefault, stream));
     UF3B_CUDA(cudaMemcpyAsync(nl->z.p, atomic_numbers, sizeof(int) * n, cudaMemcpyDefault, stream));
     int *d_err = (int *)(nl->misc.p + 6);
-    UF3B_CUDA(cudaMemsetAsync(d_err, 0, sizeof(double), stream));
-    UF3B_LAUNCH(k_prepare, 1, 1024, 0, stream, n, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
+    static const double bbox_init[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0};
+    UF3B_CUDA(cudaMemcpyAsync(nl->misc.p, bbox_init, sizeof bbox_init, cudaMemcpyHostToDevice, stream));
+    const int prep_blocks = std::min((n + 1023) / 1024, sm_count());
+    UF3B_LAUNCH(k_prepare, prep_blocks, 1024, 0, stream, n, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
                 nl->spec.p, nl->misc.p, d_err);
     double h_misc[7];
     UF3B_CUDA(cudaMemcpyAsync(h_misc, nl->misc.p, sizeof h_misc, cudaMemcpyDeviceToHost, stream));
@@ -424,8 +548,8 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     const int bin_blocks = (int)std::min<long long>((n_sup + 255) / 256, 148 * 16);
     UF3B_LAUNCH(k_bin_count, bin_blocks, 256, 0, stream, n, n_sup, nl->pos.p, nl->img_off.p, G,
                 nl->cell_of.p, nl->cell_start.p);
-    UF3B_LAUNCH(k_scan, 1, 1024, 0, stream, nl->cell_start.p, nl->cell_start.p, nullptr, nullptr,
-                (int)n_cell, nl->totals.p);
+    if (int rc = scan_arrays(nl, 1, nl->cell_start.p, nl->cell_start.p, nullptr, nullptr, (int)n_cell,
+                             nl->totals.p, stream)) return rc;
     // every supercell atom that survives the box test has a slot; n_sup bounds it
     UF3B_CUDA(nl->slots.reserve((size_t)n_sup));
     UF3B_LAUNCH(k_bin_fill, bin_blocks, 256, 0, stream, n, n_sup, nl->pos.p, nl->img_off.p,
@@ -435,7 +559,7 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     UF3B_LAUNCH(k_neighbors<false>, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G,
                 nl->slots.p, nl->cell_start.p, n, cnt2, cnt3, nullptr, nullptr, nullptr, nullptr,
                 nullptr, nullptr);
-    UF3B_LAUNCH(k_scan, 2, 1024, 0, stream, cnt2, nl->off2.p, cnt3, nl->off3.p, n, nl->totals.p + 1);
+    if (int rc = scan_arrays(nl, 2, cnt2, nl->off2.p, cnt3, nl->off3.p, n, nl->totals.p + 1, stream)) return rc;
     long long h_tot[2];
     UF3B_CUDA(cudaMemcpyAsync(h_tot, nl->totals.p + 1, sizeof h_tot, cudaMemcpyDeviceToHost, stream));
     UF3B_CUDA(cudaStreamSynchronize(stream));
