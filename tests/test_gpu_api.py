@@ -167,6 +167,19 @@ def test_device_gram_equals_host_gram_and_fit():
     dev.close()
 
 
+def test_frame_pipeline_matches_single_frame_calls():
+    from uf3_b200 import pipeline
+    names = ["syn_w16_demo", "syn_w54_demo", "syn_w36_slab", "syn_w128_demo", "syn_w16_demo"]
+    cases = [gu.Case(n) for n in names]
+    feat = BasisFeaturizer(cases[0].basis())
+    got = list(pipeline.featurize_frames(feat, [c.atoms() for c in cases]))
+    assert len(got) == len(cases)
+    for case, (xe, xf) in zip(cases, got):
+        assert np.allclose(xe, case["x_energy"], rtol=1e-5, atol=1e-8)
+        assert xf.shape == case["x_forces"].shape
+        assert np.allclose(xf, case["x_forces"], rtol=1e-5, atol=1e-8)
+
+
 def test_accumulate_frames_sharded():
     """uf3_b200.distributed.accumulate_frames on one GPU: the two shards add up to the whole."""
     from uf3_b200 import distributed

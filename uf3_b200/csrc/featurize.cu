@@ -17,6 +17,8 @@
 //           block of non-zero basis products and adds them into the compressed column
 //           of each bin.  Bins that fold onto the same column under the trio's
 //           permutation symmetry are applied in separate phases.
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -575,7 +577,10 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    int grid = sm_count() * per_sm;
+    // `waves` resident grids: 1 = persistent blocks; more lets blocks retire during the launch,
+    // so kernels of another stream (the next frame's list build) can be scheduled in between
+    static const int waves = getenv("UF3B_GRID_WAVES") ? std::max(1, atoi(getenv("UF3B_GRID_WAVES"))) : 1;
+    int grid = sm_count() * per_sm * waves;
     const int need = (n + warps - 1) / warps;
     if (grid > need) grid = need;
     const int n_gw = grid * warps;

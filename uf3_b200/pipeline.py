@@ -1,0 +1,119 @@
+"""Frame pipeline: feature rows of a stream of configurations with the device→host copy of
+frame k overlapped with the kernels of frame k+1.
+
+The reference produces one frame at a time and hands numpy rows to pandas
+(`process.py:121-174`).  On the GPU the rows of a 10 000-atom frame are 17.5 MB (F = 73) to
+110 MB (F = 456); copying them out synchronously costs 25–60 % of the step.  `FramePipeline`
+keeps `depth` slots, each with its own engine (neighbour-list handle), compute stream, row
+buffer on the device and pinned buffer on the host: the kernels of a frame run on the slot's
+stream through the device-pointer form of the C ABI (`uf3b_neighbors_build`,
+`uf3b_featurize`), a copy stream moves the finished rows out, and while the host waits on
+the two small read-backs inside one frame's list build the GPU runs the other slot's feature
+kernel.  torch is used for streams, events and pinned / device buffers only.
+"""
+import numpy as np
+import torch
+
+from uf3_b200 import geometry
+
+
+class FramePipeline:
+    def __init__(self, basis, max_atoms, device=None, forces=True, depth=2):
+        from uf3_b200.engine import Engine
+        index = torch.cuda.current_device() if device is None else int(device)
+        self.engines = [Engine(basis, device=index) for _ in range(depth)]
+        self.F = self.engines[0].n_feats
+        self.max_atoms = int(max_atoms)
+        self.forces = forces
+        self.dev = torch.device("cuda", index)
+        self.compute = [torch.cuda.Stream(self.dev) for _ in range(depth)]
+        self.copy = torch.cuda.Stream(self.dev)
+        self.depth = depth
+        rows = 3 * self.max_atoms if forces else 0
+        self.d_xf = [torch.empty((rows, self.F), dtype=torch.float64, device=self.dev) for _ in range(depth)]
+        self.d_xe = [torch.empty(self.F, dtype=torch.float64, device=self.dev) for _ in range(depth)]
+        self.h_xf = [torch.empty((rows, self.F), dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.h_xe = [torch.empty(self.F, dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.d_pos = [torch.empty((self.max_atoms, 3), dtype=torch.float64, device=self.dev) for _ in range(depth)]
+        self.d_num = [torch.empty(self.max_atoms, dtype=torch.int32, device=self.dev) for _ in range(depth)]
+        self.computed = [torch.cuda.Event() for _ in range(depth)]
+        self.copied = [torch.cuda.Event() for _ in range(depth)]
+        self.n_atoms = [0] * depth
+        self.busy = [False] * depth
+        self.turn = 0
+
+    def submit(self, positions, numbers, images):
+        """Queue one frame (host arrays, ideally pinned); returns the slot to read it from.
+        `images` = geometry.image_table(cell, pbc, r_cut)."""
+        slot = self.turn
+        self.turn = (self.turn + 1) % self.depth
+        n = len(positions)
+        if n > self.max_atoms:
+            raise ValueError("frame larger than the pipeline's max_atoms")
+        if self.busy[slot]:
+            self.copied[slot].synchronize()          # rows of the previous user of this slot are out
+        self.busy[slot] = True
+        self.n_atoms[slot] = n
+        compute, eng = self.compute[slot], self.engines[slot]
+        with torch.cuda.stream(compute):
+            self.d_pos[slot][:n].copy_(torch.from_numpy(positions), non_blocking=True)
+            self.d_num[slot][:n].copy_(torch.from_numpy(numbers), non_blocking=True)
+            stream = compute.cuda_stream
+            eng.build_neighbors_device(self.d_pos[slot].data_ptr(), self.d_num[slot].data_ptr(), n,
+                                       images, stream)
+            eng.featurize_device(self.d_xe[slot].data_ptr(),
+                                 self.d_xf[slot].data_ptr() if self.forces else None, self.F, stream)
+            self.computed[slot].record(compute)
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.computed[slot])
+            if self.forces:
+                self.h_xf[slot][:3 * n].copy_(self.d_xf[slot][:3 * n], non_blocking=True)
+            self.h_xe[slot].copy_(self.d_xe[slot], non_blocking=True)
+            self.copied[slot].record(self.copy)
+        return slot
+
+    def result(self, slot):
+        """(x_energy [F], x_forces [3N, F]) views of the pinned buffers of `slot`; valid until
+        the slot is reused `depth` submissions later."""
+        self.copied[slot].synchronize()
+        n = self.n_atoms[slot]
+        xf = self.h_xf[slot][:3 * n].numpy() if self.forces else None
+        return self.h_xe[slot].numpy(), xf
+
+    def drain(self):
+        for slot in range(self.depth):
+            if self.busy[slot]:
+                self.copied[slot].synchronize()
+
+    def launch_count(self):
+        return self.engines[0].launch_count()
+
+    def close(self):
+        self.drain()
+        for eng in self.engines:
+            eng.close()
+
+
+def featurize_frames(featurizer, frames, max_atoms=None):
+    """Generator of (x_energy, x_forces) copies for an iterable of geometries, pipelined."""
+    from uf3_b200.atoms import frame_arrays
+    frames = list(frames)
+    if not frames:
+        return
+    if max_atoms is None:
+        max_atoms = max(len(g) for g in frames)
+    pipe = FramePipeline(featurizer.bspline_config, max_atoms, device=featurizer.device,
+                         forces=featurizer.fit_forces)
+    pending = []
+    for geom in frames:
+        positions, numbers, cell, pbc = frame_arrays(geom)
+        images = geometry.image_table(cell, pbc, featurizer.r_cut) if np.any(pbc) else \
+            (np.zeros((1, 3), dtype=np.int64), np.zeros((1, 3)))
+        pending.append(pipe.submit(positions, numbers, images))
+        if len(pending) == pipe.depth:
+            xe, xf = pipe.result(pending.pop(0))
+            yield xe.copy(), (xf.copy() if xf is not None else None)
+    for slot in pending:
+        xe, xf = pipe.result(slot)
+        yield xe.copy(), (xf.copy() if xf is not None else None)
+    pipe.close()
