@@ -166,20 +166,27 @@ def test_energy_forces_match_oracle_mid_size():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["syn_w54_demo", "syn_w36_slab", "ref_ar3_default"])
-def test_register_tile_and_scatter_paths_agree(name, monkeypatch):
-    """Unary bases with a small untrimmed 3-body grid take the register-tile path of
-    k_featurize; UF3B_NO_TILE forces the general shared-memory scatter path."""
+@pytest.mark.parametrize("name", ["syn_w54_demo", "syn_w36_slab", "syn_w16_demo", "ref_ar3_default"])
+def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
+    """Unary bases with a small untrimmed 3-body grid take the leg-grouped tile path of
+    k_featurize (symmetry >= 2, rows <= 32), else the per-triangle register-tile path;
+    UF3B_NO_LEGS / UF3B_NO_TILE force the next more general path."""
     case = gu.Case(name)
-    _, eng, _ = _engine_for(case)
-    xe_tile, xf_tile = eng.featurize()
-    eng.close()
-    monkeypatch.setenv("UF3B_NO_TILE", "1")
-    _, eng, _ = _engine_for(case)
-    xe_scatter, xf_scatter = eng.featurize()
-    eng.close()
-    assert gu.rel_err(xe_tile, xe_scatter) <= 1e-12 and gu.rel_err(xf_tile, xf_scatter) <= 1e-12
-    assert gu.rel_err(xf_scatter, case["x_forces"]) <= REL
+    outs = []
+    for env in ({}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"}):
+        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        _, eng, _ = _engine_for(case)
+        outs.append(eng.featurize())
+        xe_only, _ = eng.featurize(energy=True, forces=False)
+        assert gu.rel_err(xe_only, outs[-1][0]) <= 1e-13
+        eng.close()
+    for xe, xf in outs:
+        assert gu.rel_err(xe, case["x_energy"]) <= REL
+        assert gu.rel_err(xf, case["x_forces"]) <= REL
+    assert gu.rel_err(outs[0][1], outs[2][1]) <= 1e-11 and gu.rel_err(outs[1][1], outs[2][1]) <= 1e-11
 
 
 def test_empty_and_single_atom():

@@ -144,6 +144,7 @@ struct uf3b_nlist {
     int64_t n = 0;
     int n_img = 0;
     int64_t total2 = 0, total3 = 0;
+    int max3 = 0;                  // longest row of the 3-body list
     uf3b::DevBuf<double> pos, img_off;
     uf3b::DevBuf<int> z, spec, img_inv;
     uf3b::DevBuf<int> off2, off3, idx2, idx3, scratch, cnt;

@@ -344,10 +344,170 @@ struct Tile {
     }
 };
 
+// ---------------------------------------------------------------- leg-grouped tile path
+// For a unary basis whose trio is symmetric in its two centre legs (symmetry >= 2: the l
+// and m legs share knots, so which neighbour is called l does not change the folded column),
+// the 3-body rows factor per LEG instead of per triangle:
+//   centre role    x_a += sum_j  u_aj  dB(r_aj)[l] * P_j[m,n],   P_j = sum_{k != j} B(r_ak)[m] B(r_jk)[n]
+//   energy         e   += sum_j        B(r_aj)[l]  * Pe_j[m,n],  Pe_j = same sum over k above j
+//   neighbour role x_a += -u_ia dB(r_ia)[l] * P[m,n] + B(r_ia)[l] * Q[m,n],
+//                  P = sum_k B(r_ik)[m] B(r_ak)[n],   Q = sum_k w_ak B(r_ik)[m] dB(r_ak)[n]
+// so the inner loop over partners k updates one or four scalars per lane (lane = (m, n) cell)
+// and the l dimension only appears once per leg group.  Phase A evaluates LEGS (one per
+// lane, dense by absolute basis index) instead of triangles: each leg is shared by all the
+// triangles of its group.  Requires every 3-body row involved to hold at most 32 entries.
+constexpr unsigned LG_LM = 96;          // leg (centre, x): V[4] DV[4] u[3] pad
+constexpr unsigned LG_N = 240;          // leg (x, y):      VN[12] DVN[12] w[3] pad
+constexpr unsigned LG_N_BASE = 32 * LG_LM;
+static_assert(LG_N_BASE + 32 * LG_N <= CHUNK * sizeof(TriRec), "leg caches must fit the scratch area");
+
+// One leg, dense: values / derivatives of the untrimmed basis functions [x0, x0+xa) at
+// d = |to - from| (zero when the leg is outside its knot range: the reference drops the
+// whole triangle, angles.py:502-508), and the unit vector from -> to.
+__device__ __forceinline__ void eval_dense_leg(const BasisTab &B, int leg, const Vec3 &from, const Vec3 &to,
+                                               int x0, int xa, int stride, unsigned char *out) {
+    double *val = reinterpret_cast<double *>(out), *der = val + stride, *uv = der + stride;
+    for (int k = 0; k < stride; ++k) { val[k] = 0.0; der[k] = 0.0; }
+    const double d = dist_rn(from, to);
+    const int nk = __ldg(B.trio_nk + leg);
+    const double *t = B.knots3 + __ldg(B.trio_koff + leg);
+    double inv = 0.0;
+    if (d >= t[0] && d <= t[nk - 1]) {
+        double v[4], dv[4];
+        const int idx = eval_leg(t, nk, __ldg(B.trio_scale + leg), B.poly3 + __ldg(B.trio_poff + leg), d,
+                                 B.lead3, B.trail3, v, dv);
+        if (idx >= 0) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int x = idx + p - x0;
+                if (x >= 0 && x < xa) { val[x] = v[p]; der[x] = dv[p]; }
+            }
+        }
+        inv = fast_rcp(d);
+    }
+    uv[0] = (to.x - from.x) * inv;
+    uv[1] = (to.y - from.y) * inv;
+    uv[2] = (to.z - from.z) * inv;
+}
+
+__device__ __forceinline__ void legs_three_body(const BasisTab &B, const FrameView &f, const TileGeom &g,
+                                                int a, const Vec3 &pa, unsigned char *scratch, unsigned scratch_s,
+                                                Tile<1> &tile, int lane, bool want_e, bool want_f) {
+    const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.off3 + a + 1) - row0;
+    if (n3a < 1) return;
+    const unsigned lm_s = scratch_s, nn_s = scratch_s + LG_N_BASE;
+    unsigned char *lm = scratch, *nn = scratch + LG_N_BASE;
+    const int cell = lane < g.ma * g.na ? lane : 0;
+    const unsigned off_m = 8u * (unsigned)(cell / g.na), off_n = 8u * (unsigned)(cell % g.na);
+    int dummy;
+
+    // ---- (i) `a` as the centre
+    if (lane < n3a)
+        eval_dense_leg(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0, g.la, 4,
+                       lm + lane * LG_LM);
+    __syncwarp();
+    const int np = n3a - 1;                       // partners per group
+    const int per_pass = np > 0 ? 32 / np : 32;   // groups per pass (n3a <= 32)
+    for (int g0 = 0; g0 < n3a && np > 0; g0 += per_pass) {
+        {   // phase A: legs (j, k) of up to per_pass groups, one per lane
+            const int gi = lane / np, s = lane - gi * np, j = g0 + gi;
+            if (gi < per_pass && j < n3a) {
+                const int k = s + (s >= j);
+                eval_dense_leg(B, 2, super_position(f, __ldg(f.idx3 + row0 + j), dummy),
+                               super_position(f, __ldg(f.idx3 + row0 + k), dummy), g.n0, g.na, 12,
+                               nn + lane * LG_N);
+            }
+        }
+        __syncwarp();
+        for (int gi = 0; gi < per_pass && g0 + gi < n3a; ++gi) {      // phase B: one group at a time
+            const int j = g0 + gi;
+            double P = 0.0, Pe = 0.0;
+            for (int s = 0; s < np; ++s) {
+                const int k = s + (s >= j);
+                const double vm = lds64(lm_s + (unsigned)k * LG_LM + off_m);
+                const double vn = lds64(nn_s + (unsigned)(gi * np + s) * LG_N + off_n);
+                P = fma(vm, vn, P);
+                if (k > j) Pe = fma(vm, vn, Pe);       // each unordered pair once for the energy row
+            }
+            const unsigned lj = lm_s + (unsigned)j * LG_LM;
+            const double2 u01 = lds128(lj + 64);
+            const double u2 = lds64(lj + 80);
+#pragma unroll
+            for (int l = 0; l < RT_LA; ++l) {
+                if (l < g.la) {
+                    const double v = lds64(lj + 8 * l), dP = lds64(lj + 32 + 8 * l) * P;
+                    if (want_e) tile.acc[0][l][0] = fma(v, Pe, tile.acc[0][l][0]);
+                    tile.acc[0][l][1] = fma(u01.x, dP, tile.acc[0][l][1]);
+                    tile.acc[0][l][2] = fma(u01.y, dP, tile.acc[0][l][2]);
+                    tile.acc[0][l][3] = fma(u2, dP, tile.acc[0][l][3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (!want_f) return;
+
+    // ---- (ii) `a` as a neighbour of every centre i in its list
+    for (int e = 0; e < n3a; ++e) {
+        const int m = __ldg(f.idx3 + row0 + e);
+        const int gimg = (int)((unsigned)m / (unsigned)f.n);
+        const int ci = m - gimg * f.n;
+        const int apr = __ldg(f.img_inv + gimg) * f.n + a;
+        const int rowi = __ldg(f.off3 + ci), ni = __ldg(f.off3 + ci + 1) - rowi;
+        const int mine = lane < ni ? __ldg(f.idx3 + rowi + lane) : -1;
+        const unsigned hit = __ballot_sync(FULL, mine == apr);
+        if (!hit) continue;                       // one-ulp asymmetry of the list criterion
+        const int qa = __ffs(hit) - 1;
+        const Vec3 pi = real_position(f, ci), pap = super_position(f, apr, dummy);
+        // phase A: legs (i, x) for the whole row of i, then legs (a', k) for k != a'
+        const int n_items = 2 * ni - 1;
+        for (int it0 = 0; it0 < n_items; it0 += 32) {
+            const int it = it0 + lane;
+            if (it < n_items) {                   // one call site: both leg kinds share the code
+                const bool centre_leg = it < ni;
+                const int s = it - ni, k = centre_leg ? it : s + (s >= qa);
+                eval_dense_leg(B, centre_leg ? 0 : 2, centre_leg ? pi : pap,
+                               super_position(f, __ldg(f.idx3 + rowi + k), dummy),
+                               centre_leg ? g.l0 : g.n0, centre_leg ? g.la : g.na, centre_leg ? 4 : 12,
+                               centre_leg ? lm + it * LG_LM : nn + s * LG_N);
+            }
+        }
+        __syncwarp();
+        double P = 0.0, Qx = 0.0, Qy = 0.0, Qz = 0.0;
+        for (int s = 0; s < ni - 1; ++s) {
+            const int k = s + (s >= qa);
+            const unsigned ns = nn_s + (unsigned)s * LG_N;
+            const double vm = lds64(lm_s + (unsigned)k * LG_LM + off_m);
+            const double vn = lds64(ns + off_n), dvn = lds64(ns + 96 + off_n);
+            const double2 w01 = lds128(ns + 192);
+            const double w2 = lds64(ns + 208);
+            P = fma(vm, vn, P);
+            const double t3 = vm * dvn;
+            Qx = fma(w01.x, t3, Qx);
+            Qy = fma(w01.y, t3, Qy);
+            Qz = fma(w2, t3, Qz);
+        }
+        const unsigned la_s = lm_s + (unsigned)qa * LG_LM;
+        const double2 u01 = lds128(la_s + 64);
+        const double u2 = lds64(la_s + 80);
+#pragma unroll
+        for (int l = 0; l < RT_LA; ++l) {
+            if (l < g.la) {
+                const double v = lds64(la_s + 8 * l), dP = lds64(la_s + 32 + 8 * l) * P;
+                tile.acc[0][l][1] += v * Qx - u01.x * dP;
+                tile.acc[0][l][2] += v * Qy - u01.y * dP;
+                tile.acc[0][l][3] += v * Qz - u2 * dP;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // GLOBAL_ACC: the per-warp accumulators [4 * n_feats] live in a global scratch buffer
 // (L1/L2 resident) instead of shared memory — the path for bases whose rows do not fit
 // (e.g. 18 trio interactions of a ternary system, F ~ 7000).
-// KP > 0 selects the register-tile path with KP (m, n) cells per lane.
+// KP = 1, 2 selects the register-tile path with KP (m, n) cells per lane; KP = 3 the
+// leg-grouped tile path.
 template <bool GLOBAL_ACC, int KP>
 __global__ void __launch_bounds__(256, 2)
 k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__restrict__ xf, long long ld,
@@ -369,7 +529,8 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
 
     for (int k = lane; k < 4 * F; k += 32) acc[k] = 0.0;
     __syncwarp();
-    Tile<(KP > 0 ? KP : 1)> tile;
+    constexpr bool LEGS = KP == 3;
+    Tile<((KP == 1 || KP == 2) ? KP : 1)> tile;
     if constexpr (KP > 0) tile.init(tg, lane);
 
     for (int a = gw; a < f.n; a += n_gw) {
@@ -434,7 +595,9 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
         }
 
         // ------------------------------------------------ 3-body (angles.py:17-286)
-        if (B.n_trios > 0) {
+        if constexpr (LEGS) {
+            legs_three_body(B, f, tg, a, pa, scratch, recs_s, tile, lane, want_e, want_f);
+        } else if (B.n_trios > 0) {
             const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.off3 + a + 1) - row0;
             // (i) `a` as the centre: every j<k pair of its own list
             const int n_tri = n3a * (n3a - 1) / 2;
@@ -451,7 +614,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
                         else store_record(recs + lane, T, B, 0);
                 }
                 __syncwarp();
-                if constexpr (KP > 0) tile.accumulate(tg, recs_s, min(CHUNK, n_tri - t0), want_e);
+                if constexpr (KP == 1 || KP == 2) tile.accumulate(tg, recs_s, min(CHUNK, n_tri - t0), want_e);
                 else scatter_records(B, recs_s, min(CHUNK, n_tri - t0), acc_rw, lane, want_e);
                 __syncwarp();
             }
@@ -477,7 +640,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
                             }
                         }
                         __syncwarp();
-                        if constexpr (KP > 0) tile.accumulate(tg, recs_s, min(CHUNK, total - it0), false);
+                        if constexpr (KP == 1 || KP == 2) tile.accumulate(tg, recs_s, min(CHUNK, total - it0), false);
                         else scatter_records(B, recs_s, min(CHUNK, total - it0), acc_rw, lane, false);
                         __syncwarp();
                     }
@@ -570,9 +733,14 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         if (tg.la >= 1 && tg.la <= RT_LA && tg.ma >= 1 && tg.na >= 1 && tg.ma * tg.na <= 64
             && tg.ma + tg.na <= 12 && tg.sym >= 1 && tg.sym <= 3)
             kp = tg.ma * tg.na <= 32 ? 1 : 2;
+        // leg-grouped path: l and m legs interchangeable, every 3-body row fits one warp pass
+        if (kp == 1 && tg.sym >= 2 && tg.la == tg.ma && tg.na <= 12 && nl->max3 <= 32 && !getenv("UF3B_NO_LEGS"))
+            kp = 3;
     }
     auto kernel = global_acc ? k_featurize<true, 0>
-                             : (kp == 1 ? k_featurize<false, 1> : (kp == 2 ? k_featurize<false, 2> : k_featurize<false, 0>));
+                             : (kp == 1 ? k_featurize<false, 1>
+                                : (kp == 2 ? k_featurize<false, 2>
+                                   : (kp == 3 ? k_featurize<false, 3> : k_featurize<false, 0>)));
     UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));

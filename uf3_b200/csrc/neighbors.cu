@@ -320,7 +320,7 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
             const int *__restrict__ cell_start, int n_real, int *__restrict__ cnt2,
             int *__restrict__ cnt3, const int *__restrict__ off2, const int *__restrict__ off3,
             int *__restrict__ scratch2, int *__restrict__ scratch3, int *__restrict__ idx2,
-            int *__restrict__ idx3) {
+            int *__restrict__ idx3, int *__restrict__ max3) {
     __shared__ __align__(128) Slot tile[NL_TILE];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int run_lo[9], run_n[9], n_cand;
@@ -406,7 +406,7 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
             for (int r = 0; r < 9; ++r) visit(slots + run_lo[r], run_n[r]);
         }
         if (!FILL) {
-            if (lane == 0) { cnt2[c.m] = n2; cnt3[c.m] = n3; }
+            if (lane == 0) { cnt2[c.m] = n2; cnt3[c.m] = n3; atomicMax(max3, n3); }
         } else {
             __syncwarp();
             warp_rank_sort(scratch2 + base2, idx2 + base2, n2, lane);
@@ -472,6 +472,7 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     nl->n = n_atoms;
     nl->n_img = n_images;
     nl->total2 = nl->total3 = 0;
+    nl->max3 = 0;
 
     // periodic image table: pair every image with the one of negated coordinates
     std::vector<int> inv(n_images, 0);
@@ -556,23 +557,25 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
                 nl->spec.p, nl->cell_of.p, nl->cell_start.p, nl->cell_cursor.p, nl->slots.p);
 
     int *cnt2 = nl->cnt.p, *cnt3 = nl->cnt.p + n + 1;
+    UF3B_CUDA(cudaMemsetAsync(nl->totals.p + 3, 0, sizeof(long long), stream));
     UF3B_LAUNCH(k_neighbors<false>, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G,
                 nl->slots.p, nl->cell_start.p, n, cnt2, cnt3, nullptr, nullptr, nullptr, nullptr,
-                nullptr, nullptr);
+                nullptr, nullptr, (int *)(nl->totals.p + 3));
     if (int rc = scan_arrays(nl, 2, cnt2, nl->off2.p, cnt3, nl->off3.p, n, nl->totals.p + 1, stream)) return rc;
-    long long h_tot[2];
+    long long h_tot[3];     // list totals and the longest 3-body row
     UF3B_CUDA(cudaMemcpyAsync(h_tot, nl->totals.p + 1, sizeof h_tot, cudaMemcpyDeviceToHost, stream));
     UF3B_CUDA(cudaStreamSynchronize(stream));
     if (h_tot[0] >= (1LL << 31) || h_tot[1] >= (1LL << 31))
         return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
     nl->total2 = h_tot[0];
     nl->total3 = h_tot[1];
+    nl->max3 = (int)h_tot[2];
     UF3B_CUDA(nl->idx2.reserve((size_t)h_tot[0] + 1));
     UF3B_CUDA(nl->idx3.reserve((size_t)h_tot[1] + 1));
     UF3B_CUDA(nl->scratch.reserve((size_t)(h_tot[0] + h_tot[1]) + 2));
     UF3B_LAUNCH(k_neighbors<true>, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G,
                 nl->slots.p, nl->cell_start.p, n, nullptr, nullptr, nl->off2.p, nl->off3.p,
-                nl->scratch.p, nl->scratch.p + h_tot[0], nl->idx2.p, nl->idx3.p);
+                nl->scratch.p, nl->scratch.p + h_tot[0], nl->idx2.p, nl->idx3.p, nullptr);
     guard.armed = false;
     *inout = nl;
     return UF3B_OK;
