@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "bulk bcc W 10x20x25 cells (10000 atoms/frame), sigma=0.05 A, 2+3-body featurization"
-N_POOL = 4          # distinct frames per rank, cycled
+N_POOL = 8          # distinct frames (inputs AND output row buffers) per rank, cycled
 
 
 def load_peaks():
@@ -304,25 +304,28 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    # resident arm: two slots (engine + stream + output buffers each) alternate frames, so the
-    # GPU runs one frame's feature kernel while the host reads back the two sizing scalars
-    # of the other frame's list build.  Device time from the first step's start to the last
-    # step's end; every step is preceded by an L2 flush on its own stream.
-    slots = []
-    for _ in range(2):
-        e = Engine(basis, device=local_rank)
-        slots.append((e, torch.cuda.Stream(dev), torch.empty(F, dtype=torch.float64, device=dev),
-                      torch.empty((3 * n_atoms, F), dtype=torch.float64, device=dev)))
-    flushes = [torch.empty(256 << 20, dtype=torch.uint8, device=dev) for _ in range(2)]
+    # resident arm: two slots (engine + stream each) alternate frames, so the GPU can run one
+    # frame's kernels while the host reads back the two sizing scalars of the other frame's
+    # list build.  L2: every step reads its own frame and writes its own row buffer out of a
+    # pool of N_POOL; the pool (positions + rows) is larger than the 126 MB L2, so no step
+    # finds its data in cache and no explicit flush is needed.
+    slots = [(Engine(basis, device=local_rank), torch.cuda.Stream(dev)) for _ in range(2)]
+    out_pool = [(torch.empty(F, dtype=torch.float64, device=dev),
+                 torch.empty((3 * n_atoms, F), dtype=torch.float64, device=dev)) for _ in range(N_POOL)]
+    pool_bytes = N_POOL * (3 * n_atoms * F * 8 + n_atoms * 24)
+    while pool_bytes < 160e6:                      # small bases: pad the pool past the L2 size
+        out_pool.append((torch.empty(F, dtype=torch.float64, device=dev),
+                         torch.empty((3 * n_atoms, F), dtype=torch.float64, device=dev)))
+        pool_bytes += 3 * n_atoms * F * 8
 
     def timed(steps, warmup):
         main = torch.cuda.current_stream()
 
         def run(count, first):
             for k in range(count):
-                e, st, xe_k, xf_k = slots[k % 2]
+                e, st = slots[k % 2]
+                xe_k, xf_k = out_pool[(first + k) % len(out_pool)]
                 with torch.cuda.stream(st):
-                    flushes[k % 2].zero_()
                     e.build_neighbors_device(d_pos[(first + k) % N_POOL].data_ptr(), d_num.data_ptr(),
                                              n_atoms, images, st.cuda_stream)
                     e.featurize_device(xe_k.data_ptr(), xf_k.data_ptr(), F, st.cuda_stream)
@@ -332,10 +335,10 @@ def run_ours(args, rank, world, local_rank):
         launches0 = eng.launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(main)
-        for _, st, _, _ in slots:
+        for _, st in slots:
             st.wait_stream(main)
         run(steps, warmup)
-        for _, st, _, _ in slots:
+        for _, st in slots:
             main.wait_stream(st)
         stop.record(main)
         barrier()
@@ -399,7 +402,8 @@ def run_ours(args, rank, world, local_rank):
                    "frames_per_rank_pool": N_POOL, "pairs_per_atom": e2 / n_atoms,
                    "list3_per_atom": e3 / n_atoms,
                    "step": "neighbour lists + energy row + 3N force rows of one frame per rank",
-                   "l2": "flushed before every step (256 MiB memset on the step's stream, inside the timed region)",
+                   "l2": "inputs larger than L2: every step uses its own frame and row buffer out of a pool of "
+                         f"{len(out_pool)} ({pool_bytes / 1e6:.0f} MB > 126 MB L2); no explicit flush",
                    "streams": "two slots alternate frames (one engine + stream each)"},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "ms_per_step": e2e_ms / args.steps,
                 "how": "uf3_b200.pipeline.FramePipeline: pinned host positions in, rows read back on the "

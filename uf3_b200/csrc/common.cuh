@@ -113,8 +113,9 @@ struct FrameView {
     const int *spec;          // [n]
     const double *img_off;    // [n_img*3]
     const int *img_inv;       // [n_img] rank of the image with negated coordinates
-    const int *off2, *idx2;   // pair list CSR   (max(r_min,0) < d < r_max per pair)
-    const int *off3, *idx3;   // 3-body list CSR (r3min < d <= r3max)
+    // per-centre rows (start, count) into the index arrays; every row sorted by supercell index
+    const int *off2, *cnt2, *idx2;   // pair list   (max(r_min,0) < d < r_max per pair)
+    const int *off3, *cnt3, *idx3;   // 3-body list (r3min < d <= r3max)
 };
 
 }  // namespace uf3b
@@ -147,7 +148,7 @@ struct uf3b_nlist {
     int max3 = 0;                  // longest row of the 3-body list
     uf3b::DevBuf<double> pos, img_off;
     uf3b::DevBuf<int> z, spec, img_inv;
-    uf3b::DevBuf<int> off2, off3, idx2, idx3, scratch, cnt;
+    uf3b::DevBuf<int> off2, off3, cnt2, cnt3, idx2, idx3, scratch2, scratch3;
     uf3b::DevBuf<int> cell_of, cell_start, cell_cursor;
     uf3b::DevBuf<uf3b::Slot> slots;
     uf3b::DevBuf<double> misc;     // bbox (6) on device

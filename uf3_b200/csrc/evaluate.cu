@@ -83,7 +83,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
         if (lane == 0) e_acc += __ldg(B.coeff + sa);                    // calculator.py:183-189
 
         // ---- 2-body: E += S(r) per ordered pair; F_a = 2 sum_j S'(r_aj) (x_j - x_a)/r_aj
-        const int r0 = __ldg(f.off2 + a), r1 = __ldg(f.off2 + a + 1);
+        const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
         for (int e = r0 + lane; e < r1; e += 32) {
             int aj;
             const Vec3 pj = super_position(f, __ldg(f.idx2 + e), aj);
@@ -110,7 +110,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
 
         // ---- 3-body
         if (B.n_trios > 0) {
-            const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.off3 + a + 1) - row0;
+            const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
             const int n_tri = n3a * (n3a - 1) / 2;
             for (int t = lane; t < n_tri; t += 32) {
                 int qj, qk;

@@ -393,7 +393,7 @@ __device__ __forceinline__ void eval_dense_leg(const BasisTab &B, int leg, const
 __device__ __forceinline__ void legs_three_body(const BasisTab &B, const FrameView &f, const TileGeom &g,
                                                 int a, const Vec3 &pa, unsigned char *scratch, unsigned scratch_s,
                                                 Tile<1> &tile, int lane, bool want_e, bool want_f) {
-    const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.off3 + a + 1) - row0;
+    const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
     if (n3a < 1) return;
     const unsigned lm_s = scratch_s, nn_s = scratch_s + LG_N_BASE;
     unsigned char *lm = scratch, *nn = scratch + LG_N_BASE;
@@ -453,7 +453,7 @@ __device__ __forceinline__ void legs_three_body(const BasisTab &B, const FrameVi
         const int gimg = (int)((unsigned)m / (unsigned)f.n);
         const int ci = m - gimg * f.n;
         const int apr = __ldg(f.img_inv + gimg) * f.n + a;
-        const int rowi = __ldg(f.off3 + ci), ni = __ldg(f.off3 + ci + 1) - rowi;
+        const int rowi = __ldg(f.off3 + ci), ni = __ldg(f.cnt3 + ci);
         const int mine = lane < ni ? __ldg(f.idx3 + rowi + lane) : -1;
         const unsigned hit = __ballot_sync(FULL, mine == apr);
         if (!hit) continue;                       // one-ulp asymmetry of the list criterion
@@ -536,10 +536,12 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
     for (int a = gw; a < f.n; a += n_gw) {
         const int sa = __ldg(f.spec + a);
         const Vec3 pa = real_position(f, a);
+        if (lane == 0) acc[4 * sa] += 1.0;      // composition column n_el (composition.py:96-111)
+        __syncwarp();
 
         // ------------------------------------------------ 2-body (bspline.py:810-895)
         {
-            const int r0 = __ldg(f.off2 + a), r1 = __ldg(f.off2 + a + 1);
+            const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
             for (int base = r0; base < r1; base += CHUNK) {
                 const int e = base + lane;
                 PairRec rec;
@@ -598,7 +600,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
         if constexpr (LEGS) {
             legs_three_body(B, f, tg, a, pa, scratch, recs_s, tile, lane, want_e, want_f);
         } else if (B.n_trios > 0) {
-            const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.off3 + a + 1) - row0;
+            const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
             // (i) `a` as the centre: every j<k pair of its own list
             const int n_tri = n3a * (n3a - 1) / 2;
             for (int t0 = 0; t0 < n_tri; t0 += CHUNK) {
@@ -667,25 +669,25 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
 }
 
 // Energy row = element counts (composition.py:96-111) + fixed-order sum of the warps'
-// partial rows.  One block per feature column.
+// partial rows.  One block per 32 feature columns: warp w sums rows w, w+8, ... with
+// coalesced reads, then the eight per-warp sums are added in a fixed order.
 __global__ void __launch_bounds__(256)
 k_energy_row(const double *__restrict__ partials, int n_rows, int n_feats, int ne,
              const int *__restrict__ spec, int n, double *__restrict__ xe) {
-    __shared__ double red[256];
-    const int col = blockIdx.x;
+    __shared__ double red[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
     double s = 0.0;
-    if (col < ne) {
-        for (int a = threadIdx.x; a < n; a += blockDim.x) s += (spec[a] == col) ? 1.0 : 0.0;
-    } else {
-        for (int r = threadIdx.x; r < n_rows; r += blockDim.x) s += partials[(size_t)r * n_feats + col];
-    }
-    red[threadIdx.x] = s;
+    if (col < n_feats)      // the element-count columns were accumulated by k_featurize as well
+        for (int r = warp; r < n_rows; r += 8) s += partials[(size_t)r * n_feats + col];
+    red[warp][lane] = s;
     __syncthreads();
-    for (int h = 128; h > 0; h >>= 1) {
-        if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
-        __syncthreads();
+    if (warp == 0 && col < n_feats) {
+        double t = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += red[w][lane];
+        xe[col] = t;
     }
-    if (threadIdx.x == 0) xe[col] = red[0];
 }
 
 }  // namespace uf3b
@@ -780,7 +782,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                 basis->partials.p, basis->gacc.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (x_energy)
-        UF3B_LAUNCH(k_energy_row, F, 256, 0, stream, basis->partials.p, n_gw, F, basis->tab.ne,
+        UF3B_LAUNCH(k_energy_row, (F + 31) / 32, 256, 0, stream, basis->partials.p, n_gw, F, basis->tab.ne,
                     view.spec, n, d_xe);
     bool need_sync = g_timing;
     if (x_forces && !f_dev) {

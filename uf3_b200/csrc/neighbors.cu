@@ -309,21 +309,27 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     } while (!done);
 }
 
+constexpr int NL_BUF2 = 160, NL_BUF3 = 96;     // hits buffered per centre before the row is placed
+
 // Block = one cell, warp = one real centre of that cell.  The slots of the 3x3x3 block of
 // cells around it are 9 contiguous z-runs in the binned array; one thread stages them into
 // shared memory with 9 TMA bulk copies tracked by an mbarrier, and every warp then sweeps
-// the staged tile 32 candidates at a time.  FILL=false counts, FILL=true writes the hits
-// (ballot-compacted) and sorts each row by supercell index.
-template <bool FILL>
+// the staged tile 32 candidates at a time.  One pass: hits are ballot-compacted into a
+// per-warp shared buffer, the row's place in the index array is claimed with one atomicAdd
+// per list, and the row is written sorted by supercell index.  Rows are contiguous but
+// appear in claim order: the lists are (start, count) per centre.  If the arrays are too
+// small the claims still count, `status[2]` is raised and the host grows them and reruns.
+//   status: [0] entries claimed in list 2, [1] in list 3, [2] overflow, [3] longest list-3 row
 __global__ void __launch_bounds__(NL_WARPS * 32)
 k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots,
-            const int *__restrict__ cell_start, int n_real, int *__restrict__ cnt2,
-            int *__restrict__ cnt3, const int *__restrict__ off2, const int *__restrict__ off3,
-            int *__restrict__ scratch2, int *__restrict__ scratch3, int *__restrict__ idx2,
-            int *__restrict__ idx3, int *__restrict__ max3) {
+            const int *__restrict__ cell_start, int n_real, int *__restrict__ off2,
+            int *__restrict__ cnt2, int *__restrict__ off3, int *__restrict__ cnt3,
+            int *__restrict__ idx2, int *__restrict__ idx3, int *__restrict__ scratch2,
+            int *__restrict__ scratch3, int cap2, int cap3, int *__restrict__ status) {
     __shared__ __align__(128) Slot tile[NL_TILE];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int run_lo[9], run_n[9], n_cand;
+    __shared__ int hit2[NL_WARPS][NL_BUF2], hit3[NL_WARPS][NL_BUF3];
     const int cell = blockIdx.x;
     const int s0 = cell_start[cell], s1 = cell_start[cell + 1];
     if (s0 == s1) return;
@@ -375,43 +381,73 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
         const Slot c = slots[s];
         if (c.m >= n_real) continue;        // ghosts are never centres
         const Vec3 pc = {c.x, c.y, c.z};
+        // pass = 0: count and buffer; pass = 1 (only for rows longer than the buffers): write
+        // the hits straight to the global scratch rows
         int n2 = 0, n3 = 0, base2 = 0, base3 = 0;
-        if (FILL) { base2 = off2[c.m]; base3 = off3[c.m]; }
-        auto visit = [&](const Slot *cand, int count) {
-            for (int q0 = 0; q0 < count; q0 += 32) {
-                const int q = q0 + lane;
-                bool k2 = false, k3 = false;
-                int m = 0;
-                if (q < count) {
-                    const Slot t = cand[q];
-                    const Vec3 pt = {t.x, t.y, t.z};
-                    const double d = dist_rn(pc, pt);
-                    const int p = pair_index(B.ne, c.spec, t.spec);
-                    k2 = d > B.pair_lo[p] && d < B.pair_hi[p];
-                    k3 = has3 && d > B.r3min && d <= B.r3max;
-                    m = t.m;
+        bool fits = true, placed = true;
+        for (int pass = 0; pass < 2; ++pass) {
+            n2 = n3 = 0;
+            auto visit = [&](const Slot *cand, int count) {
+                for (int q0 = 0; q0 < count; q0 += 32) {
+                    const int q = q0 + lane;
+                    bool k2 = false, k3 = false;
+                    int m = 0;
+                    if (q < count) {
+                        const Slot t = cand[q];
+                        const Vec3 pt = {t.x, t.y, t.z};
+                        const double d = dist_rn(pc, pt);
+                        const int p = pair_index(B.ne, c.spec, t.spec);
+                        k2 = d > B.pair_lo[p] && d < B.pair_hi[p];
+                        k3 = has3 && d > B.r3min && d <= B.r3max;
+                        m = t.m;
+                    }
+                    const unsigned b2 = __ballot_sync(FULL, k2), b3 = __ballot_sync(FULL, k3);
+                    const int p2 = n2 + __popc(b2 & lt), p3 = n3 + __popc(b3 & lt);
+                    if (pass == 0) {
+                        if (k2 && p2 < NL_BUF2) hit2[warp][p2] = m;
+                        if (k3 && p3 < NL_BUF3) hit3[warp][p3] = m;
+                    } else if (placed) {
+                        if (k2) scratch2[base2 + p2] = m;
+                        if (k3) scratch3[base3 + p3] = m;
+                    }
+                    n2 += __popc(b2);
+                    n3 += __popc(b3);
                 }
-                const unsigned b2 = __ballot_sync(FULL, k2), b3 = __ballot_sync(FULL, k3);
-                if (FILL) {
-                    if (k2) scratch2[base2 + n2 + __popc(b2 & lt)] = m;
-                    if (k3) scratch3[base3 + n3 + __popc(b3 & lt)] = m;
-                }
-                n2 += __popc(b2);
-                n3 += __popc(b3);
+            };
+            if (staged) {
+                visit(tile, total);
+            } else {
+                for (int r = 0; r < 9; ++r) visit(slots + run_lo[r], run_n[r]);
             }
-        };
-        if (staged) {
-            visit(tile, total);
-        } else {
-            for (int r = 0; r < 9; ++r) visit(slots + run_lo[r], run_n[r]);
+            if (pass == 1) break;
+            // claim the rows
+            if (lane == 0) {
+                base2 = atomicAdd(status + 0, n2);
+                base3 = atomicAdd(status + 1, n3);
+                atomicMax(status + 3, n3);
+            }
+            base2 = __shfl_sync(FULL, base2, 0);
+            base3 = __shfl_sync(FULL, base3, 0);
+            placed = base2 + n2 <= cap2 && base3 + n3 <= cap3;
+            if (!placed && lane == 0) status[2] = 1;
+            fits = n2 <= NL_BUF2 && n3 <= NL_BUF3;
+            if (fits || !placed) break;
         }
-        if (!FILL) {
-            if (lane == 0) { cnt2[c.m] = n2; cnt3[c.m] = n3; atomicMax(max3, n3); }
-        } else {
-            __syncwarp();
-            warp_rank_sort(scratch2 + base2, idx2 + base2, n2, lane);
-            warp_rank_sort(scratch3 + base3, idx3 + base3, n3, lane);
+        __syncwarp();
+        if (lane == 0) {
+            off2[c.m] = base2; cnt2[c.m] = placed ? n2 : 0;
+            off3[c.m] = base3; cnt3[c.m] = placed ? n3 : 0;
         }
+        if (placed) {
+            if (fits) {
+                warp_rank_sort(hit2[warp], idx2 + base2, n2, lane);
+                warp_rank_sort(hit3[warp], idx3 + base3, n3, lane);
+            } else {
+                warp_rank_sort(scratch2 + base2, idx2 + base2, n2, lane);
+                warp_rank_sort(scratch3 + base3, idx3 + base3, n3, lane);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -443,8 +479,8 @@ FrameView uf3b_nlist::view() const {
     f.spec = spec.p;
     f.img_off = img_off.p;
     f.img_inv = img_inv.p;
-    f.off2 = off2.p; f.idx2 = idx2.p;
-    f.off3 = off3.p; f.idx3 = idx3.p;
+    f.off2 = off2.p; f.cnt2 = cnt2.p; f.idx2 = idx2.p;
+    f.off3 = off3.p; f.cnt3 = cnt3.p; f.idx3 = idx3.p;
     return f;
 }
 
@@ -492,12 +528,10 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     UF3B_CUDA(nl->img_inv.reserve(n_images));
     UF3B_CUDA(nl->off2.reserve((size_t)n + 1));
     UF3B_CUDA(nl->off3.reserve((size_t)n + 1));
-    UF3B_CUDA(nl->totals.reserve(4));
+    UF3B_CUDA(nl->totals.reserve(8));
     UF3B_CUDA(cudaMemcpyAsync(nl->img_off.p, image_offsets, sizeof(double) * 3 * n_images, cudaMemcpyDefault, stream));
     UF3B_CUDA(cudaMemcpyAsync(nl->img_inv.p, inv.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, stream));
     if (n == 0) {
-        UF3B_CUDA(cudaMemsetAsync(nl->off2.p, 0, sizeof(int), stream));
-        UF3B_CUDA(cudaMemsetAsync(nl->off3.p, 0, sizeof(int), stream));
         UF3B_CUDA(cudaStreamSynchronize(stream));
         guard.armed = false;
         *inout = nl;
@@ -507,7 +541,6 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     UF3B_CUDA(nl->z.reserve(n));
     UF3B_CUDA(nl->spec.reserve(n));
     UF3B_CUDA(nl->misc.reserve(8));
-    UF3B_CUDA(nl->cnt.reserve(2 * (size_t)n + 2));
     UF3B_CUDA(cudaMemcpyAsync(nl->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyDefault, stream));
     UF3B_CUDA(cudaMemcpyAsync(nl->z.p, atomic_numbers, sizeof(int) * n, cudaMemcpyDefault, stream));
     int *d_err = (int *)(nl->misc.p + 6);
@@ -556,26 +589,35 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     UF3B_LAUNCH(k_bin_fill, bin_blocks, 256, 0, stream, n, n_sup, nl->pos.p, nl->img_off.p,
                 nl->spec.p, nl->cell_of.p, nl->cell_start.p, nl->cell_cursor.p, nl->slots.p);
 
-    int *cnt2 = nl->cnt.p, *cnt3 = nl->cnt.p + n + 1;
-    UF3B_CUDA(cudaMemsetAsync(nl->totals.p + 3, 0, sizeof(long long), stream));
-    UF3B_LAUNCH(k_neighbors<false>, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G,
-                nl->slots.p, nl->cell_start.p, n, cnt2, cnt3, nullptr, nullptr, nullptr, nullptr,
-                nullptr, nullptr, (int *)(nl->totals.p + 3));
-    if (int rc = scan_arrays(nl, 2, cnt2, nl->off2.p, cnt3, nl->off3.p, n, nl->totals.p + 1, stream)) return rc;
-    long long h_tot[3];     // list totals and the longest 3-body row
-    UF3B_CUDA(cudaMemcpyAsync(h_tot, nl->totals.p + 1, sizeof h_tot, cudaMemcpyDeviceToHost, stream));
-    UF3B_CUDA(cudaStreamSynchronize(stream));
-    if (h_tot[0] >= (1LL << 31) || h_tot[1] >= (1LL << 31))
-        return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
-    nl->total2 = h_tot[0];
-    nl->total3 = h_tot[1];
-    nl->max3 = (int)h_tot[2];
-    UF3B_CUDA(nl->idx2.reserve((size_t)h_tot[0] + 1));
-    UF3B_CUDA(nl->idx3.reserve((size_t)h_tot[1] + 1));
-    UF3B_CUDA(nl->scratch.reserve((size_t)(h_tot[0] + h_tot[1]) + 2));
-    UF3B_LAUNCH(k_neighbors<true>, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G,
-                nl->slots.p, nl->cell_start.p, n, nullptr, nullptr, nl->off2.p, nl->off3.p,
-                nl->scratch.p, nl->scratch.p + h_tot[0], nl->idx2.p, nl->idx3.p, nullptr);
+    // one pass; the index arrays keep their capacity from earlier builds (first guess below)
+    int *status = (int *)(nl->totals.p + 1);        // 4 ints
+    int h_status[4];
+    UF3B_CUDA(nl->cnt2.reserve((size_t)n + 1));
+    UF3B_CUDA(nl->cnt3.reserve((size_t)n + 1));
+    if (nl->idx2.cap == 0) UF3B_CUDA(nl->idx2.reserve((size_t)n * 80 + 1024));
+    if (nl->idx3.cap == 0 && basis->tab.n_trios > 0) UF3B_CUDA(nl->idx3.reserve((size_t)n * 40 + 1024));
+    if (nl->idx3.cap == 0) UF3B_CUDA(nl->idx3.reserve(64));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        UF3B_CUDA(nl->scratch2.reserve(nl->idx2.cap));
+        UF3B_CUDA(nl->scratch3.reserve(nl->idx3.cap));
+        UF3B_CUDA(cudaMemsetAsync(status, 0, sizeof h_status, stream));
+        const int cap2 = (int)std::min<size_t>(nl->idx2.cap, (size_t)INT32_MAX);
+        const int cap3 = (int)std::min<size_t>(nl->idx3.cap, (size_t)INT32_MAX);
+        UF3B_LAUNCH(k_neighbors, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G, nl->slots.p,
+                    nl->cell_start.p, n, nl->off2.p, nl->cnt2.p, nl->off3.p, nl->cnt3.p, nl->idx2.p,
+                    nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status);
+        UF3B_CUDA(cudaMemcpyAsync(h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, stream));
+        UF3B_CUDA(cudaStreamSynchronize(stream));
+        if (h_status[0] < 0 || h_status[1] < 0)
+            return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
+        if (!h_status[2]) break;
+        if (attempt == 1) return fail(UF3B_ERR_CAPACITY, "neighbour list did not fit after regrowth");
+        UF3B_CUDA(nl->idx2.reserve((size_t)h_status[0] + 1));     // reserve() adds 25 % headroom
+        UF3B_CUDA(nl->idx3.reserve((size_t)h_status[1] + 1));
+    }
+    nl->total2 = h_status[0];
+    nl->total3 = h_status[1];
+    nl->max3 = h_status[3];
     guard.armed = false;
     *inout = nl;
     return UF3B_OK;
@@ -590,15 +632,25 @@ int uf3b_neighbors_count(const uf3b_nlist *nl, int which, int64_t *n_entries) {
 int uf3b_neighbors_export(const uf3b_nlist *nl, int which, int64_t *offsets, int64_t *supercell_index) {
     if (!nl || !offsets || (which != 2 && which != 3)) return fail(UF3B_ERR_INVALID, "bad argument");
     const int64_t total = which == 2 ? nl->total2 : nl->total3;
-    std::vector<int> off((size_t)nl->n + 1), idx((size_t)total);
+    const size_t n = (size_t)nl->n;
+    std::vector<int> start(n), count(n), idx((size_t)total);
     UF3B_CUDA(cudaDeviceSynchronize());
-    UF3B_CUDA(cudaMemcpy(off.data(), which == 2 ? nl->off2.p : nl->off3.p, sizeof(int) * off.size(), cudaMemcpyDeviceToHost));
+    if (n) {
+        UF3B_CUDA(cudaMemcpy(start.data(), which == 2 ? nl->off2.p : nl->off3.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+        UF3B_CUDA(cudaMemcpy(count.data(), which == 2 ? nl->cnt2.p : nl->cnt3.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    }
     if (total) {
         if (!supercell_index) return fail(UF3B_ERR_INVALID, "null index buffer");
         UF3B_CUDA(cudaMemcpy(idx.data(), which == 2 ? nl->idx2.p : nl->idx3.p, sizeof(int) * idx.size(), cudaMemcpyDeviceToHost));
     }
-    for (size_t i = 0; i < off.size(); ++i) offsets[i] = off[i];
-    for (size_t i = 0; i < idx.size(); ++i) supercell_index[i] = idx[i];
+    // rows live in claim order on the device; the export is the standard CSR by atom
+    int64_t run = 0;
+    for (size_t a = 0; a < n; ++a) {
+        offsets[a] = run;
+        for (int k = 0; k < count[a]; ++k) supercell_index[run + k] = idx[(size_t)start[a] + k];
+        run += count[a];
+    }
+    offsets[n] = run;
     return UF3B_OK;
 }
 

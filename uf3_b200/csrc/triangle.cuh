@@ -121,7 +121,7 @@ __device__ __forceinline__ int publish_views(const BasisTab &B, const FrameView 
         int dummy;
         const Vec3 pi = real_position(f, ci), pa = super_position(f, apr, dummy);
         const double d = dist_rn(pi, pa);      // same expression the list kernel evaluated
-        if (d > B.r3min && d <= B.r3max) cnt = __ldg(f.off3 + ci + 1) - __ldg(f.off3 + ci);
+        if (d > B.r3min && d <= B.r3max) cnt = __ldg(f.cnt3 + ci);
     }
     int inc = cnt;
 #pragma unroll
