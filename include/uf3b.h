@@ -130,7 +130,9 @@ int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy,
 /* -- inference path --------------------------------------------------------------- */
 /* replaces: UFCalculator._get_potential_energy / _get_forces
  * (forcefield/calculator.py:156-343).  energy: 1 double or NULL; forces [n_atoms*3] or
- * NULL; virial [9] or NULL (sum over pairs/triplets of r (x) f, for analytic stress). */
+ * NULL; virial [9] (row-major 3x3, symmetric) or NULL: W = dE/d(strain) = sum over every leg
+ * of every pair / triplet term of (dE/dr) r u (x) u; stress = W / volume.  Replaces the
+ * twelve strained-cell energy evaluations of calculator.py:399-404. */
 int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, double *energy,
                        double *forces, double *virial, void *stream);
 

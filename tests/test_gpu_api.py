@@ -100,11 +100,71 @@ def test_calculator_matches_reference(name):
     assert calc.results["energy"] == e and calc.results["free_energy"] == e
 
 
+@pytest.mark.parametrize("name", ["calc_w8_pbc", "calc_syn_w54_model23", "calc_syn_nexe64_pair",
+                                  "calc_syn_w128_model23"])
+def test_analytic_stress_matches_numerical_stress(name):
+    """The kernel's analytic strain derivative against the reference's method (central
+    differences over strained cells, calculator.py:399-404) on pair and 2+3-body models.
+    (calc_w_dimer_pbc is left out on purpose: its 3 A cell edge puts image pairs exactly on
+    r_max = 6 A, where the shipped coefficients are non-zero, so the strained-cell energy
+    jumps and the finite difference diverges like 1/d — the analytic value is the limit.)"""
+    case = gu.Case(name)
+    model = ls.WeightedLinearModel(case.basis())
+    model.coefficients = np.array(case["coefficients"])
+    atoms = case.atoms()
+    analytic = UFCalculator(model)
+    atoms.calc = analytic
+    got = atoms.get_stress()
+    assert got.shape == (6,) and "stress" in analytic.results
+    want = UFCalculator(model, numerical_stress=True)._get_stress(atoms, d=1e-5)
+    assert np.abs(got - want).max() <= 2e-6 * max(np.abs(want).max(), 1e-3)
+    # the 3x3 tensor is symmetric and the virial call leaves energy / forces untouched
+    eng = analytic.engine
+    e0, f0 = eng.energy_forces()
+    e1, f1, w = eng.energy_forces(virial=True)
+    assert np.array_equal(w, w.T)
+    assert abs(e0 - e1) <= 1e-12 * abs(e0) and gu.rel_err(f1, f0) <= 1e-12
+
+
+def test_analytic_stress_matches_oracle_energy_differences():
+    """Stress from the kernel against central differences of the ORACLE's energy over the six
+    strain components (the reference's definition, with the CPU restatement as the energy)."""
+    from oracle import uf3_oracle as orc
+    from uf3_b200 import geometry
+    case = gu.Case("calc_syn_w54_model23")
+    basis, coeff = case.basis(), np.array(case["coefficients"])
+    model = ls.WeightedLinearModel(basis)
+    model.coefficients = coeff
+    atoms = case.atoms()
+    got = UFCalculator(model)._get_stress(atoms)
+    packed = orc.PackedBasis(basis)
+    cell0, pos0 = np.array(atoms.get_cell()), np.array(atoms.get_positions())
+    numbers, pbc = np.array(atoms.get_atomic_numbers()), np.array(atoms.get_pbc())
+    d, want = 1e-5, np.zeros((3, 3))
+    for i in range(3):
+        for j in range(i, 3):
+            energies = []
+            for sign in (1, -1):
+                strain = np.eye(3)
+                if i == j:
+                    strain[i, i] += sign * d
+                else:
+                    strain[i, j] += sign * d / 2
+                    strain[j, i] += sign * d / 2
+                cell = cell0 @ strain
+                pos = pos0 @ strain
+                images = geometry.image_table(cell, pbc, basis.r_cut)
+                energies.append(orc.energy_forces(basis, packed, coeff, pos, numbers, images[1])[0])
+            want[i, j] = want[j, i] = (energies[0] - energies[1]) / (2 * d * abs(np.linalg.det(cell0)))
+    want = want.flat[[0, 4, 8, 5, 2, 1]]
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
 def test_numerical_stress_is_energy_derivative():
     case = gu.Case("calc_w8_pbc")
     model = ls.WeightedLinearModel(case.basis())
     model.coefficients = np.array(case["coefficients"])
-    calc = UFCalculator(model)
+    calc = UFCalculator(model, numerical_stress=True)
     atoms = case.atoms()
     stress = calc._get_stress(atoms)
     assert stress.shape == (6,) and np.all(np.isfinite(stress))

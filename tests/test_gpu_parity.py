@@ -166,15 +166,17 @@ def test_energy_forces_match_oracle_mid_size():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["syn_w54_demo", "syn_w36_slab", "syn_w16_demo", "ref_ar3_default"])
+@pytest.mark.parametrize("name", ["syn_w54_demo", "syn_w36_slab", "syn_w16_demo", "ref_ar3_default",
+                                  "syn_w54_manuscript"])
 def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     """Unary bases with a small untrimmed 3-body grid take the leg-grouped tile path of
-    k_featurize (symmetry >= 2, rows <= 32), else the per-triangle register-tile path;
+    k_featurize (symmetry >= 2, rows <= 32), larger grids of symmetry 2 the plane path
+    (UF3B_PLANES forces it for small grids too), else the per-triangle register-tile path;
     UF3B_NO_LEGS / UF3B_NO_TILE force the next more general path."""
     case = gu.Case(name)
     outs = []
-    for env in ({}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"}):
-        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE"):
+    for env in ({}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"}, {"UF3B_PLANES": "1"}):
+        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
@@ -186,7 +188,9 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     for xe, xf in outs:
         assert gu.rel_err(xe, case["x_energy"]) <= REL
         assert gu.rel_err(xf, case["x_forces"]) <= REL
-    assert gu.rel_err(outs[0][1], outs[2][1]) <= 1e-11 and gu.rel_err(outs[1][1], outs[2][1]) <= 1e-11
+    for other in (0, 1, 3):
+        assert gu.rel_err(outs[other][1], outs[2][1]) <= 1e-11
+        assert gu.rel_err(outs[other][0], outs[2][0]) <= 1e-11
 
 
 def test_empty_and_single_atom():

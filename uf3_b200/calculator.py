@@ -6,9 +6,12 @@ API mirror of `/root/reference/uf3/forcefield/calculator.py:40-153,399-404,490-5
 `calculate(atoms, properties, system_changes)` filling `self.results`, the attributes
 `solutions` / `pair_potentials` / `trio_potentials` (coefficient vectors and decompressed
 coefficient grids per interaction — the reference stores `ndsplines.NDSpline` objects
-there; here they are the arrays the kernels contract against) and numerical stress by
-central finite differences of the energy over strain, as ASE's
-`calculate_numerical_stress` does.  If ASE is installed the class derives from
+there; here they are the arrays the kernels contract against).  Stress: the reference takes
+central finite differences of the energy over strain (ASE's `calculate_numerical_stress`,
+12 energy evaluations); here the evaluator kernel accumulates the analytic strain derivative
+in the same pair / triangle walk (`uf3b_energy_forces(..., virial)`), and
+`UFCalculator(model, numerical_stress=True)` selects the reference's method.  If ASE is
+installed the class derives from
 `ase.calculators.calculator.Calculator`; otherwise from a minimal stand-in with the
 same protocol (`get_potential_energy`, `get_forces`, `get_stress`, `results`).
 """
@@ -88,8 +91,9 @@ def coefficients_by_interaction(element_list, interactions_map, partition_sizes,
 class UFCalculator(_Base):
     implemented_properties = ["energy", "forces", "stress"]
 
-    def __init__(self, model, device=None, **kwargs):
+    def __init__(self, model, device=None, numerical_stress=False, **kwargs):
         super().__init__(**kwargs)
+        self.numerical_stress = numerical_stress
         self.bspline_config = model.bspline_config
         self.model = model
         self.device = device
@@ -165,4 +169,13 @@ class UFCalculator(_Base):
         return self._evaluate(atoms, False, True)[1]
 
     def _get_stress(self, atoms=None, **kwargs):
-        return self.calculate_numerical_stress(atoms, **kwargs)
+        """Voigt stress [xx, yy, zz, yz, xz, xy] (calculator.py:399-404)."""
+        if self.numerical_stress or kwargs:
+            return self.calculate_numerical_stress(atoms, **kwargs)
+        positions, numbers, cell, pbc = frame_arrays(atoms)
+        images = geometry.image_table(cell, pbc, self.r_cut) if np.any(pbc) else None
+        eng = self.engine
+        eng.build_neighbors(positions, numbers, images=images)
+        _, _, w = eng.energy_forces(energy=False, forces=False, virial=True)
+        volume = abs(np.linalg.det(np.asarray(cell, dtype=np.float64)))
+        return (w / volume).flat[[0, 4, 8, 5, 2, 1]]

@@ -108,6 +108,7 @@ struct __align__(32) Slot {
 // Read-only view of one configuration and its neighbour lists.
 struct FrameView {
     int n;                    // real atoms
+    unsigned n_magic;         // floor(2^32 / n) (2^32 - 1 for n = 1): image_of() without a division
     int n_img;
     const double *pos;        // [n*3]
     const int *spec;          // [n]

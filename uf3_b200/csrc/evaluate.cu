@@ -59,7 +59,12 @@ constexpr int EV_WARPS = 4;
 
 // grid_in_smem: the decompressed coefficient grids (n_grid doubles) are staged in shared
 // memory once per block.
-template <bool NEWTON>
+// VIRIAL: also accumulate W = sum over every leg of every energy term of
+// (dE/dr_leg) r_leg u (x) u  (= dE/d(strain) under a homogeneous deformation; stress = W / V),
+// the analytic form of what the reference obtains by finite differences over strained
+// cells (calculator.py:399-404).  Six per-lane accumulators, written next to the per-warp
+// energies: e_partials[n_gw * (1 + c) + gw], c = xx, yy, zz, yz, xz, xy.
+template <bool NEWTON, bool VIRIAL>
 __global__ void __launch_bounds__(EV_WARPS * 32, 4)
 k_energy_forces(const BasisTab B, const FrameView f, double *forces,
                 double *__restrict__ e_partials, int want_e_, int want_f_, int n_grid, int grid_in_smem) {
@@ -75,6 +80,12 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
     const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
     RoleViews *views = s_views + warp;
     double e_acc = 0.0;
+    double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    auto add_virial = [&](double k, double x, double y, double z) {   // k = (dE/dr) r, u = (x, y, z)
+        const double kx = k * x, ky = k * y;
+        w[0] += kx * x; w[1] += ky * y; w[2] += k * z * z;
+        w[3] += ky * z; w[4] += kx * z; w[5] += kx * y;
+    };
 
     for (int a = gw; a < f.n; a += n_gw) {
         const int sa = __ldg(f.spec + a);
@@ -106,6 +117,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
             fx += k * (pj.x - pa.x);
             fy += k * (pj.y - pa.y);
             fz += k * (pj.z - pa.z);
+            if (VIRIAL) add_virial(ds / d, pj.x - pa.x, pj.y - pa.y, pj.z - pa.z);
         }
 
         // ---- 3-body
@@ -125,6 +137,11 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
                 fx += gl * T.A[0] + gm * T.B[0];
                 fy += gl * T.A[1] + gm * T.B[1];
                 fz += gl * T.A[2] + gm * T.B[2];
+                if (VIRIAL) {       // role 0: A = u_ij, B = u_ik
+                    add_virial(gl * T.r[0], T.A[0], T.A[1], T.A[2]);
+                    add_virial(gm * T.r[1], T.B[0], T.B[1], T.B[2]);
+                    add_virial(gn * T.r[2], T.ujk[0], T.ujk[1], T.ujk[2]);
+                }
                 if (NEWTON && want_f) {
                     // reactions: F_j = -gl u_ij + gn u_jk, F_k = -gm u_ik - gn u_jk, added to
                     // the parent atoms of j and k; (A, B) hold (u_ij, u_ik), u_jk is rebuilt
@@ -182,13 +199,22 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
         e_acc = warp_sum(e_acc);
         if (lane == 0) e_partials[gw] = e_acc;
     }
+    if (VIRIAL) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double s = warp_sum(w[c]);
+            if (lane == 0) e_partials[(size_t)n_gw * (1 + c) + gw] = s;
+        }
+    }
 }
 
-// Fixed-order sum of the per-warp energies.
+// Fixed-order sum of the per-warp energies (block 0) and virial components (blocks 1..6).
 __global__ void __launch_bounds__(256) k_energy_sum(const double *__restrict__ partials, int n,
                                                     double *__restrict__ energy) {
     __shared__ double red[256];
     double s = 0.0;
+    partials += (size_t)blockIdx.x * n;
+    energy += blockIdx.x;
     for (int r = threadIdx.x; r < n; r += blockDim.x) s += partials[r];
     red[threadIdx.x] = s;
     __syncthreads();
@@ -207,22 +233,27 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
                                   double *forces, double *virial, void *stream_) {
     if (!basis || !nl) return fail(UF3B_ERR_INVALID, "null handle");
     if (!basis->has_coeff) return fail(UF3B_ERR_STATE, "coefficients not set");
-    if (virial) return fail(UF3B_ERR_INVALID, "analytic virial is not implemented yet; pass NULL");
-    if (!energy && !forces) return UF3B_OK;
+    if (!energy && !forces && !virial) return UF3B_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n = (int)nl->n;
     const bool e_dev = energy && is_device_pointer(energy);
     const bool f_dev = forces && is_device_pointer(forces);
+    const bool w_dev = virial && is_device_pointer(virial);
     if (n == 0) {
         if (energy) {
             if (e_dev) UF3B_CUDA(cudaMemsetAsync(energy, 0, sizeof(double), stream));
             else *energy = 0.0;
         }
+        if (virial) {
+            if (w_dev) UF3B_CUDA(cudaMemsetAsync(virial, 0, 9 * sizeof(double), stream));
+            else for (int k = 0; k < 9; ++k) virial[k] = 0.0;
+        }
         return UF3B_OK;
     }
     const bool deterministic = getenv("UF3B_DETERMINISTIC_FORCES") != nullptr;
     const bool newton = !deterministic && basis->tab.n_trios > 0;
-    auto kernel = newton ? k_energy_forces<true> : k_energy_forces<false>;
+    auto kernel = virial ? (newton ? k_energy_forces<true, true> : k_energy_forces<false, true>)
+                         : (newton ? k_energy_forces<true, false> : k_energy_forces<false, false>);
     const int n_grid = basis->n_bins;
     const size_t grid_bytes = sizeof(double) * (size_t)n_grid;
     const int grid_in_smem = (n_grid > 0 && grid_bytes <= 48 * 1024) ? 1 : 0;
@@ -234,15 +265,17 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     const int need = (n + EV_WARPS - 1) / EV_WARPS;
     if (grid > need) grid = need;
     const int n_gw = grid * EV_WARPS;
-    UF3B_CUDA(basis->partials.reserve((size_t)n_gw + 1));
+    UF3B_CUDA(basis->partials.reserve((size_t)n_gw * 7 + 1));
     double *d_f = forces;
     if (forces && !f_dev) {
         UF3B_CUDA(basis->stage.reserve((size_t)3 * n));
         d_f = basis->stage.p;
     }
     double *d_e = energy;
-    if (energy && !e_dev) {
-        UF3B_CUDA(basis->stage_e.reserve(1));
+    // sums land in stage_e[0..7) = energy, W_xx, W_yy, W_zz, W_yz, W_xz, W_xy unless the
+    // energy alone goes straight to a device address
+    if ((energy && !e_dev) || virial) {
+        UF3B_CUDA(basis->stage_e.reserve(7));
         d_e = basis->stage_e.p;
     }
     const FrameView view = nl->view();
@@ -256,8 +289,16 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     UF3B_LAUNCH(kernel, grid, EV_WARPS * 32, smem, stream, basis->tab, view, d_f,
                 basis->partials.p, energy ? 1 : 0, forces ? 1 : 0, n_grid, grid_in_smem);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
-    if (energy) UF3B_LAUNCH(k_energy_sum, 1, 256, 0, stream, basis->partials.p, n_gw, d_e);
+    if (energy || virial)
+        UF3B_LAUNCH(k_energy_sum, virial ? 7 : 1, 256, 0, stream, basis->partials.p, n_gw, d_e);
     bool need_sync = g_timing;
+    double h_sums[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (virial) {       // 7 doubles: read back, expand the symmetric tensor on the host
+        UF3B_CUDA(cudaMemcpyAsync(h_sums, d_e, sizeof(h_sums), cudaMemcpyDeviceToHost, stream));
+        if (energy && e_dev)
+            UF3B_CUDA(cudaMemcpyAsync(energy, d_e, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        need_sync = true;
+    }
     if (forces && !f_dev) {
         UF3B_CUDA(cudaMemcpyAsync(forces, d_f, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, stream));
         need_sync = true;
@@ -267,6 +308,12 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
         need_sync = true;
     }
     if (need_sync) UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (virial) {
+        const double full[9] = {h_sums[1], h_sums[6], h_sums[5], h_sums[6], h_sums[2], h_sums[4],
+                                h_sums[5], h_sums[4], h_sums[3]};
+        if (w_dev) UF3B_CUDA(cudaMemcpy(virial, full, sizeof(full), cudaMemcpyHostToDevice));
+        else for (int k = 0; k < 9; ++k) virial[k] = full[k];
+    }
     if (g_timing) {
         float ms = 0.f;
         UF3B_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));

@@ -233,6 +233,7 @@ struct TileGeom {
     int la, ma, na;        // untrimmed extents (la <= RT_LA, ma + na <= 12, ma * na <= 64)
     int dim_m, dim_n;      // full grid extents of legs m, n
     int goff, col0, sym;
+    int warp_bytes;        // shared memory per warp (accumulators + scratch)
 };
 
 // Tile record: [flags][A B C][vl[4] dvl[4]][vm[ma] dvm[ma] vn[na] dvn[na]], dense by
@@ -450,7 +451,7 @@ __device__ __forceinline__ void legs_three_body(const BasisTab &B, const FrameVi
     // ---- (ii) `a` as a neighbour of every centre i in its list
     for (int e = 0; e < n3a; ++e) {
         const int m = __ldg(f.idx3 + row0 + e);
-        const int gimg = (int)((unsigned)m / (unsigned)f.n);
+        const int gimg = image_of(f, m);
         const int ci = m - gimg * f.n;
         const int apr = __ldg(f.img_inv + gimg) * f.n + a;
         const int rowi = __ldg(f.off3 + ci), ni = __ldg(f.cnt3 + ci);
@@ -503,11 +504,232 @@ __device__ __forceinline__ void legs_three_body(const BasisTab &B, const FrameVi
     }
 }
 
+// ---------------------------------------------------------------- plane path
+// The leg-grouped factorisation above for grids of ANY size (the manuscript basis: 7 x 7 x 17
+// untrimmed cells, 456 columns): nothing is kept dense in registers.  Legs are stored
+// sparsely (first basis index + 4 values + 4 derivatives + unit vector); for one leg group
+// the partner sums P[m,n] (and, in the neighbour role, the vector sums Q[m,n]) are built in
+// a per-warp shared-memory plane by lanes = (p, q) of the 4 x 4 non-zero products of each
+// partner; then the plane is contracted with the group's 4 non-zero l values straight into
+// the warp's column accumulators (bin_col gives the compressed column).
+// One pass of the outer stage touches bins of ONE l, so two lanes never meet in a column
+// for a trio of symmetry 2 ((l,m,n) ~ (m,l,n)); passes are ordered with __syncwarp.
+// Lanes with nothing to add (trimmed / out-of-range basis index, empty cell, folded-away
+// bin) aim their read-modify-write at a dummy slot instead of branching, so the loops are
+// branch-free and the warp stays converged.
+// Energy row: every unordered neighbour pair is met twice (as (j,k) and (k,j)) and both
+// orders fold onto the same column, so e += (1/2) B_l(r_aj) P_j — exact halving.
+constexpr unsigned SPL_REC = 96;        // l / m leg: v[4] dv[4] u[3] {int idx - x0, pad}
+constexpr unsigned SPN_REC = 112;       // n leg:     v[4] dv[4] {1, wx, wy, wz} {int idx - x0, pad} pad
+constexpr unsigned SPL_IDX = 88, SPN_IDX = 96;
+constexpr unsigned SP_N_BASE = 32 * SPL_REC, SP_PLANE = SP_N_BASE + 32 * SPN_REC;
+constexpr int PL_MAX_CELLS = 128;
+constexpr int SP_DEAD = -(1 << 20);     // idx of a leg outside its knot range
+__host__ __device__ inline size_t plane_scratch_bytes(int n_cells) {   // + one dummy quad
+    return SP_PLANE + 32 * (size_t)n_cells + 32;
+}
+
+template <bool N_LEG>
+__device__ __forceinline__ void eval_sparse_leg(const BasisTab &B, int leg, const Vec3 &from, const Vec3 &to,
+                                                int x0, unsigned char *out) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0}, dv[4] = {0.0, 0.0, 0.0, 0.0};
+    const double d = dist_rn(from, to);
+    const int nk = __ldg(B.trio_nk + leg);
+    const double *t = B.knots3 + __ldg(B.trio_koff + leg);
+    double inv = 0.0;
+    int rel = SP_DEAD;
+    if (d >= t[0] && d <= t[nk - 1]) {              // angles.py:502-508 drops the whole triangle
+        const int idx = eval_leg(t, nk, __ldg(B.trio_scale + leg), B.poly3 + __ldg(B.trio_poff + leg), d,
+                                 B.lead3, B.trail3, v, dv);
+        if (idx >= 0) rel = idx - x0;
+        inv = fast_rcp(d);
+    }
+    const double ux = (to.x - from.x) * inv, uy = (to.y - from.y) * inv, uz = (to.z - from.z) * inv;
+    const double tag = __longlong_as_double((long long)(unsigned)rel);
+    double2 *o = reinterpret_cast<double2 *>(out);
+    o[0] = make_double2(v[0], v[1]);
+    o[1] = make_double2(v[2], v[3]);
+    o[2] = make_double2(dv[0], dv[1]);
+    o[3] = make_double2(dv[2], dv[3]);
+    if (N_LEG) {
+        o[4] = make_double2(1.0, ux);
+        o[5] = make_double2(uy, uz);
+        o[6] = make_double2(tag, 0.0);
+    } else {
+        o[4] = make_double2(ux, uy);
+        o[5] = make_double2(uz, tag);
+    }
+}
+
+// Contract the plane of one leg group with the group's own leg (record `lrec`) into the
+// column accumulators and clear the plane.  CENTRE: slots 0/1 hold the partner sum P split
+// over even / odd partners; else the slots are (P, Qx, Qy, Qz).
+template <bool CENTRE, int KC>
+__device__ __forceinline__ void plane_outer(const BasisTab &B, const TileGeom &g, unsigned plane_s, unsigned dummy_s,
+                                            unsigned lrec, const int (&bin0)[KC], int n_cells, unsigned acc_s,
+                                            int lane, bool want_e) {
+    const int il = lds32(lrec + SPL_IDX);
+    const double2 v01 = lds128(lrec), v23 = lds128(lrec + 16), d01 = lds128(lrec + 32), d23 = lds128(lrec + 48);
+    const double2 u01 = lds128(lrec + 64);
+    const double u2 = lds64(lrec + 80);
+    const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
+    const int lmn = g.dim_m * g.dim_n;
+    const double half_e = want_e ? 0.5 : 0.0;
+    double P[KC], Qx[KC], Qy[KC], Qz[KC];
+    bool live[KC];
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+        const int cell = lane + 32 * kk;
+        live[kk] = cell < n_cells;
+        const unsigned pa = live[kk] ? plane_s + 32u * (unsigned)cell : dummy_s;
+        const double2 a = lds128(pa);
+        sts128(pa, make_double2(0.0, 0.0));
+        if (CENTRE) {
+            P[kk] = a.x + a.y;
+            Qx[kk] = Qy[kk] = Qz[kk] = 0.0;
+            live[kk] = live[kk] && P[kk] != 0.0;
+        } else {
+            const double2 b = lds128(pa + 16);
+            sts128(pa + 16, make_double2(0.0, 0.0));
+            P[kk] = a.x; Qx[kk] = a.y; Qy[kk] = b.x; Qz[kk] = b.y;
+            live[kk] = live[kk] && (a.x != 0.0 || a.y != 0.0 || b.x != 0.0 || b.y != 0.0);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int lrel = il + p;
+        if ((unsigned)lrel < (unsigned)g.la) {       // warp-uniform
+            unsigned ad[KC];
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                const int col = live[kk] ? __ldg(B.bin_col + bin0[kk] + lrel * lmn) : -1;
+                ad[kk] = col >= 0 ? acc_s + 32u * (unsigned)(g.col0 + col) : dummy_s;
+            }
+            double2 q0[KC], q1[KC];
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) { q0[kk] = lds128(ad[kk]); q1[kk] = lds128(ad[kk] + 16); }
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                const double dP = dv[p] * P[kk];
+                if (CENTRE) {
+                    q0[kk].x = fma(half_e * v[p], P[kk], q0[kk].x);
+                    q0[kk].y = fma(u01.x, dP, q0[kk].y);
+                    q1[kk].x = fma(u01.y, dP, q1[kk].x);
+                    q1[kk].y = fma(u2, dP, q1[kk].y);
+                } else {
+                    q0[kk].y += v[p] * Qx[kk] - u01.x * dP;
+                    q1[kk].x += v[p] * Qy[kk] - u01.y * dP;
+                    q1[kk].y += v[p] * Qz[kk] - u2 * dP;
+                }
+                sts128(ad[kk], q0[kk]);
+                sts128(ad[kk] + 16, q1[kk]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int KC>
+__device__ __forceinline__ void plane_three_body(const BasisTab &B, const FrameView &f, const TileGeom &g,
+                                                 int a, const Vec3 &pa, unsigned char *scratch, unsigned scratch_s,
+                                                 unsigned acc_s, const int (&bin0)[KC], int lane,
+                                                 bool want_e, bool want_f) {
+    const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
+    if (n3a < 1) return;
+    const int n_cells = g.ma * g.na;
+    const unsigned lm_s = scratch_s, nn_s = scratch_s + SP_N_BASE, plane_s = scratch_s + SP_PLANE;
+    const unsigned dummy_s = plane_s + 32u * (unsigned)n_cells;
+    unsigned char *lm = scratch, *nn = scratch + SP_N_BASE;
+    const unsigned ma = (unsigned)g.ma, na = (unsigned)g.na;
+    const int half = lane >> 4, p = (lane >> 2) & 3, q = lane & 3;
+    int dummy;
+
+    // ---- (i) `a` as the centre
+    if (lane < n3a)
+        eval_sparse_leg<false>(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0,
+                               lm + lane * SPL_REC);
+    __syncwarp();
+    const int per_pass = 32 / n3a;                // groups per pass (n3a <= 32); slot = gi * n3a + k
+    for (int g0 = 0; g0 < n3a && n3a > 1; g0 += per_pass) {
+        {   // phase A: legs (j, k) of up to per_pass groups, one per lane
+            const int gi = lane / n3a, k = lane - gi * n3a, j = g0 + gi;
+            if (gi < per_pass && j < n3a && k != j)
+                eval_sparse_leg<true>(B, 2, super_position(f, __ldg(f.idx3 + row0 + j), dummy),
+                                      super_position(f, __ldg(f.idx3 + row0 + k), dummy), g.n0,
+                                      nn + lane * SPN_REC);
+        }
+        __syncwarp();
+        for (int gi = 0; gi < per_pass && g0 + gi < n3a; ++gi) {
+            const int j = g0 + gi;
+            const unsigned n_row = nn_s + (unsigned)(gi * n3a) * SPN_REC;
+            for (int k0 = 0; k0 < n3a; k0 += 2) {         // two partners per pass, one per half-warp
+                const int k = min(k0 + half, n3a - 1);
+                const unsigned lk = lm_s + (unsigned)k * SPL_REC, ns = n_row + (unsigned)k * SPN_REC;
+                const unsigned mrel = (unsigned)(lds32(lk + SPL_IDX) + p);
+                const unsigned nrel = (unsigned)(k == j ? SP_DEAD : lds32(ns + SPN_IDX) + q);
+                const bool ok = mrel < ma && nrel < na && k0 + half < n3a;
+                const unsigned ad = ok ? plane_s + 32u * (mrel * na + nrel) + 8u * (unsigned)half : dummy_s;
+                sts64(ad, fma(lds64(lk + 8 * p), lds64(ns + 8 * q), lds64(ad)));
+                __syncwarp();
+            }
+            plane_outer<true, KC>(B, g, plane_s, dummy_s, lm_s + (unsigned)j * SPL_REC, bin0, n_cells, acc_s,
+                                  lane, want_e);
+        }
+        __syncwarp();
+    }
+    if (!want_f) return;
+
+    // ---- (ii) `a` as a neighbour of every centre i in its list
+    const unsigned off_a = 32u * (unsigned)half + 8u * (unsigned)q;   // v[q] | dv[q]
+    const unsigned off_w = 64u + 16u * (unsigned)half;                // (1, wx) | (wy, wz)
+    for (int e = 0; e < n3a; ++e) {
+        const int m = __ldg(f.idx3 + row0 + e);
+        const int gimg = image_of(f, m);
+        const int ci = m - gimg * f.n;
+        const int apr = __ldg(f.img_inv + gimg) * f.n + a;
+        const int rowi = __ldg(f.off3 + ci), ni = __ldg(f.cnt3 + ci);
+        const int mine = lane < ni ? __ldg(f.idx3 + rowi + lane) : -1;
+        const unsigned hit = __ballot_sync(FULL, mine == apr);
+        if (!hit) continue;                       // one-ulp asymmetry of the list criterion
+        const int qa = __ffs(hit) - 1;
+        const Vec3 pi = real_position(f, ci), pap = super_position(f, apr, dummy);
+        // phase A: legs (i, x) for the whole row of i, then legs (a', k) for k != a' (slot k)
+        for (int it0 = 0; it0 < 2 * ni; it0 += 32) {
+            const int it = it0 + lane;
+            const bool centre_leg = it < ni;
+            const int k = centre_leg ? it : it - ni;
+            if (it < 2 * ni && (centre_leg || k != qa)) {
+                const Vec3 pk = super_position(f, __ldg(f.idx3 + rowi + k), dummy);
+                if (centre_leg) eval_sparse_leg<false>(B, 0, pi, pk, g.l0, lm + k * SPL_REC);
+                else eval_sparse_leg<true>(B, 2, pap, pk, g.n0, nn + k * SPN_REC);
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < ni; ++k) {            // lanes 0-15 own (P, Qx), lanes 16-31 (Qy, Qz)
+            if (k == qa) continue;
+            const unsigned lk = lm_s + (unsigned)k * SPL_REC, ns = nn_s + (unsigned)k * SPN_REC;
+            const unsigned mrel = (unsigned)(lds32(lk + SPL_IDX) + p), nrel = (unsigned)(lds32(ns + SPN_IDX) + q);
+            const bool ok = mrel < ma && nrel < na;
+            const unsigned ad = ok ? plane_s + 32u * (mrel * na + nrel) + 16u * (unsigned)half : dummy_s;
+            const double vm = lds64(lk + 8 * p), x = lds64(ns + off_a), dvn = lds64(ns + 32 + 8 * q);
+            const double2 w = lds128(ns + off_w);
+            double2 c = lds128(ad);
+            c.x = fma(vm * x, w.x, c.x);          // P += vm vn       | Qy += wy vm dvn
+            c.y = fma(vm * dvn, w.y, c.y);        // Qx += wx vm dvn  | Qz += wz vm dvn
+            sts128(ad, c);
+            __syncwarp();
+        }
+        plane_outer<false, KC>(B, g, plane_s, dummy_s, lm_s + (unsigned)qa * SPL_REC, bin0, n_cells, acc_s,
+                               lane, false);
+        __syncwarp();
+    }
+}
+
 // GLOBAL_ACC: the per-warp accumulators [4 * n_feats] live in a global scratch buffer
 // (L1/L2 resident) instead of shared memory — the path for bases whose rows do not fit
 // (e.g. 18 trio interactions of a ternary system, F ~ 7000).
 // KP = 1, 2 selects the register-tile path with KP (m, n) cells per lane; KP = 3 the
-// leg-grouped tile path.
+// leg-grouped tile path; KP = 4, 5, 6 the plane path with 1, 2, 4 chunks of 32 (m, n) cells.
 template <bool GLOBAL_ACC, int KP>
 __global__ void __launch_bounds__(256, 2)
 k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__restrict__ xf, long long ld,
@@ -517,7 +739,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
     const int gw = blockIdx.x * nw + warp, n_gw = gridDim.x * nw;
     const int F = B.n_feats;
     const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
-    unsigned char *mine = smem + (size_t)warp * featurize_warp_bytes(F, GLOBAL_ACC);
+    unsigned char *mine = smem + (size_t)warp * (size_t)tg.warp_bytes;
     double *acc = GLOBAL_ACC ? gacc + (size_t)gw * 4 * F : (double *)mine;
     unsigned char *scratch = mine + featurize_acc_bytes(F, GLOBAL_ACC);
     TriRec *recs = (TriRec *)scratch;
@@ -529,9 +751,22 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
 
     for (int k = lane; k < 4 * F; k += 32) acc[k] = 0.0;
     __syncwarp();
-    constexpr bool LEGS = KP == 3;
+    constexpr bool LEGS = KP == 3, PLANES = KP >= 4;
+    constexpr int KC = KP == 4 ? 1 : (KP == 5 ? 2 : 4);
     Tile<((KP == 1 || KP == 2) ? KP : 1)> tile;
-    if constexpr (KP > 0) tile.init(tg, lane);
+    if constexpr (KP > 0 && !PLANES) tile.init(tg, lane);
+    int bin0[KC];          // plane path: grid bin of (l0, m, n) for the lane's cells
+    if constexpr (PLANES) {
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const int cell = lane + 32 * kk, ok = cell < tg.ma * tg.na;
+            const int mi = ok ? cell / tg.na : 0, ni = ok ? cell % tg.na : 0;
+            bin0[kk] = tg.goff + (tg.l0 * tg.dim_m + tg.m0 + mi) * tg.dim_n + tg.n0 + ni;
+        }
+        double2 *plane = reinterpret_cast<double2 *>(scratch + SP_PLANE);
+        for (int k = lane; k < 2 * (tg.ma * tg.na + 1); k += 32) plane[k] = make_double2(0.0, 0.0);
+        __syncwarp();
+    }
 
     for (int a = gw; a < f.n; a += n_gw) {
         const int sa = __ldg(f.spec + a);
@@ -597,7 +832,9 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
         }
 
         // ------------------------------------------------ 3-body (angles.py:17-286)
-        if constexpr (LEGS) {
+        if constexpr (PLANES) {
+            plane_three_body<KC>(B, f, tg, a, pa, scratch, recs_s, acc_rw.base, bin0, lane, want_e, want_f);
+        } else if constexpr (LEGS) {
             legs_three_body(B, f, tg, a, pa, scratch, recs_s, tile, lane, want_e, want_f);
         } else if (B.n_trios > 0) {
             const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
@@ -651,7 +888,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
         }
 
         // ------------------------------------------------ rows fx_a, fy_a, fz_a
-        if constexpr (KP > 0) tile.flush(B, tg, acc_rw);
+        if constexpr (KP > 0 && !PLANES) tile.flush(B, tg, acc_rw);
         __syncwarp();
         if (want_f) {
             for (int col = lane; col < F; col += 32) {
@@ -712,16 +949,14 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         return UF3B_OK;
     }
 
-    // launch shape: as many warps per block as fit, grid sized to the SM count
-    int dev = 0, smem_max = 0;
+    // launch shape: as many warps per SM as shared memory and registers allow, grid sized to
+    // the SM count
+    int dev = 0, smem_max = 0, smem_sm = 0;
     UF3B_CUDA(cudaGetDevice(&dev));
     UF3B_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    UF3B_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     // accumulators in shared memory while at least two warps fit a block, else in global memory
     const bool global_acc = 2 * featurize_warp_bytes(F, false) > (size_t)smem_max;
-    const size_t per_warp = featurize_warp_bytes(F, global_acc);
-    int warps = global_acc ? 4 : 8;
-    while (warps > 1 && (size_t)warps * per_warp > (size_t)smem_max / 2) warps >>= 1;
-    const size_t smem = (size_t)warps * per_warp;
     // register-tile path: unary basis, unit folding weights, small untrimmed 3-body grid
     TileGeom tg = {};
     int kp = 0;
@@ -738,11 +973,37 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         // leg-grouped path: l and m legs interchangeable, every 3-body row fits one warp pass
         if (kp == 1 && tg.sym >= 2 && tg.la == tg.ma && tg.na <= 12 && nl->max3 <= 32 && !getenv("UF3B_NO_LEGS"))
             kp = 3;
+        // plane path: the same factorisation for larger grids (symmetry 2, up to 128 (m, n) cells)
+        const bool planes_ok = tg.sym == 2 && tg.la == tg.ma && tg.la >= 1 && tg.na >= 1
+                               && tg.ma * tg.na <= PL_MAX_CELLS && nl->max3 <= 32 && !getenv("UF3B_NO_LEGS")
+                               && !getenv("UF3B_NO_PLANES");
+        if (planes_ok && (kp == 0 || getenv("UF3B_PLANES")))
+            kp = tg.ma * tg.na <= 32 ? 4 : (tg.ma * tg.na <= 64 ? 5 : 6);
     }
-    auto kernel = global_acc ? k_featurize<true, 0>
-                             : (kp == 1 ? k_featurize<false, 1>
-                                : (kp == 2 ? k_featurize<false, 2>
-                                   : (kp == 3 ? k_featurize<false, 3> : k_featurize<false, 0>)));
+    const size_t scratch_bytes = kp >= 4 ? plane_scratch_bytes(tg.ma * tg.na) : ((WARP_SCRATCH + 15) & ~size_t(15));
+    const size_t per_warp = featurize_acc_bytes(F, global_acc) + scratch_bytes;
+    tg.warp_bytes = (int)per_warp;
+    // warps per block: the count that keeps most warps resident (128 registers per thread
+    // allow 16 warps per SM; each block also pays 1 KB of reserved shared memory)
+    int warps = 1, best = 0;
+    for (int w = global_acc ? 4 : 8; w >= 1; --w) {
+        const size_t blk = (size_t)w * per_warp;
+        if (blk > (size_t)smem_max) continue;
+        const int resident = std::min((int)((size_t)smem_sm / (blk + 1024)), 16 / w) * w;
+        if (resident > best) { best = resident; warps = w; }
+    }
+    const size_t smem = (size_t)warps * per_warp;
+    auto kernel = k_featurize<false, 0>;
+    switch (global_acc ? -1 : kp) {
+        case -1: kernel = k_featurize<true, 0>; break;
+        case 1: kernel = k_featurize<false, 1>; break;
+        case 2: kernel = k_featurize<false, 2>; break;
+        case 3: kernel = k_featurize<false, 3>; break;
+        case 4: kernel = k_featurize<false, 4>; break;
+        case 5: kernel = k_featurize<false, 5>; break;
+        case 6: kernel = k_featurize<false, 6>; break;
+        default: break;
+    }
     UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));

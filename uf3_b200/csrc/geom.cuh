@@ -13,10 +13,18 @@ __device__ __forceinline__ int pair_index(int ne, int a, int b) {
 
 struct Vec3 { double x, y, z; };
 
+// image rank g = m / n of supercell index m = g * n + atom (0 <= m < 2^31), exact: the
+// multiply-high estimate is at most one too small, one correction step fixes it.
+__device__ __forceinline__ int image_of(const FrameView &f, int m) {
+    int g = (int)__umulhi((unsigned)m, f.n_magic);
+    if (m - g * f.n >= f.n) ++g;
+    return g;
+}
+
 // Ghost position exactly as the reference builds it (data/geometry.py:146-147):
 // positions + image offset, one rounded addition per component.
 __device__ __forceinline__ Vec3 super_position(const FrameView &f, int m, int &atom) {
-    const int g = (int)((unsigned)m / (unsigned)f.n);
+    const int g = image_of(f, m);
     atom = m - g * f.n;
     Vec3 p;
     p.x = __dadd_rn(__ldg(f.pos + 3 * atom + 0), __ldg(f.img_off + 3 * g + 0));
@@ -66,6 +74,14 @@ __device__ __forceinline__ double lds64(unsigned a) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
     return v;
+}
+__device__ __forceinline__ int lds32(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory");
 }
 __device__ __forceinline__ double2 lds128(unsigned a) {
     double2 v;

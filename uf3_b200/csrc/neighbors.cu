@@ -474,6 +474,7 @@ static int scan_arrays(uf3b_nlist *nl, int n_arrays, const int *in0, int *out0, 
 FrameView uf3b_nlist::view() const {
     FrameView f;
     f.n = (int)n;
+    f.n_magic = n > 1 ? (unsigned)((1ull << 32) / (unsigned long long)n) : 0xffffffffu;
     f.n_img = n_img;
     f.pos = pos.p;
     f.spec = spec.p;

@@ -26,6 +26,7 @@ struct Triangle {
     int dim_m, dim_n;           // grid extents of legs m and n
     int lo[3], cnt[3];          // untrimmed part [lo, lo+cnt) of each leg's 4 basis functions
     double ujk[3];              // unit vector j -> k (after the atomic-number reordering)
+    double r[3];                // leg lengths r_ij, r_ik, r_jk (after the reordering)
     int atom_j, atom_k;         // parent atoms of j and k (after the reordering)
 };
 
@@ -80,6 +81,7 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
     const double ujk[3] = {(pk.x - pj.x) * in_, (pk.y - pj.y) * in_, (pk.z - pj.z) * in_};
     T.atom_j = aj;
     T.atom_k = ak;
+    T.r[0] = dij; T.r[1] = dik; T.r[2] = djk;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         T.ujk[c] = ujk[c];
@@ -115,7 +117,7 @@ __device__ __forceinline__ int publish_views(const BasisTab &B, const FrameView 
     int cnt = 0, ci = 0, apr = 0;
     if (e < n3a) {
         const int m = __ldg(f.idx3 + __ldg(f.off3 + a) + e);
-        const int g = (int)((unsigned)m / (unsigned)f.n);
+        const int g = image_of(f, m);
         ci = m - g * f.n;
         apr = __ldg(f.img_inv + g) * f.n + a;
         int dummy;

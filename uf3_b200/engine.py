@@ -132,13 +132,18 @@ class Engine:
             self._basis, self._nlist, _ptr(out_energy),
             C.c_void_p(forces_ptr) if forces_ptr else None, int(ld), stream))
 
-    def energy_forces(self, energy=True, forces=True, stream=None):
+    def energy_forces(self, energy=True, forces=True, virial=False, stream=None):
+        """(energy, forces [N,3]) of the current configuration; with `virial=True` also the
+        3x3 strain derivative W = dE/d(strain) (stress = W / volume) as a third item."""
         n = self.n_atoms
         e = np.zeros(1) if energy else None
         f = np.zeros((n, 3)) if forces else None
+        w = np.zeros((3, 3)) if virial else None
         _native.check(self._lib.uf3b_energy_forces(
             self._basis, self._nlist, _ptr(e) if energy else None,
-            _ptr(f) if (forces and n) else None, None, stream))
+            _ptr(f) if (forces and n) else None, _ptr(w) if virial else None, stream))
+        if virial:
+            return (float(e[0]) if energy else None), f, w
         return (float(e[0]) if energy else None), f
 
     def energy_forces_device(self, energy_ptr, forces_ptr, stream=None):
