@@ -10,5 +10,6 @@ for what in "$@"; do
     demo) python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>&1 | python -c "$summ" demo ;;
     man) python bench.py --steps 30 --warmup 5 --basis manuscript --no-cpu-baseline 2>&1 | python -c "$summ" manuscript ;;
     planes) UF3B_PLANES=1 python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>&1 | python -c "$summ" demo-planes ;;
+    *) env $what python bench.py --steps 30 --warmup 5 --no-cpu-baseline ${BASIS:+--basis $BASIS} 2>&1 | python -c "$summ" "$what" ;;
   esac
 done

@@ -171,12 +171,14 @@ def test_energy_forces_match_oracle_mid_size():
 def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     """Unary bases with a small untrimmed 3-body grid take the leg-grouped tile path of
     k_featurize (symmetry >= 2, rows <= 32), larger grids of symmetry 2 the plane path
-    (UF3B_PLANES forces it for small grids too), else the per-triangle register-tile path;
-    UF3B_NO_LEGS / UF3B_NO_TILE force the next more general path."""
+    as the cooperative block-per-atom kernel (UF3B_PLANES forces it for small grids too,
+    UF3B_NO_COOP selects the warp-per-atom plane path), else the per-triangle register-tile
+    path; UF3B_NO_LEGS / UF3B_NO_TILE force the next more general path."""
     case = gu.Case(name)
     outs = []
-    for env in ({}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"}, {"UF3B_PLANES": "1"}):
-        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES"):
+    for env in ({}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"}, {"UF3B_PLANES": "1"},
+                {"UF3B_PLANES": "1", "UF3B_NO_COOP": "1"}):
+        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES", "UF3B_NO_COOP"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
@@ -188,7 +190,7 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     for xe, xf in outs:
         assert gu.rel_err(xe, case["x_energy"]) <= REL
         assert gu.rel_err(xf, case["x_forces"]) <= REL
-    for other in (0, 1, 3):
+    for other in (0, 1, 3, 4):
         assert gu.rel_err(outs[other][1], outs[2][1]) <= 1e-11
         assert gu.rel_err(outs[other][0], outs[2][0]) <= 1e-11
 

@@ -725,6 +725,66 @@ __device__ __forceinline__ void plane_three_body(const BasisTab &B, const FrameV
     }
 }
 
+// 2-body rows of atom `a` (bspline.py:810-895) added into acc[4 * col + (e, fx, fy, fz)]:
+// lanes evaluate 32 pairs at a time into `prec`, then every lane gathers the records that
+// touch ITS feature column.
+__device__ __forceinline__ void two_body_rows(const BasisTab &B, const FrameView &f, int a, int sa, const Vec3 &pa,
+                                              double *acc, PairRec *prec, int lane) {
+    const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
+    for (int base = r0; base < r1; base += CHUNK) {
+        const int e = base + lane;
+        PairRec rec;
+        rec.col0 = -(1 << 20);
+        if (e < r1) {
+            int aj;
+            const Vec3 pj = super_position(f, __ldg(f.idx2 + e), aj);
+            const double d = dist_rn(pa, pj);
+            const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
+            const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
+                                     B.poly2 + __ldg(B.pair_poff + pr), d, B.lead2, B.trail2,
+                                     rec.v, rec.dv);
+            if (idx >= 0) {
+                rec.col0 = __ldg(B.pair_col + pr) + idx;
+                const double inv = 1.0 / d;
+                rec.u[0] = (pj.x - pa.x) * inv;
+                rec.u[1] = (pj.y - pa.y) * inv;
+                rec.u[2] = (pj.z - pa.z) * inv;
+            }
+        }
+        prec[lane] = rec;
+        __syncwarp();
+        const int count = min(CHUNK, r1 - base);
+        for (int sj = 0; sj < B.ne; ++sj) {
+            const int pr = pair_index(B.ne, sa, sj);
+            const int c0 = __ldg(B.pair_col + pr), nb = __ldg(B.pair_nk + pr) - 4;
+            for (int cb = 0; cb < nb; cb += 32) {
+                const int col = c0 + cb + lane;
+                double se = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+                for (int t = 0; t < count; ++t) {
+                    const unsigned r = (unsigned)(col - prec[t].col0);
+                    if (r < 4u) {
+                        se += prec[t].v[r];
+                        const double dv = prec[t].dv[r];
+                        sx += dv * prec[t].u[0];
+                        sy += dv * prec[t].u[1];
+                        sz += dv * prec[t].u[2];
+                    }
+                }
+                if (cb + lane < nb) {
+                    // every bond is seen from both ends (distances.py:118-120):
+                    // x[a] = 2 * sum_j B'(r_aj) (x_j - x_a) / r_aj
+                    double *dst = acc + 4 * (size_t)col;
+                    dst[0] += se;
+                    dst[1] += 2.0 * sx;
+                    dst[2] += 2.0 * sy;
+                    dst[3] += 2.0 * sz;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // GLOBAL_ACC: the per-warp accumulators [4 * n_feats] live in a global scratch buffer
 // (L1/L2 resident) instead of shared memory — the path for bases whose rows do not fit
 // (e.g. 18 trio interactions of a ternary system, F ~ 7000).
@@ -775,61 +835,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
         __syncwarp();
 
         // ------------------------------------------------ 2-body (bspline.py:810-895)
-        {
-            const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
-            for (int base = r0; base < r1; base += CHUNK) {
-                const int e = base + lane;
-                PairRec rec;
-                rec.col0 = -(1 << 20);
-                if (e < r1) {
-                    int aj;
-                    const Vec3 pj = super_position(f, __ldg(f.idx2 + e), aj);
-                    const double d = dist_rn(pa, pj);
-                    const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
-                    const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
-                                             B.poly2 + __ldg(B.pair_poff + pr), d, B.lead2, B.trail2,
-                                             rec.v, rec.dv);
-                    if (idx >= 0) {
-                        rec.col0 = __ldg(B.pair_col + pr) + idx;
-                        const double inv = 1.0 / d;
-                        rec.u[0] = (pj.x - pa.x) * inv;
-                        rec.u[1] = (pj.y - pa.y) * inv;
-                        rec.u[2] = (pj.z - pa.z) * inv;
-                    }
-                }
-                prec[lane] = rec;
-                __syncwarp();
-                const int count = min(CHUNK, r1 - base);
-                for (int sj = 0; sj < B.ne; ++sj) {
-                    const int pr = pair_index(B.ne, sa, sj);
-                    const int c0 = __ldg(B.pair_col + pr), nb = __ldg(B.pair_nk + pr) - 4;
-                    for (int cb = 0; cb < nb; cb += 32) {
-                        const int col = c0 + cb + lane;
-                        double se = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-                        for (int t = 0; t < count; ++t) {
-                            const unsigned r = (unsigned)(col - prec[t].col0);
-                            if (r < 4u) {
-                                se += prec[t].v[r];
-                                const double dv = prec[t].dv[r];
-                                sx += dv * prec[t].u[0];
-                                sy += dv * prec[t].u[1];
-                                sz += dv * prec[t].u[2];
-                            }
-                        }
-                        if (cb + lane < nb) {
-                            // every bond is seen from both ends (distances.py:118-120):
-                            // x[a] = 2 * sum_j B'(r_aj) (x_j - x_a) / r_aj
-                            double *dst = acc + 4 * (size_t)col;
-                            dst[0] += se;
-                            dst[1] += 2.0 * sx;
-                            dst[2] += 2.0 * sy;
-                            dst[3] += 2.0 * sz;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
+        two_body_rows(B, f, a, sa, pa, acc, prec, lane);
 
         // ------------------------------------------------ 3-body (angles.py:17-286)
         if constexpr (PLANES) {
@@ -905,6 +911,300 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
         for (int col = lane; col < F; col += 32) partials[(size_t)gw * F + col] = acc[4 * col];
 }
 
+// ---------------------------------------------------------------- cooperative plane kernel
+// k_featurize_coop: one BLOCK of W = ceil(cells / 32) warps owns one atom; thread = one
+// (m, n) cell of the untrimmed grid and keeps that cell's accumulators for every l in
+// REGISTERS ([la][e, fx, fy, fz]).  The plane kernel above spends its time moving
+// accumulator quads through shared memory (one read-modify-write per (group, l, cell): the
+// LSU data pipe was 81 % busy, half of it bank conflicts); here shared memory only carries
+// the sparse leg records and the partner-sum planes:
+//   round:  warp w takes leg group g0 + w (groups 0..n3-1: `a` is the centre and the group
+//           is its leg to neighbour j; groups n3..2 n3-1: `a` is a neighbour of centre i),
+//           evaluates the group's legs and builds ITS plane P[m,n] (, Q[m,n]) as before;
+//           __syncthreads; every thread reads its cell from each of the W planes and adds
+//           the 4 non-zero l terms of that group to its registers; __syncthreads.
+//   atom end: registers are folded into the block's column accumulators (bin_col; bins
+//           with l <= m first, then l > m, so the two mirror bins of a column never race)
+//           and the three rows are written with all threads.
+// Plane layout: two arrays per warp with a row stride `nap` = na rounded up to 4 mod 8
+// cells, so the 16 (p, q) products of a partner fall in distinct banks — (P, Qx) and
+// (Qy, Qz) as 16-byte entries for the neighbour role, P split over even / odd partners
+// as 8-byte entries for the centre role.
+constexpr unsigned GL_REC = 160;        // group leg, dense: (V[l], DV[l]) x 8, u[3], {idx, role}
+constexpr int CO_LA = 8;                // max untrimmed l extent
+
+struct CoopGeom {
+    TileGeom g;
+    int warps;              // per block
+    int nap;                // plane row stride in cells
+    int slots;              // leg records per table
+    int off_ltab, off_gleg; // block-shared: legs of the atom's own row; W group legs
+    int off_warp, warp_bytes;   // per-warp region: [L records][N records][plane A][plane B][dummy]
+    int off_plane;          // of plane A inside the warp region
+    int plane_bytes;        // of one plane array
+};
+
+// n leg record for the cooperative kernel (96 B): v[4] dv[4] {idx - x0 bits, wx} {wy, wz}
+__device__ __forceinline__ void eval_n_leg(const BasisTab &B, const Vec3 &from, const Vec3 &to, int x0,
+                                           unsigned char *out) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0}, dv[4] = {0.0, 0.0, 0.0, 0.0};
+    const double d = dist_rn(from, to);
+    const int nk = __ldg(B.trio_nk + 2);
+    const double *t = B.knots3 + __ldg(B.trio_koff + 2);
+    double inv = 0.0;
+    int rel = SP_DEAD;
+    if (d >= t[0] && d <= t[nk - 1]) {
+        const int idx = eval_leg(t, nk, __ldg(B.trio_scale + 2), B.poly3 + __ldg(B.trio_poff + 2), d,
+                                 B.lead3, B.trail3, v, dv);
+        if (idx >= 0) rel = idx - x0;
+        inv = fast_rcp(d);
+    }
+    double2 *o = reinterpret_cast<double2 *>(out);
+    o[0] = make_double2(v[0], v[1]);
+    o[1] = make_double2(v[2], v[3]);
+    o[2] = make_double2(dv[0], dv[1]);
+    o[3] = make_double2(dv[2], dv[3]);
+    o[4] = make_double2(__longlong_as_double((long long)(unsigned)rel), (to.x - from.x) * inv);
+    o[5] = make_double2((to.y - from.y) * inv, (to.z - from.z) * inv);
+}
+
+// Publish the group's own leg (sparse record `src`) densely for the consumers.
+__device__ __forceinline__ void publish_group_leg(unsigned src, unsigned dst, int role, int lane) {
+    const int rel = lds32(src + SPL_IDX);
+    if (lane < CO_LA) {
+        const unsigned r = (unsigned)(lane - rel);
+        const bool in = r < 4u;
+        const double v = in ? lds64(src + 8u * (in ? r : 0u)) : 0.0;
+        const double dv = in ? lds64(src + 32u + 8u * (in ? r : 0u)) : 0.0;
+        sts128(dst + 16u * (unsigned)lane, make_double2(v, dv));
+    } else if (lane == CO_LA) {
+        sts128(dst + 128, lds128(src + 64));                               // ux, uy
+    } else if (lane == CO_LA + 1) {
+        const long long tag = ((long long)role << 32) | (unsigned)rel;
+        sts128(dst + 144, make_double2(lds64(src + 80), __longlong_as_double(tag)));   // uz, {idx, role}
+    }
+}
+
+template <int LA>
+__global__ void __launch_bounds__(128, 4)
+k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double *__restrict__ xf, long long ld,
+                 double *__restrict__ partials, int want_e_, int want_f_) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TileGeom &g = cg.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = cg.warps;
+    const int F = B.n_feats;
+    const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
+    double *acc = reinterpret_cast<double *>(smem);                         // [F][e, fx, fy, fz]
+    const unsigned smem_s = pin(smem_addr(smem));
+    const unsigned ltab_s = smem_s + (unsigned)cg.off_ltab, gleg_s = smem_s + (unsigned)cg.off_gleg;
+    unsigned char *mine = smem + cg.off_warp + warp * cg.warp_bytes;
+    const unsigned mine_s = smem_s + (unsigned)(cg.off_warp + warp * cg.warp_bytes);
+    unsigned char *lm = mine, *nn = mine + cg.slots * SPL_REC;
+    const unsigned lm_s = mine_s, nn_s = mine_s + (unsigned)cg.slots * SPL_REC;
+    const unsigned pl_a = mine_s + (unsigned)cg.off_plane, pl_b = pl_a + (unsigned)cg.plane_bytes;
+    const unsigned dummy_s = pl_b + (unsigned)cg.plane_bytes;
+    PairRec *prec = reinterpret_cast<PairRec *>(mine);
+
+    // the thread's cell
+    const int n_cells = g.ma * g.na;
+    const bool has_cell = tid < n_cells;
+    const int mi = has_cell ? tid / g.na : 0, ni = has_cell ? tid % g.na : 0;
+    const unsigned cellp = (unsigned)(mi * cg.nap + ni);
+    const int lmn = g.dim_m * g.dim_n;
+    const int bin_base = g.goff + (g.l0 * g.dim_m + g.m0 + mi) * g.dim_n + g.n0 + ni;
+    const unsigned ma = (unsigned)g.ma, na = (unsigned)g.na, nap = (unsigned)cg.nap;
+    const int half = lane >> 4, p = (lane >> 2) & 3, q = lane & 3;
+    const double half_e = want_e ? 0.5 : 0.0;
+
+    double r[LA][4];
+#pragma unroll
+    for (int l = 0; l < LA; ++l)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[l][c] = 0.0;
+    for (int k = tid; k < 4 * F; k += blockDim.x) acc[k] = 0.0;
+    {
+        double2 *z = reinterpret_cast<double2 *>(mine + cg.off_plane);
+        for (int k = lane; k < (2 * cg.plane_bytes + 32) / 16; k += 32) z[k] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    int dummy;
+
+    for (int a = blockIdx.x; a < f.n; a += gridDim.x) {
+        const int sa = __ldg(f.spec + a);
+        const Vec3 pa = real_position(f, a);
+        const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
+        // legs of a's own row (last warp) while warp 0 does the pair rows
+        if (warp == W - 1 && lane < n3a)
+            eval_sparse_leg<false>(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0,
+                                   smem + cg.off_ltab + lane * SPL_REC);
+        if (warp == 0) {
+            if (lane == 0) acc[4 * sa] += 1.0;      // composition column n_el (composition.py:96-111)
+            __syncwarp();
+            two_body_rows(B, f, a, sa, pa, acc, prec, lane);
+        }
+        __syncthreads();
+
+        const int n_groups = n3a < 1 ? 0 : (want_f ? 2 * n3a : (n3a > 1 ? n3a : 0));
+        for (int g0 = 0; g0 < n_groups; g0 += W) {
+            const int gs = g0 + warp;
+            int role = 0;                         // 0 none, 1 centre, 2 neighbour
+            if (gs < n3a) {
+                // ---- `a` is the centre, the group is its leg to neighbour j
+                const int j = gs;
+                if (n3a > 1) {
+                    if (lane < n3a && lane != j)
+                        eval_n_leg(B, super_position(f, __ldg(f.idx3 + row0 + j), dummy),
+                                   super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.n0, nn + lane * SPL_REC);
+                    __syncwarp();
+                    for (int k0 = 0; k0 < n3a; k0 += 2) {     // two partners per pass, one per half-warp
+                        const int k = min(k0 + half, n3a - 1);
+                        const unsigned lk = ltab_s + (unsigned)k * SPL_REC, ns = nn_s + (unsigned)k * SPL_REC;
+                        const unsigned mrel = (unsigned)(lds32(lk + SPL_IDX) + p);
+                        const unsigned nrel = (unsigned)(k == j ? SP_DEAD : lds32(ns + 64) + q);
+                        const bool ok = mrel < ma && nrel < na && k0 + half < n3a;
+                        const unsigned ad = ok ? (half ? pl_b : pl_a) + 8u * (mrel * nap + nrel) : dummy_s;
+                        sts64(ad, fma(lds64(lk + 8 * p), lds64(ns + 8 * q), lds64(ad)));
+                        __syncwarp();
+                    }
+                    publish_group_leg(ltab_s + (unsigned)j * SPL_REC, gleg_s + (unsigned)warp * GL_REC, 1, lane);
+                    role = 1;
+                }
+            } else if (gs < n_groups) {
+                // ---- `a` is a neighbour of centre i = entry e of its list
+                const int m = __ldg(f.idx3 + row0 + (gs - n3a));
+                const int gimg = image_of(f, m);
+                const int ci = m - gimg * f.n;
+                const int apr = __ldg(f.img_inv + gimg) * f.n + a;
+                const int rowi = __ldg(f.off3 + ci), ni_ = __ldg(f.cnt3 + ci);
+                const int its = lane < ni_ ? __ldg(f.idx3 + rowi + lane) : -1;
+                const unsigned hit = __ballot_sync(FULL, its == apr);
+                if (hit) {                        // (a miss: one-ulp asymmetry of the list criterion)
+                    const int qa = __ffs(hit) - 1;
+                    const Vec3 pi = real_position(f, ci), pap = super_position(f, apr, dummy);
+                    for (int it0 = 0; it0 < 2 * ni_; it0 += 32) {
+                        const int it = it0 + lane;
+                        const bool centre_leg = it < ni_;
+                        const int k = centre_leg ? it : it - ni_;
+                        if (it < 2 * ni_ && (centre_leg || k != qa)) {
+                            const Vec3 pk = super_position(f, __ldg(f.idx3 + rowi + k), dummy);
+                            if (centre_leg) eval_sparse_leg<false>(B, 0, pi, pk, g.l0, lm + k * SPL_REC);
+                            else eval_n_leg(B, pap, pk, g.n0, nn + k * SPL_REC);
+                        }
+                    }
+                    __syncwarp();
+                    const unsigned off_x = 32u * (unsigned)half + 8u * (unsigned)q;      // v[q] | dv[q]
+                    const unsigned off_w = 64u + 16u * (unsigned)half;                   // (idx, wx) | (wy, wz)
+                    const unsigned pl = half ? pl_b : pl_a;
+                    for (int k = 0; k < ni_; ++k) {           // lanes 0-15 own (P, Qx), lanes 16-31 (Qy, Qz)
+                        if (k == qa) continue;
+                        const unsigned lk = lm_s + (unsigned)k * SPL_REC, ns = nn_s + (unsigned)k * SPL_REC;
+                        const unsigned mrel = (unsigned)(lds32(lk + SPL_IDX) + p), nrel = (unsigned)(lds32(ns + 64) + q);
+                        const bool ok = mrel < ma && nrel < na;
+                        const unsigned ad = ok ? pl + 16u * (mrel * nap + nrel) : dummy_s;
+                        const double vm = lds64(lk + 8 * p), x = lds64(ns + off_x), dvn = lds64(ns + 32 + 8 * q);
+                        const double2 w = lds128(ns + off_w);
+                        double2 c = lds128(ad);
+                        c.x = fma(vm * x, half ? w.x : 1.0, c.x);      // P += vm vn       | Qy += wy vm dvn
+                        c.y = fma(vm * dvn, w.y, c.y);                 // Qx += wx vm dvn  | Qz += wz vm dvn
+                        sts128(ad, c);
+                        __syncwarp();
+                    }
+                    publish_group_leg(lm_s + (unsigned)qa * SPL_REC, gleg_s + (unsigned)warp * GL_REC, 2, lane);
+                    role = 2;
+                }
+            }
+            if (role == 0 && lane == 0) sts128(gleg_s + (unsigned)warp * GL_REC + 144, make_double2(0.0, 0.0));
+            __syncthreads();
+
+            // ---- consume: every thread adds the W published groups to its cell's registers
+            for (int w2 = 0; w2 < W; ++w2) {
+                const unsigned gl = gleg_s + (unsigned)w2 * GL_REC;
+                const int il = lds32(gl + 152), grole = lds32(gl + 156);
+                if (grole == 0) continue;         // block-uniform
+                const unsigned wa = smem_s + (unsigned)(cg.off_warp + w2 * cg.warp_bytes + cg.off_plane);
+                const unsigned wb = wa + (unsigned)cg.plane_bytes;
+                const double2 u01 = lds128(gl + 128);
+                const double u2 = lds64(gl + 144);
+                if (grole == 1) {
+                    double P = 0.0;
+                    if (has_cell) {
+                        P = lds64(wa + 8u * cellp) + lds64(wb + 8u * cellp);
+                        sts64(wa + 8u * cellp, 0.0);
+                        sts64(wb + 8u * cellp, 0.0);
+                    }
+#pragma unroll
+                    for (int l = 0; l < LA; ++l) {
+                        if ((unsigned)(l - il) < 4u) {        // block-uniform: the leg's 4 non-zero l
+                            const double2 vd = lds128(gl + 16u * (unsigned)l);
+                            const double dP = vd.y * P;
+                            r[l][0] = fma(half_e * vd.x, P, r[l][0]);
+                            r[l][1] = fma(u01.x, dP, r[l][1]);
+                            r[l][2] = fma(u01.y, dP, r[l][2]);
+                            r[l][3] = fma(u2, dP, r[l][3]);
+                        }
+                    }
+                } else {
+                    double2 pq = make_double2(0.0, 0.0), qq = make_double2(0.0, 0.0);
+                    if (has_cell) {
+                        pq = lds128(wa + 16u * cellp);
+                        qq = lds128(wb + 16u * cellp);
+                        sts128(wa + 16u * cellp, make_double2(0.0, 0.0));
+                        sts128(wb + 16u * cellp, make_double2(0.0, 0.0));
+                    }
+#pragma unroll
+                    for (int l = 0; l < LA; ++l) {
+                        if ((unsigned)(l - il) < 4u) {
+                            const double2 vd = lds128(gl + 16u * (unsigned)l);
+                            const double dP = vd.y * pq.x;
+                            r[l][1] += vd.x * pq.y - u01.x * dP;
+                            r[l][2] += vd.x * qq.x - u01.y * dP;
+                            r[l][3] += vd.x * qq.y - u2 * dP;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- fold the registers into the column accumulators: bins with l <= m, then l > m
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+            for (int l = 0; l < LA; ++l) {
+                if (l < g.la && has_cell && ((g.l0 + l > g.m0 + mi) == (ph == 1))) {
+                    const int col = __ldg(B.bin_col + bin_base + l * lmn);
+                    if (col >= 0) {
+                        double2 *dst = reinterpret_cast<double2 *>(acc + 4 * (size_t)(g.col0 + col));
+                        double2 u = dst[0], w = dst[1];
+                        u.x += r[l][0]; u.y += r[l][1]; w.x += r[l][2]; w.y += r[l][3];
+                        dst[0] = u;
+                        dst[1] = w;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int l = 0; l < LA; ++l)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) r[l][c] = 0.0;
+
+        // ---- rows fx_a, fy_a, fz_a
+        if (want_f) {
+            for (int col = tid; col < F; col += blockDim.x) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    xf[((long long)c * f.n + a) * ld + col] = acc[4 * col + 1 + c];
+                    acc[4 * col + 1 + c] = 0.0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (want_e)
+        for (int col = tid; col < F; col += blockDim.x) partials[(size_t)blockIdx.x * F + col] = acc[4 * col];
+}
+
 // Energy row = element counts (composition.py:96-111) + fixed-order sum of the warps'
 // partial rows.  One block per 32 feature columns: warp w sums rows w, w+8, ... with
 // coalesced reads, then the eight per-warp sums are added in a fixed order.
@@ -930,6 +1230,31 @@ k_energy_row(const double *__restrict__ partials, int n_rows, int n_feats, int n
 }  // namespace uf3b
 
 using namespace uf3b;
+
+// Copies to host buffers (if any), synchronisation and kernel timing shared by the launch paths.
+static int finish_featurize(uf3b_basis *basis, double *x_energy, double *x_forces, int64_t ld, double *d_xe,
+                            double *d_xf, int F, int n, bool e_dev, bool f_dev, cudaStream_t stream,
+                            cudaEvent_t ev0, cudaEvent_t ev1) {
+    bool need_sync = g_timing;
+    if (x_forces && !f_dev) {
+        UF3B_CUDA(cudaMemcpy2DAsync(x_forces, sizeof(double) * ld, d_xf, sizeof(double) * F,
+                                    sizeof(double) * F, (size_t)3 * n, cudaMemcpyDeviceToHost, stream));
+        need_sync = true;
+    }
+    if (x_energy && !e_dev) {
+        UF3B_CUDA(cudaMemcpyAsync(x_energy, d_xe, sizeof(double) * F, cudaMemcpyDeviceToHost, stream));
+        need_sync = true;
+    }
+    if (need_sync) UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (g_timing) {
+        float ms = 0.f;
+        UF3B_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        g_last_kernel_ms = ms;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return UF3B_OK;
+}
 
 extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy,
                               double *x_forces, int64_t ld, void *stream_) {
@@ -979,6 +1304,61 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                                && !getenv("UF3B_NO_PLANES");
         if (planes_ok && (kp == 0 || getenv("UF3B_PLANES")))
             kp = tg.ma * tg.na <= 32 ? 4 : (tg.ma * tg.na <= 64 ? 5 : 6);
+    }
+    // cooperative plane kernel: one block per atom, thread = (m, n) cell, registers hold the l axis
+    const bool coop = kp >= 4 && tg.la <= CO_LA && !getenv("UF3B_NO_COOP");
+    if (coop) {
+        CoopGeom cg = {};
+        cg.g = tg;
+        const int n_cells = tg.ma * tg.na;
+        cg.warps = (n_cells + 31) / 32;
+        if (cg.warps == 3) cg.warps = 4;
+        cg.nap = tg.na + ((4 - tg.na % 8) + 8) % 8;
+        cg.slots = std::max(16, std::min(32, (nl->max3 + 3) & ~3));
+        cg.plane_bytes = tg.ma * cg.nap * 16;
+        cg.off_ltab = (int)featurize_acc_bytes(F, false);
+        cg.off_gleg = cg.off_ltab + cg.slots * (int)SPL_REC;
+        cg.off_warp = cg.off_gleg + cg.warps * (int)GL_REC;
+        cg.off_plane = 2 * cg.slots * (int)SPL_REC;
+        cg.warp_bytes = cg.off_plane + 2 * cg.plane_bytes + 32;
+        const size_t smem_c = (size_t)cg.off_warp + (size_t)cg.warps * cg.warp_bytes;
+        auto kc = tg.la <= 4 ? k_featurize_coop<4> : k_featurize_coop<8>;
+        if (smem_c <= (size_t)smem_max) {
+            UF3B_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+            int per_sm = 1;
+            UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc, cg.warps * 32, smem_c));
+            if (per_sm < 1) per_sm = 1;
+            int grid = std::min(sm_count() * per_sm, n);
+            double *d_xf = x_forces;
+            long long d_ld = ld;
+            if (x_forces && !f_dev) {
+                UF3B_CUDA(basis->stage.reserve((size_t)3 * n * F));
+                d_xf = basis->stage.p;
+                d_ld = F;
+            }
+            double *d_xe = x_energy;
+            if (x_energy) {
+                UF3B_CUDA(basis->partials.reserve((size_t)grid * F));
+                if (!e_dev) {
+                    UF3B_CUDA(basis->stage_e.reserve(F));
+                    d_xe = basis->stage_e.p;
+                }
+            }
+            const FrameView view = nl->view();
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (g_timing) {
+                UF3B_CUDA(cudaEventCreate(&ev0));
+                UF3B_CUDA(cudaEventCreate(&ev1));
+                UF3B_CUDA(cudaEventRecord(ev0, stream));
+            }
+            UF3B_LAUNCH(kc, grid, cg.warps * 32, smem_c, stream, basis->tab, view, cg, d_xf, d_ld,
+                        basis->partials.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
+            if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
+            if (x_energy)
+                UF3B_LAUNCH(k_energy_row, (F + 31) / 32, 256, 0, stream, basis->partials.p, grid, F, basis->tab.ne,
+                            view.spec, n, d_xe);
+            return finish_featurize(basis, x_energy, x_forces, ld, d_xe, d_xf, F, n, e_dev, f_dev, stream, ev0, ev1);
+        }
     }
     const size_t scratch_bytes = kp >= 4 ? plane_scratch_bytes(tg.ma * tg.na) : ((WARP_SCRATCH + 15) & ~size_t(15));
     const size_t per_warp = featurize_acc_bytes(F, global_acc) + scratch_bytes;
@@ -1045,23 +1425,5 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     if (x_energy)
         UF3B_LAUNCH(k_energy_row, (F + 31) / 32, 256, 0, stream, basis->partials.p, n_gw, F, basis->tab.ne,
                     view.spec, n, d_xe);
-    bool need_sync = g_timing;
-    if (x_forces && !f_dev) {
-        UF3B_CUDA(cudaMemcpy2DAsync(x_forces, sizeof(double) * ld, d_xf, sizeof(double) * F,
-                                    sizeof(double) * F, (size_t)3 * n, cudaMemcpyDeviceToHost, stream));
-        need_sync = true;
-    }
-    if (x_energy && !e_dev) {
-        UF3B_CUDA(cudaMemcpyAsync(x_energy, d_xe, sizeof(double) * F, cudaMemcpyDeviceToHost, stream));
-        need_sync = true;
-    }
-    if (need_sync) UF3B_CUDA(cudaStreamSynchronize(stream));
-    if (g_timing) {
-        float ms = 0.f;
-        UF3B_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-        g_last_kernel_ms = ms;
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
-    }
-    return UF3B_OK;
+    return finish_featurize(basis, x_energy, x_forces, ld, d_xe, d_xf, F, n, e_dev, f_dev, stream, ev0, ev1);
 }
