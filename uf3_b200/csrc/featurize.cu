@@ -985,6 +985,43 @@ __device__ __forceinline__ void publish_group_leg(unsigned src, unsigned dst, in
     }
 }
 
+// One published group added to the thread's registers: the 4 l values IL..IL+3 of the
+// group's leg, statically indexed (the switch in add_group picks IL = idx - l0).
+template <int LA, int IL, bool CENTRE>
+__device__ __forceinline__ void add_group_at(double (&r)[LA][4], unsigned gl, double P, double qx, double qy,
+                                             double qz, double ux, double uy, double uz, double half_e) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        constexpr int L0 = IL;
+        const int l = L0 + p;
+        if (l >= 0 && l < LA) {
+            const double2 vd = lds128(gl + 16u * (unsigned)l);     // (B_l, B'_l) of the group's leg
+            const double dP = vd.y * P;
+            if (CENTRE) {
+                r[l][0] = fma(half_e * vd.x, P, r[l][0]);
+                r[l][1] = fma(ux, dP, r[l][1]);
+                r[l][2] = fma(uy, dP, r[l][2]);
+                r[l][3] = fma(uz, dP, r[l][3]);
+            } else {
+                r[l][1] += vd.x * qx - ux * dP;
+                r[l][2] += vd.x * qy - uy * dP;
+                r[l][3] += vd.x * qz - uz * dP;
+            }
+        }
+    }
+}
+template <int LA, bool CENTRE>
+__device__ __forceinline__ void add_group(double (&r)[LA][4], int il, unsigned gl, double P, double qx, double qy,
+                                          double qz, double ux, double uy, double uz, double half_e) {
+#define UF3B_CASE(IL) case IL: if (IL < LA) add_group_at<LA, IL, CENTRE>(r, gl, P, qx, qy, qz, ux, uy, uz, half_e); break;
+    switch (il) {
+        UF3B_CASE(-3) UF3B_CASE(-2) UF3B_CASE(-1) UF3B_CASE(0) UF3B_CASE(1) UF3B_CASE(2) UF3B_CASE(3)
+        UF3B_CASE(4) UF3B_CASE(5) UF3B_CASE(6) UF3B_CASE(7)
+        default: break;
+    }
+#undef UF3B_CASE
+}
+
 template <int LA>
 __global__ void __launch_bounds__(128, 4)
 k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double *__restrict__ xf, long long ld,
@@ -1033,22 +1070,34 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
         const int sa = __ldg(f.spec + a);
         const Vec3 pa = real_position(f, a);
         const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
-        // legs of a's own row (last warp) while warp 0 does the pair rows
-        if (warp == W - 1 && lane < n3a)
-            eval_sparse_leg<false>(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0,
-                                   smem + cg.off_ltab + lane * SPL_REC);
-        if (warp == 0) {
-            if (lane == 0) acc[4 * sa] += 1.0;      // composition column n_el (composition.py:96-111)
-            __syncwarp();
-            two_body_rows(B, f, a, sa, pa, acc, prec, lane);
+        // work slots of the atom, dealt to the warps W at a time: slot 0 = pair rows, then the
+        // neighbour-role groups, then the centre-role groups.  The legs of a's own row are only
+        // read by centre-role groups: the warp of slot 1 evaluates them in round 0 unless a
+        // centre group already falls into round 0 (few neighbours / energy only).
+        const int c0 = 1 + (want_f ? n3a : 0);        // first centre-role slot
+        const int n_slots = c0 + (n3a > 1 ? n3a : 0);
+        const bool early = c0 < W;
+        if (early) {
+            if (warp == 0 && lane < n3a)
+                eval_sparse_leg<false>(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0,
+                                       smem + cg.off_ltab + lane * SPL_REC);
+            __syncthreads();
         }
-        __syncthreads();
-
-        const int n_groups = n3a < 1 ? 0 : (want_f ? 2 * n3a : (n3a > 1 ? n3a : 0));
-        for (int g0 = 0; g0 < n_groups; g0 += W) {
-            const int gs = g0 + warp;
+        for (int g0 = 0; g0 < n_slots; g0 += W) {
+            const int slot = g0 + warp;
+            if (!early && slot == (W > 1 ? 1 : 0) && lane < n3a)
+                eval_sparse_leg<false>(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0,
+                                       smem + cg.off_ltab + lane * SPL_REC);
+            if (slot == 0) {
+                if (lane == 0) acc[4 * sa] += 1.0;      // composition column n_el (composition.py:96-111)
+                __syncwarp();
+                two_body_rows(B, f, a, sa, pa, acc, prec, lane);
+            }
+            // gs: group index in the old numbering (centre groups 0..n3a-1, neighbour groups n3a..)
+            const int gs = slot == 0 ? -1 : (slot < c0 ? n3a + (slot - 1) : (slot < n_slots ? slot - c0 : -1));
+            const int n_groups = 2 * n3a;
             int role = 0;                         // 0 none, 1 centre, 2 neighbour
-            if (gs < n3a) {
+            if (gs >= 0 && gs < n3a) {
                 // ---- `a` is the centre, the group is its leg to neighbour j
                 const int j = gs;
                 if (n3a > 1) {
@@ -1069,7 +1118,7 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
                     publish_group_leg(ltab_s + (unsigned)j * SPL_REC, gleg_s + (unsigned)warp * GL_REC, 1, lane);
                     role = 1;
                 }
-            } else if (gs < n_groups) {
+            } else if (gs >= n3a && gs < n_groups) {
                 // ---- `a` is a neighbour of centre i = entry e of its list
                 const int m = __ldg(f.idx3 + row0 + (gs - n3a));
                 const int gimg = image_of(f, m);
@@ -1132,17 +1181,7 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
                         sts64(wa + 8u * cellp, 0.0);
                         sts64(wb + 8u * cellp, 0.0);
                     }
-#pragma unroll
-                    for (int l = 0; l < LA; ++l) {
-                        if ((unsigned)(l - il) < 4u) {        // block-uniform: the leg's 4 non-zero l
-                            const double2 vd = lds128(gl + 16u * (unsigned)l);
-                            const double dP = vd.y * P;
-                            r[l][0] = fma(half_e * vd.x, P, r[l][0]);
-                            r[l][1] = fma(u01.x, dP, r[l][1]);
-                            r[l][2] = fma(u01.y, dP, r[l][2]);
-                            r[l][3] = fma(u2, dP, r[l][3]);
-                        }
-                    }
+                    add_group<LA, true>(r, il, gl, P, 0.0, 0.0, 0.0, u01.x, u01.y, u2, half_e);
                 } else {
                     double2 pq = make_double2(0.0, 0.0), qq = make_double2(0.0, 0.0);
                     if (has_cell) {
@@ -1151,16 +1190,7 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
                         sts128(wa + 16u * cellp, make_double2(0.0, 0.0));
                         sts128(wb + 16u * cellp, make_double2(0.0, 0.0));
                     }
-#pragma unroll
-                    for (int l = 0; l < LA; ++l) {
-                        if ((unsigned)(l - il) < 4u) {
-                            const double2 vd = lds128(gl + 16u * (unsigned)l);
-                            const double dP = vd.y * pq.x;
-                            r[l][1] += vd.x * pq.y - u01.x * dP;
-                            r[l][2] += vd.x * qq.x - u01.y * dP;
-                            r[l][3] += vd.x * qq.y - u2 * dP;
-                        }
-                    }
+                    add_group<LA, false>(r, il, gl, pq.x, pq.y, qq.x, qq.y, u01.x, u01.y, u2, half_e);
                 }
             }
             __syncthreads();
