@@ -425,6 +425,86 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- MD strong scaling
+def run_md(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: velocity-Verlet loop on ONE 100 000-atom W frame, forces from
+    the 2+3-body model every step, atoms split over the ranks by index range
+    (uf3_b200.distributed.ShardedEvaluator: own-range neighbour rows + evaluator, one NCCL
+    all-reduce of 3N+1 doubles per step).  Strong scaling: total work fixed."""
+    import torch
+    import torch.distributed as dist
+    from uf3_b200 import bspline, composition, geometry, synthetic
+    from uf3_b200.distributed import ShardedEvaluator
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    data = np.load(os.path.join(ROOT, "tests", "golden", "calc_syn_w54_model23.npz"))
+    cfg = json.loads(str(data["config"]))
+    knots = {}
+    for key, val in cfg["kwargs"]["knots_map"].items():
+        parts = tuple(key.split("-"))
+        knots[parts] = np.array(val) if len(parts) == 2 else [np.array(v) for v in val]
+    chem = composition.ChemicalSystem(cfg["element_list"], degree=cfg["degree"])
+    lead = {int(k): v for k, v in cfg["kwargs"]["leading_trim"].items()}
+    trail = {int(k): v for k, v in cfg["kwargs"]["trailing_trim"].items()}
+    basis = bspline.BSplineBasis(chem, knots_map=knots, leading_trim=lead, trailing_trim=trail)
+    pos, numbers, cell, pbc = synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0)
+    n = len(pos)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    ev = ShardedEvaluator(basis, np.array(data["coefficients"]), device=local_rank)
+    x = torch.from_numpy(pos).to(dev)
+    z = torch.from_numpy(numbers).to(dev)
+    v = torch.zeros_like(x)
+    dt, inv_m = args.dt, 9.648533e-3 / 183.84      # fs; (eV/A)/amu -> A/fs^2
+
+    def step(f):
+        v.add_(f, alpha=0.5 * dt * inv_m)
+        x.add_(v, alpha=dt)
+        e, f_new = ev.energy_forces(x, z, images)
+        v.add_(f_new, alpha=0.5 * dt * inv_m)
+        return e, f_new
+
+    e0, f = ev.energy_forces(x, z, images)
+    for _ in range(args.warmup):
+        e, f = step(f)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = ev.engine.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        e, f = step(f)
+    stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = ev.engine.launch_count() - launches0
+    if rank == 0:
+        ke = 0.5 * 183.84 / 9.648533e-3 * float((v * v).sum())
+        print(json.dumps({
+            "metric": "atom-steps/s, MD loop (neighbour lists + energy + forces per step) on 100k-atom W",
+            "value": n * args.steps / (ms * 1e-3), "unit": "atom-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "bulk bcc W 25x40x50 cells (100000 atoms), a=3.206 A, sigma=0.15 A, "
+                                   f"velocity Verlet dt={args.dt} fs, model_2and3 (2+3-body)",
+                       "partition": "atom ranges, replicated positions, one all-reduce of 3N+1 doubles per step"},
+            "gpu_launches": launches,
+            "energy_drift_eV": float(e) + ke - float(e0), "energy0_eV": float(e0)}), flush=True)
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,12 +514,17 @@ def main():
     ap.add_argument("--basis", default="demo", choices=["demo", "manuscript"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
     ap.add_argument("--extra", action="store_true", help="also time the inference configs (Ne/Xe 50k, W 100k)")
+    ap.add_argument("--dt", type=float, default=1.0, help="MD time step in fs (--workload md)")
+    ap.add_argument("--workload", default="featurize", choices=["featurize", "md"],
+                    help="featurize = BASELINE.json headline (default); md = configs[4] MD loop, strong scaling")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "md":
+        run_md(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -110,6 +110,17 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
                          const int32_t *atomic_numbers, int32_t n_images,
                          const double *image_offsets, const int32_t *image_abc,
                          uf3b_nlist **inout, void *stream);
+/* Same for the centres [first_centre, first_centre + n_centres) only (the other rows stay
+ * empty): the atom-range partition of ONE large frame over ranks (MD strong scaling).  All
+ * atoms are still binned, so every rank sees every neighbour.  uf3b_energy_forces on such a
+ * list returns this rank's PARTIAL energy, forces [n_atoms*3] (own atoms' pair and centre
+ * terms plus the 3-body reactions on any atom) and virial; the sum over ranks is the total.
+ * uf3b_featurize refuses a partial list. */
+int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double *positions,
+                               const int32_t *atomic_numbers, int32_t n_images,
+                               const double *image_offsets, const int32_t *image_abc,
+                               int64_t first_centre, int64_t n_centres,
+                               uf3b_nlist **inout, void *stream);
 /* Number of entries in list `which` (2 or 3). */
 int uf3b_neighbors_count(const uf3b_nlist *nl, int which, int64_t *n_entries);
 /* Parity hook: CSR offsets [n_atoms+1] and supercell indices [n_entries] (host). */

@@ -71,3 +71,42 @@ def test_shard_is_a_partition():
     parts = [distributed.shard(items, r, 4) for r in range(4)]
     assert sorted(sum(parts, [])) == items
     assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def _range_worker(rank, world, port, out_dir):
+    """Atom-range partition of one frame (MD strong scaling): every rank contributes a partial
+    [forces, energy] buffer, one all-reduce completes it.  The per-rank partials are stood in
+    by the oracle's full result restricted to the rank's atom range (forces) and an equal
+    share of the energy — on the GPU they come from uf3b_neighbors_build_range +
+    uf3b_energy_forces (tests/test_gpu_api.py::test_centre_ranges_sum_to_the_full_frame)."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = gu.Case("calc_syn_w54_model23")
+    n = len(case.numbers)
+    first, count = distributed.atom_range(n, rank, world)
+    buf = torch.zeros(3 * n + 1, dtype=torch.float64)
+    buf[3 * first:3 * (first + count)] = torch.from_numpy(np.asarray(case["forces"]).reshape(-1)[3 * first:3 * (first + count)])
+    buf[3 * n] = float(case["energy"]) / world
+    distributed.all_reduce_partials(buf)
+    np.save(os.path.join(out_dir, f"partial_{rank}.npy"), buf.numpy())
+    dist.destroy_process_group()
+
+
+def test_atom_ranges_cover_and_reduce(tmp_path):
+    for n, world in ((10, 3), (100000, 8), (5, 8), (0, 2)):
+        ranges = [distributed.atom_range(n, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and sum(c for _, c in ranges) == n
+        assert all(ranges[r][0] + ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        assert max(c for _, c in ranges) - min(c for _, c in ranges) <= 1
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_range_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    case = gu.Case("calc_syn_w54_model23")
+    want = np.concatenate([np.asarray(case["forces"]).reshape(-1), [float(case["energy"])]])
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), f"partial_{rank}.npy"))
+        assert np.allclose(got, want, rtol=1e-14, atol=0)

@@ -160,6 +160,41 @@ def test_analytic_stress_matches_oracle_energy_differences():
     assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("name", ["calc_syn_w128_model23", "calc_syn_nexe64_pair", "calc_w8_pbc"])
+def test_centre_ranges_sum_to_the_full_frame(name):
+    """One frame split into atom ranges (uf3b_neighbors_build_range): the partial energies,
+    forces and virials of the ranges add up to the full-frame result, which matches the
+    reference fixture; feature rows refuse a partial list."""
+    from uf3_b200 import _native, distributed
+    from uf3_b200.atoms import frame_arrays
+    from uf3_b200.engine import Engine
+    case = gu.Case(name)
+    basis = case.basis()
+    positions, numbers, cell, pbc = frame_arrays(case.atoms())
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    eng = Engine(basis)
+    eng.set_coefficients(np.array(case["coefficients"]))
+    eng.build_neighbors(positions, numbers, images=images)
+    e_full, f_full, w_full = eng.energy_forces(virial=True)
+    total2 = eng.neighbor_count(2)
+    n = len(positions)
+    for world in (2, 3):
+        e_sum, f_sum, w_sum, pairs = 0.0, np.zeros((n, 3)), np.zeros((3, 3)), 0
+        for rank in range(world):
+            eng.build_neighbors(positions, numbers, images=images, centres=distributed.atom_range(n, rank, world))
+            e, f, w = eng.energy_forces(virial=True)
+            e_sum, f_sum, w_sum = e_sum + e, f_sum + f, w_sum + w
+            pairs += eng.neighbor_count(2)
+            with pytest.raises(_native.UF3BError):
+                eng.featurize()
+        assert pairs == total2
+        assert abs(e_sum - e_full) <= 1e-12 * abs(e_full)
+        assert gu.rel_err(f_sum, f_full) <= 1e-12 and gu.rel_err(w_sum, w_full) <= 1e-12
+    assert abs(e_full - float(case["energy"])) <= 1e-6 * abs(float(case["energy"]))
+    assert gu.rel_err(f_full, case["forces"]) <= 1e-6
+    eng.close()
+
+
 def test_numerical_stress_is_energy_derivative():
     case = gu.Case("calc_w8_pbc")
     model = ls.WeightedLinearModel(case.basis())

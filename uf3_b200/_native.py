@@ -53,6 +53,9 @@ SIGNATURES = {
     "uf3b_basis_destroy": (None, [C.c_void_p]),
     "uf3b_neighbors_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    "uf3b_neighbors_build_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                             C.POINTER(C.c_void_p), C.c_void_p]),
     "uf3b_neighbors_count": (C.c_int, [C.c_void_p, C.c_int, _i64p]),
     "uf3b_neighbors_export": (C.c_int, [C.c_void_p, C.c_int, _i64p, _i64p]),
     "uf3b_nlist_destroy": (None, [C.c_void_p]),

@@ -110,6 +110,8 @@ struct FrameView {
     int n;                    // real atoms
     unsigned n_magic;         // floor(2^32 / n) (2^32 - 1 for n = 1): image_of() without a division
     int n_img;
+    int c_first, c_count;     // centres whose rows were built (all atoms unless the frame is
+                              // split over ranks: uf3b_neighbors_build_range)
     const double *pos;        // [n*3]
     const int *spec;          // [n]
     const double *img_off;    // [n_img*3]
@@ -147,6 +149,7 @@ struct uf3b_nlist {
     int n_img = 0;
     int64_t total2 = 0, total3 = 0;
     int max3 = 0;                  // longest row of the 3-body list
+    int c_first = 0, c_count = 0;  // centre range of the last build
     uf3b::DevBuf<double> pos, img_off;
     uf3b::DevBuf<int> z, spec, img_inv;
     uf3b::DevBuf<int> off2, off3, cnt2, cnt3, idx2, idx3, scratch2, scratch3;

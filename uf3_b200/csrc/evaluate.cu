@@ -15,6 +15,7 @@
 // those atomics varies from run to run at the 1e-16 level.  Owner-computes
 // (UF3B_DETERMINISTIC_FORCES=1): each atom also visits the triangles of the centres in
 // its list and adds only its own share — no atomics, bit-reproducible, 3x the triangles.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -87,7 +88,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
         w[3] += ky * z; w[4] += kx * z; w[5] += kx * y;
     };
 
-    for (int a = gw; a < f.n; a += n_gw) {
+    for (int a = f.c_first + gw; a < f.c_first + f.c_count; a += n_gw) {
         const int sa = __ldg(f.spec + a);
         const Vec3 pa = real_position(f, a);
         double fx = 0.0, fy = 0.0, fz = 0.0;
@@ -250,8 +251,9 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
         }
         return UF3B_OK;
     }
-    const bool deterministic = getenv("UF3B_DETERMINISTIC_FORCES") != nullptr;
-    const bool newton = !deterministic && basis->tab.n_trios > 0;
+    const bool partial = nl->c_count < n;       // this rank owns a range of centres only
+    const bool deterministic = getenv("UF3B_DETERMINISTIC_FORCES") != nullptr && !partial;
+    const bool newton = (!deterministic && basis->tab.n_trios > 0) || partial;
     auto kernel = virial ? (newton ? k_energy_forces<true, true> : k_energy_forces<false, true>)
                          : (newton ? k_energy_forces<true, false> : k_energy_forces<false, false>);
     const int n_grid = basis->n_bins;
@@ -262,7 +264,7 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EV_WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count() * per_sm;
-    const int need = (n + EV_WARPS - 1) / EV_WARPS;
+    const int need = std::max(1, (nl->c_count + EV_WARPS - 1) / EV_WARPS);
     if (grid > need) grid = need;
     const int n_gw = grid * EV_WARPS;
     UF3B_CUDA(basis->partials.reserve((size_t)n_gw * 7 + 1));

@@ -1293,6 +1293,8 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     const int F = basis->n_feats;
     const int n = (int)nl->n;
     if (x_forces && ld < F) return fail(UF3B_ERR_INVALID, "ld smaller than n_feats");
+    if (nl->c_count < n)
+        return fail(UF3B_ERR_STATE, "feature rows need the lists of every centre (built for a centre range)");
     if (!x_energy && !x_forces) return UF3B_OK;
     const bool e_dev = x_energy && is_device_pointer(x_energy);
     const bool f_dev = x_forces && is_device_pointer(x_forces);

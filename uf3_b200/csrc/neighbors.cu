@@ -322,7 +322,7 @@ constexpr int NL_BUF2 = 160, NL_BUF3 = 96;     // hits buffered per centre befor
 //   status: [0] entries claimed in list 2, [1] in list 3, [2] overflow, [3] longest list-3 row
 __global__ void __launch_bounds__(NL_WARPS * 32)
 k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots,
-            const int *__restrict__ cell_start, int n_real, int *__restrict__ off2,
+            const int *__restrict__ cell_start, int c_first, int c_count, int *__restrict__ off2,
             int *__restrict__ cnt2, int *__restrict__ off3, int *__restrict__ cnt3,
             int *__restrict__ idx2, int *__restrict__ idx3, int *__restrict__ scratch2,
             int *__restrict__ scratch3, int cap2, int cap3, int *__restrict__ status) {
@@ -336,7 +336,7 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // any real atom in this cell?  (ghost-only cells of the padding do no work)
     int real_here = 0;
-    for (int s = s0 + (int)threadIdx.x; s < s1; s += NL_WARPS * 32) real_here |= slots[s].m < n_real;
+    for (int s = s0 + (int)threadIdx.x; s < s1; s += NL_WARPS * 32) real_here |= (unsigned)(slots[s].m - c_first) < (unsigned)c_count;
     if (!__syncthreads_or(real_here)) return;
 
     const int cz = cell % G.nz, cy = (cell / G.nz) % G.ny, cx = cell / (G.nz * G.ny);
@@ -379,7 +379,8 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
     const bool has3 = B.n_trios > 0;
     for (int s = s0 + warp; s < s1; s += NL_WARPS) {
         const Slot c = slots[s];
-        if (c.m >= n_real) continue;        // ghosts are never centres
+        if ((unsigned)(c.m - c_first) >= (unsigned)c_count) continue;   // ghosts (and real atoms of
+                                                                       // other ranks) are never centres
         const Vec3 pc = {c.x, c.y, c.z};
         // pass = 0: count and buffer; pass = 1 (only for rows longer than the buffers): write
         // the hits straight to the global scratch rows
@@ -476,6 +477,8 @@ FrameView uf3b_nlist::view() const {
     f.n = (int)n;
     f.n_magic = n > 1 ? (unsigned)((1ull << 32) / (unsigned long long)n) : 0xffffffffu;
     f.n_img = n_img;
+    f.c_first = c_first;
+    f.c_count = c_count;
     f.pos = pos.p;
     f.spec = spec.p;
     f.img_off = img_off.p;
@@ -491,7 +494,18 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
                          const int32_t *atomic_numbers, int32_t n_images,
                          const double *image_offsets, const int32_t *image_abc,
                          uf3b_nlist **inout, void *stream_) {
+    return uf3b_neighbors_build_range(basis, n_atoms, positions, atomic_numbers, n_images, image_offsets,
+                                      image_abc, 0, n_atoms, inout, stream_);
+}
+
+int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double *positions,
+                               const int32_t *atomic_numbers, int32_t n_images,
+                               const double *image_offsets, const int32_t *image_abc,
+                               int64_t first_centre, int64_t n_centres,
+                               uf3b_nlist **inout, void *stream_) {
     if (!basis || !inout) return fail(UF3B_ERR_INVALID, "null argument");
+    if (first_centre < 0 || n_centres < 0 || first_centre + n_centres > n_atoms)
+        return fail(UF3B_ERR_INVALID, "centre range outside [0, n_atoms)");
     if (n_atoms < 0 || n_images < 1) return fail(UF3B_ERR_INVALID, "bad n_atoms / n_images");
     if (n_atoms > 0 && (!positions || !atomic_numbers)) return fail(UF3B_ERR_INVALID, "null positions");
     if (!image_offsets || !image_abc) return fail(UF3B_ERR_INVALID, "null image table");
@@ -510,6 +524,8 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
     nl->n_img = n_images;
     nl->total2 = nl->total3 = 0;
     nl->max3 = 0;
+    nl->c_first = (int)first_centre;
+    nl->c_count = (int)n_centres;
 
     // periodic image table: pair every image with the one of negated coordinates
     std::vector<int> inv(n_images, 0);
@@ -602,10 +618,16 @@ int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *posit
         UF3B_CUDA(nl->scratch2.reserve(nl->idx2.cap));
         UF3B_CUDA(nl->scratch3.reserve(nl->idx3.cap));
         UF3B_CUDA(cudaMemsetAsync(status, 0, sizeof h_status, stream));
+        if (nl->c_count < n) {      // rows of the atoms other ranks own stay empty
+            UF3B_CUDA(cudaMemsetAsync(nl->cnt2.p, 0, sizeof(int) * n, stream));
+            UF3B_CUDA(cudaMemsetAsync(nl->cnt3.p, 0, sizeof(int) * n, stream));
+            UF3B_CUDA(cudaMemsetAsync(nl->off2.p, 0, sizeof(int) * n, stream));
+            UF3B_CUDA(cudaMemsetAsync(nl->off3.p, 0, sizeof(int) * n, stream));
+        }
         const int cap2 = (int)std::min<size_t>(nl->idx2.cap, (size_t)INT32_MAX);
         const int cap3 = (int)std::min<size_t>(nl->idx3.cap, (size_t)INT32_MAX);
         UF3B_LAUNCH(k_neighbors, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G, nl->slots.p,
-                    nl->cell_start.p, n, nl->off2.p, nl->cnt2.p, nl->off3.p, nl->cnt3.p, nl->idx2.p,
+                    nl->cell_start.p, nl->c_first, nl->c_count, nl->off2.p, nl->cnt2.p, nl->off3.p, nl->cnt3.p, nl->idx2.p,
                     nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status);
         UF3B_CUDA(cudaMemcpyAsync(h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, stream));
         UF3B_CUDA(cudaStreamSynchronize(stream));

@@ -6,6 +6,14 @@ independent, so here frame f goes to rank f mod world_size, every rank accumulat
 own Gram statistics (`least_squares.GramStats`, 2 F^2 + 2 F + 6 doubles) and a single
 `all_reduce(SUM)` over NCCL (GPU ranks) or gloo (CPU tests) replaces `gather_and_merge`.
 There is no collective on the featurization path itself.
+
+Inference on ONE large frame (the MD loop of BASELINE.json configs[4]) strong-scales by an
+atom-range partition instead: positions are replicated, rank r builds the neighbour rows
+of its own contiguous atom range (`uf3b_neighbors_build_range`) and evaluates those centres;
+the 3-body reactions it adds to atoms of other ranks make its force array a PARTIAL sum, so
+one `all_reduce(SUM)` of 3N + 1 doubles (forces + energy; 2.4 MB at 100 000 atoms) per step
+completes it (`ShardedEvaluator`).  The reference has no counterpart (its calculator is
+single-process, forcefield/calculator.py:124-153).
 """
 import numpy as np
 
@@ -61,3 +69,53 @@ def accumulate_frames(featurizer, frames, stats=None, rank=0, world_size=1):
             stats.add_force_rows_device(rows.data_ptr(), np.asarray(forces, dtype=np.float64).reshape(-1),
                                         3 * n, F, stream)
     return stats
+
+
+def atom_range(n_atoms, rank, world_size):
+    """Contiguous, balanced atom range (first, count) of `rank`."""
+    base, rem = divmod(int(n_atoms), int(world_size))
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def all_reduce_partials(buffer, group=None):
+    """Sum a rank's partial [forces (3N), energy] buffer over the group in place."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buffer, op=dist.ReduceOp.SUM, group=group)
+    return buffer
+
+
+class ShardedEvaluator:
+    """Energy and forces of one frame with its atoms split over the ranks of `group`.
+
+    Everything stays on the device: `positions` / `numbers` are CUDA tensors holding the
+    WHOLE frame on every rank, the result is a CUDA tensor [3N + 1] (forces row-major, then
+    the energy), identical on all ranks after the all-reduce."""
+
+    def __init__(self, basis, coefficients, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        from uf3_b200.engine import Engine
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.engine = Engine(basis, device=self.device)
+        self.engine.set_coefficients(coefficients)
+        self.out = None
+
+    def energy_forces(self, positions, numbers, images):
+        import torch
+        n = positions.shape[0]
+        if self.out is None or self.out.numel() != 3 * n + 1:
+            self.out = torch.empty(3 * n + 1, dtype=torch.float64, device=positions.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        self.engine.build_neighbors_device(positions.data_ptr(), numbers.data_ptr(), n, images, stream,
+                                           centres=atom_range(n, self.rank, self.world))
+        self.engine.energy_forces_device(self.out[3 * n:].data_ptr(), self.out.data_ptr(), stream)
+        all_reduce_partials(self.out, self.group)
+        return self.out[3 * n], self.out[:3 * n].view(n, 3)
+
+    def close(self):
+        self.engine.close()

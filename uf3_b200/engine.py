@@ -54,9 +54,12 @@ class Engine:
             self._basis, c.ctypes.data_as(C.POINTER(C.c_double)), len(c)))
         self.has_coefficients = True
 
-    def build_neighbors(self, positions, numbers, cell=None, pbc=None, images=None, stream=None):
+    def build_neighbors(self, positions, numbers, cell=None, pbc=None, images=None, stream=None,
+                        centres=None):
         """Kernel A.  `images` = (abc (n_img,3) int, offsets (n_img,3) float64) overrides the
-        periodic-image table derived from (cell, pbc, r_cut) by `geometry.image_table`."""
+        periodic-image table derived from (cell, pbc, r_cut) by `geometry.image_table`.
+        `centres` = (first, count) builds the rows of that atom range only (one frame split
+        over ranks); `energy_forces` then returns this rank's partial sums."""
         positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
         numbers = np.ascontiguousarray(numbers, dtype=np.int32)
         if len(numbers) != len(positions):
@@ -68,19 +71,21 @@ class Engine:
                 images = geometry.image_table(cell, pbc, self.tables.r_cut)
         abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
         offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
-        _native.check(self._lib.uf3b_neighbors_build(
+        first, count = (0, len(positions)) if centres is None else centres
+        _native.check(self._lib.uf3b_neighbors_build_range(
             self._basis, len(positions), _ptr(positions), _ptr(numbers), len(offsets),
-            _ptr(offsets), _ptr(abc), C.byref(self._nlist), stream))
+            _ptr(offsets), _ptr(abc), int(first), int(count), C.byref(self._nlist), stream))
         self.n_atoms = len(positions)
         return self
 
-    def build_neighbors_device(self, positions_ptr, numbers_ptr, n_atoms, images, stream=None):
+    def build_neighbors_device(self, positions_ptr, numbers_ptr, n_atoms, images, stream=None, centres=None):
         """Same with DEVICE pointers for positions (n,3 float64) and numbers (n int32)."""
         abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
         offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
-        _native.check(self._lib.uf3b_neighbors_build(
+        first, count = (0, int(n_atoms)) if centres is None else centres
+        _native.check(self._lib.uf3b_neighbors_build_range(
             self._basis, int(n_atoms), C.c_void_p(positions_ptr), C.c_void_p(numbers_ptr),
-            len(offsets), _ptr(offsets), _ptr(abc), C.byref(self._nlist), stream))
+            len(offsets), _ptr(offsets), _ptr(abc), int(first), int(count), C.byref(self._nlist), stream))
         self.n_atoms = int(n_atoms)
         return self
 
@@ -147,6 +152,7 @@ class Engine:
         return (float(e[0]) if energy else None), f
 
     def energy_forces_device(self, energy_ptr, forces_ptr, stream=None):
+        """Device-pointer form (energy: 1 double, forces: [N,3]); asynchronous on `stream`."""
         _native.check(self._lib.uf3b_energy_forces(
             self._basis, self._nlist, C.c_void_p(energy_ptr) if energy_ptr else None,
             C.c_void_p(forces_ptr) if forces_ptr else None, None, stream))
