@@ -505,6 +505,111 @@ def run_md(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- fit at scale
+def run_fit(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: stream 10 000-atom W frames through neighbour lists -> feature
+    rows (left in HBM) -> normal-equation accumulation (csrc/gram.cu) on every rank, then ONE
+    all-reduce of 2F^2 + 2F + 6 doubles and the regularised solve on cuSOLVER.  A step is one
+    frame per rank; targets are synthetic (rows @ c_true + noise, prepared before timing)."""
+    import torch
+    import torch.distributed as dist
+    from uf3_b200 import distributed, geometry, least_squares as ls
+    from uf3_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    basis = make_basis(args.basis)
+    eng = Engine(basis, device=local_rank)
+    F = eng.n_feats
+    frames = [frame(rank * N_POOL + i) for i in range(N_POOL)]
+    n_atoms = len(frames[0][0])
+    images = geometry.image_table(frames[0][2], frames[0][3], basis.r_cut)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_pos = [torch.from_numpy(fr[0]).to(dev) for fr in frames]
+    d_num = torch.from_numpy(frames[0][1]).to(dev)
+    rows = torch.empty((3 * n_atoms, F), dtype=torch.float64, device=dev)
+    c_true = torch.from_numpy(np.random.default_rng(11).normal(size=F) * 0.1).to(dev)
+    n_total = args.steps + args.warmup
+    xe_all = torch.zeros((n_total, F), dtype=torch.float64, device=dev)
+    y_pool, y_mom = [], []
+    for i in range(N_POOL):                       # synthetic targets, outside the timed region
+        eng.build_neighbors_device(d_pos[i].data_ptr(), d_num.data_ptr(), n_atoms, images, stream)
+        eng.featurize_device(xe_all[0].data_ptr(), rows.data_ptr(), F, stream)
+        gen = torch.Generator(device=dev).manual_seed(100 * rank + i)
+        y = rows @ c_true + 1e-3 * torch.randn(3 * n_atoms, dtype=torch.float64, device=dev, generator=gen)
+        y_pool.append(y)
+        y_mom.append((float(y.sum()), float((y * y).sum())))
+    acc = ls.GramAccumulator(F)
+
+    def step(k):
+        i = k % N_POOL
+        eng.build_neighbors_device(d_pos[i].data_ptr(), d_num.data_ptr(), n_atoms, images, stream)
+        eng.featurize_device(xe_all[k].data_ptr(), rows.data_ptr(), F, stream)
+        acc.add_force_rows_device(rows.data_ptr(), y_pool[i].data_ptr(), 3 * n_atoms, F, stream,
+                                  y_moments=y_mom[i])
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = eng.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(args.warmup, n_total):
+        step(k)
+    stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = start.elapsed_time(stop)
+    launches = eng.launch_count() - launches0
+    # energy rows: one small copy, folded on the host (targets = x_e @ c_true)
+    xe_host = xe_all.cpu().numpy()
+    c_host = c_true.cpu().numpy()
+    for k in range(n_total):
+        acc.add_energy_row(xe_host[k], float(xe_host[k] @ c_host), n_atoms)
+    t0 = time.perf_counter()
+    distributed.all_reduce_stats(acc)
+    model = ls.WeightedLinearModel(basis, solver="cusolver", ridge_1b=1e-10, ridge_2b=1e-10, ridge_3b=1e-10)
+    model.fit_from_accumulator(acc, weight=0.5)
+    torch.cuda.synchronize()
+    tail_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms, tail_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, tail_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        # sanity of the device solve: residual of the regularised normal equations it solved,
+        # rebuilt on the host from the all-reduced statistics
+        stats = acc.export()
+        w_e, w_f = ls.calc_E_F_weights(stats["n_e"], stats["n_f"], stats["std_e"], stats["std_f"])
+        gram, ordinate = model.combine_weighted_gram(stats["gram_e"], stats["gram_f"], stats["ord_e"],
+                                                     stats["ord_f"], w_e, w_f, 0.5)
+        mask = model.mask
+        reg = ls.freeze_regularizer(model.regularizer, mask)
+        lhs = gram[np.ix_(mask, mask)] + reg.T @ reg
+        res = lhs @ model.coefficients[mask] - ordinate[mask]
+        err = float(np.linalg.norm(res) / np.linalg.norm(ordinate[mask]))
+        print(json.dumps({
+            "metric": "atom-steps/s, fit pipeline (neighbour lists + feature rows + normal equations) on 10k-atom W",
+            "value": world * n_atoms * args.steps / (ms * 1e-3), "unit": "atom-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD + " + Gram accumulation", "basis": args.basis, "n_feats": F,
+                       "frames_total": world * n_total},
+            "gpu_launches": launches,
+            "all_reduce_and_solve_ms": tail_ms, "all_reduce_doubles": 2 * F * F + 2 * F + 6,
+            "normal_equation_residual_rel": err}), flush=True)
+    acc.close()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -515,8 +620,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
     ap.add_argument("--extra", action="store_true", help="also time the inference configs (Ne/Xe 50k, W 100k)")
     ap.add_argument("--dt", type=float, default=1.0, help="MD time step in fs (--workload md)")
-    ap.add_argument("--workload", default="featurize", choices=["featurize", "md"],
-                    help="featurize = BASELINE.json headline (default); md = configs[4] MD loop, strong scaling")
+    ap.add_argument("--workload", default="featurize", choices=["featurize", "md", "fit"],
+                    help="featurize = BASELINE.json headline (default); md = configs[4] MD loop, strong scaling; "
+                         "fit = configs[3] featurize + normal equations + all-reduce + solve")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -525,6 +631,8 @@ def main():
         run_reference(args, rank, world)
     elif args.workload == "md":
         run_md(args, rank, world, local_rank)
+    elif args.workload == "fit":
+        run_fit(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -155,6 +155,10 @@ int uf3b_gram_accumulate(uf3b_gram *gram, const double *x, const double *y, int6
                          int64_t ld, int is_force, void *stream);
 int uf3b_gram_export(const uf3b_gram *gram, int is_force, double *gram_out, double *ord_out);
 void uf3b_gram_destroy(uf3b_gram *gram);
+/* Dense solve A x = b on the device (cuSOLVER getrf + getrs), the regularised normal
+ * equations of regression/least_squares.py:248-272,763-771.  a [n*n] row-major, b and x
+ * [n_rhs][n]; host or device pointers; synchronises the stream. */
+int uf3b_solve(const double *a, const double *b, int32_t n, int32_t n_rhs, double *x, void *stream);
 
 /* -- host-side probe ----------------------------------------------------------------- */
 /* Runs the table builder of uf3b_basis_create on one knot vector and evaluates the four

@@ -262,6 +262,34 @@ def test_device_gram_equals_host_gram_and_fit():
     dev.close()
 
 
+def test_cusolver_solve_matches_host_lapack():
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 73, 456):
+        m = rng.normal(size=(n + 5, n))
+        a = m.T @ m + 1e-3 * np.eye(n)
+        b = rng.normal(size=n)
+        want = np.linalg.solve(a, b)
+        got = ls.device_solve(a, b)
+        assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    b2 = rng.normal(size=(n, 3))
+    assert np.allclose(ls.device_solve(a, b2), np.linalg.solve(a, b2), rtol=1e-8, atol=1e-10)
+    a_unsym = rng.normal(size=(9, 9)) + 4 * np.eye(9)      # row-major handling: A x = b, not A^T x = b
+    b = rng.normal(size=9)
+    assert np.allclose(ls.device_solve(a_unsym, b), np.linalg.solve(a_unsym, b), rtol=1e-10)
+    # a model fitted with solver="cusolver" equals the host fit
+    case = gu.Case("syn_w54_demo")
+    basis = case.basis()
+    y_e = float(case["x_energy"] @ np.linspace(-1, 1, basis.n_feats))
+    y_f = case["x_forces"] @ np.linspace(-1, 1, basis.n_feats)
+    fits = []
+    for solver in ("host", "cusolver"):
+        model = ls.WeightedLinearModel(basis, solver=solver, ridge_1b=1e-6, ridge_2b=1e-6, ridge_3b=1e-6)
+        n = len(case.numbers)
+        model.fit(case["x_energy"][None, :] / n, np.array([y_e / n]), case["x_forces"], y_f)
+        fits.append(model.coefficients)
+    assert np.abs(fits[0] - fits[1]).max() <= 1e-7 * np.abs(fits[0]).max()
+
+
 def test_frame_pipeline_matches_single_frame_calls():
     from uf3_b200 import pipeline
     names = ["syn_w16_demo", "syn_w54_demo", "syn_w36_slab", "syn_w128_demo", "syn_w16_demo"]

@@ -4,6 +4,8 @@
 // that are already on the device, so a frame's 3N x F force rows never have to be
 // copied to the host before the fit.  Two accumulators (energy rows / force rows) are
 // kept, as WeightedLinearModel.fit_from_file does (:393-412).
+#include <algorithm>
+
 #include "common.cuh"
 
 struct uf3b_gram {
@@ -17,37 +19,52 @@ namespace uf3b {
 
 constexpr int GT = 64;        // output tile edge
 constexpr int GK = 16;        // rows per shared-memory stage
-constexpr int GROWS = 512;    // rows per block (split over the row dimension)
 
-// Tile (bi <= bj) of X^T X over rows [z*GROWS, (z+1)*GROWS); 256 threads, 4x4 per thread.
+// Tile (bi <= bj) of X^T X over rows [z*rows_per_block, (z+1)*rows_per_block); 256 threads,
+// 4x4 per thread.  The host picks rows_per_block so that tiles x row-splits fill the SMs.
+// Stages of GK rows are double-buffered through registers (the next stage's global loads
+// are in flight while the current one is multiplied) and read back from shared memory with
+// 16-byte loads: 4 loads per 16 FMAs, so the FP64 pipe, not the LSU, is the limit.
 __global__ void __launch_bounds__(256)
-k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols,
+k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols, int rows_per_block,
        double *__restrict__ g) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bi > bj) return;
-    __shared__ double sa[GK][GT + 1], sb[GK][GT + 1];
+    __shared__ __align__(16) double sa[GK][GT], sb[GK][GT];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const long long r_begin = (long long)blockIdx.z * GROWS;
-    const long long r_end = r_begin + GROWS < rows ? r_begin + GROWS : rows;
-    double acc[4][4] = {};
-    for (long long r0 = r_begin; r0 < r_end; r0 += GK) {
-        for (int k = threadIdx.x; k < GK * GT; k += 256) {
-            const int rr = k / GT, cc = k % GT;
-            const long long r = r0 + rr;
-            const int ca = bi * GT + cc, cb = bj * GT + cc;
-            sa[rr][cc] = (r < r_end && ca < n_cols) ? x[r * ld + ca] : 0.0;
-            sb[rr][cc] = (r < r_end && cb < n_cols) ? x[r * ld + cb] : 0.0;
+    const long long r_begin = (long long)blockIdx.z * rows_per_block;
+    const long long r_end = r_begin + rows_per_block < rows ? r_begin + rows_per_block : rows;
+    // element k = threadIdx.x + 256 i of a stage: row k / 64, column k % 64
+    const int l_row = threadIdx.x >> 6, l_col = threadIdx.x & 63;
+    const int ca = bi * GT + l_col, cb = bj * GT + l_col;
+    const bool a_ok = ca < n_cols, b_ok = cb < n_cols;
+    double ra[4], rb[4];
+    auto fetch = [&](long long r0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = r0 + l_row + 4 * i;
+            ra[i] = (r < r_end && a_ok) ? __ldg(x + r * ld + ca) : 0.0;
+            rb[i] = (r < r_end && b_ok) ? __ldg(x + r * ld + cb) : 0.0;
         }
+    };
+    double acc[4][4] = {};
+    fetch(r_begin);
+    for (long long r0 = r_begin; r0 < r_end; r0 += GK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sa[l_row + 4 * i][l_col] = ra[i]; sb[l_row + 4 * i][l_col] = rb[i]; }
         __syncthreads();
+        if (r0 + GK < r_end) fetch(r0 + GK);
 #pragma unroll
         for (int rr = 0; rr < GK; ++rr) {
-            double a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = sa[rr][ty * 4 + i]; b[i] = sb[rr][tx * 4 + i]; }
+            const double2 a01 = *reinterpret_cast<const double2 *>(&sa[rr][ty * 4]);
+            const double2 a23 = *reinterpret_cast<const double2 *>(&sa[rr][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2 *>(&sb[rr][tx * 4]);
+            const double2 b23 = *reinterpret_cast<const double2 *>(&sb[rr][tx * 4 + 2]);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -61,15 +78,28 @@ k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols,
         }
 }
 
+constexpr int OROWS = 256;    // rows per block of k_ordinate
+
+// b += X^T y: block = 32 columns x OROWS rows; warp w takes rows w, w + 8, ... (coalesced
+// 256-byte reads), the eight per-warp sums are combined in shared memory.
 __global__ void __launch_bounds__(256)
 k_ordinate(const double *__restrict__ x, long long ld, const double *__restrict__ y, long long rows,
            int n_cols, double *__restrict__ b) {
-    const long long r_begin = (long long)blockIdx.x * GROWS;
-    const long long r_end = r_begin + GROWS < rows ? r_begin + GROWS : rows;
-    for (int col = threadIdx.x; col < n_cols; col += blockDim.x) {
-        double s = 0.0;
-        for (long long r = r_begin; r < r_end; ++r) s += x[r * ld + col] * y[r];
-        if (s != 0.0) atomicAdd(b + col, s);
+    __shared__ double red[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const long long r_begin = (long long)blockIdx.y * OROWS;
+    const long long r_end = r_begin + OROWS < rows ? r_begin + OROWS : rows;
+    double s = 0.0;
+    if (col < n_cols)
+        for (long long r = r_begin + warp; r < r_end; r += 8) s = fma(__ldg(x + r * ld + col), __ldg(y + r), s);
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && col < n_cols) {
+        double t = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += red[w][lane];
+        if (t != 0.0) atomicAdd(b + col, t);
     }
 }
 
@@ -119,10 +149,18 @@ int uf3b_gram_accumulate(uf3b_gram *gm, const double *x, const double *y, int64_
         dy = gm->stage_y.p;
     }
     const int nb = (gm->n_cols + GT - 1) / GT;
-    const unsigned nz = (unsigned)((rows + GROWS - 1) / GROWS);
-    if (nz > 65535) return fail(UF3B_ERR_CAPACITY, "too many rows in one call (max %d)", 65535 * GROWS);
-    UF3B_LAUNCH(k_gram, dim3(nb, nb, nz), 256, 0, stream, dx, dld, (long long)rows, gm->n_cols, gm->g[which]);
-    UF3B_LAUNCH(k_ordinate, nz, 256, 0, stream, dx, dld, dy, (long long)rows, gm->n_cols, gm->b[which]);
+    // row split: about four blocks per SM over the nb (nb + 1) / 2 upper tiles, at least 4 stages each
+    const long long want_z = std::max<long long>(1, (4LL * sm_count()) / (nb * (nb + 1) / 2));
+    long long rpb = std::max<long long>(4 * GK, (rows + want_z - 1) / want_z);
+    rpb = (rpb + GK - 1) / GK * GK;
+    while ((rows + rpb - 1) / rpb > 65535) rpb *= 2;
+    const unsigned nz = (unsigned)((rows + rpb - 1) / rpb);
+    UF3B_LAUNCH(k_gram, dim3(nb, nb, nz), 256, 0, stream, dx, dld, (long long)rows, gm->n_cols, (int)rpb,
+                gm->g[which]);
+    const unsigned ny = (unsigned)((rows + OROWS - 1) / OROWS);
+    if (ny > 65535) return fail(UF3B_ERR_CAPACITY, "too many rows in one call (max %d)", 65535 * OROWS);
+    UF3B_LAUNCH(k_ordinate, dim3((gm->n_cols + 31) / 32, ny), 256, 0, stream, dx, dld, dy, (long long)rows,
+                gm->n_cols, gm->b[which]);
     if (dx != x || dy != y) UF3B_CUDA(cudaStreamSynchronize(stream));
     return UF3B_OK;
 }

@@ -1,0 +1,65 @@
+// solve.cu — the regularised normal-equation solve on the device (cuSOLVER).
+//
+// Replaces regression/least_squares.py:763-771 (lu_factorization: scipy lu_factor /
+// lu_solve on (G + R^T R) c = b).  The matrix is p x p with p <= ~1000, so this is one
+// getrf + getrs; it exists so that a fit whose Gram blocks were accumulated and
+// all-reduced on the device never has to round-trip through host LAPACK.
+#include <cusolverDn.h>
+
+#include "common.cuh"
+
+using namespace uf3b;
+
+#define UF3B_SOLVER(expr)                                                                 \
+    do {                                                                                  \
+        cusolverStatus_t s_ = (expr);                                                     \
+        if (s_ != CUSOLVER_STATUS_SUCCESS) {                                              \
+            rc = fail(UF3B_ERR_CUDA, "%s: cusolver status %d", #expr, (int)s_);           \
+            goto done;                                                                    \
+        }                                                                                 \
+    } while (0)
+#define UF3B_CUDA_GOTO(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            rc = fail(UF3B_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));            \
+            goto done;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+extern "C" int uf3b_solve(const double *a, const double *b, int32_t n, int32_t n_rhs, double *x,
+                          void *stream_) {
+    if (!a || !b || !x || n < 1 || n_rhs < 1) return fail(UF3B_ERR_INVALID, "bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = UF3B_OK;
+    cusolverDnHandle_t handle = nullptr;
+    double *d_a = nullptr, *d_b = nullptr, *d_work = nullptr;
+    int *d_piv = nullptr, *d_info = nullptr;
+    int lwork = 0, h_info = 0;
+    const size_t a_bytes = sizeof(double) * (size_t)n * n, b_bytes = sizeof(double) * (size_t)n * n_rhs;
+    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_a, a_bytes));
+    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_b, b_bytes));
+    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_piv, sizeof(int) * n));
+    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_info, sizeof(int)));
+    // `a` is row-major: LAPACK sees its transpose, so the solve below uses op = T
+    UF3B_CUDA_GOTO(cudaMemcpyAsync(d_a, a, a_bytes, cudaMemcpyDefault, stream));
+    UF3B_CUDA_GOTO(cudaMemcpyAsync(d_b, b, b_bytes, cudaMemcpyDefault, stream));   // [n_rhs][n]: column-major n x n_rhs
+    UF3B_SOLVER(cusolverDnCreate(&handle));
+    UF3B_SOLVER(cusolverDnSetStream(handle, stream));
+    UF3B_SOLVER(cusolverDnDgetrf_bufferSize(handle, n, n, d_a, n, &lwork));
+    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_work, sizeof(double) * (size_t)std::max(lwork, 1)));
+    UF3B_SOLVER(cusolverDnDgetrf(handle, n, n, d_a, n, d_work, d_piv, d_info));
+    UF3B_SOLVER(cusolverDnDgetrs(handle, CUBLAS_OP_T, n, n_rhs, d_a, n, d_piv, d_b, n, d_info));
+    UF3B_CUDA_GOTO(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    UF3B_CUDA_GOTO(cudaMemcpyAsync(x, d_b, b_bytes, cudaMemcpyDefault, stream));
+    UF3B_CUDA_GOTO(cudaStreamSynchronize(stream));
+    if (h_info != 0) rc = fail(UF3B_ERR_STATE, "singular normal equations (getrf info %d)", h_info);
+done:
+    if (handle) cusolverDnDestroy(handle);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaFree(d_work);
+    cudaFree(d_piv);
+    cudaFree(d_info);
+    return rc;
+}

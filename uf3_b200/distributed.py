@@ -15,6 +15,8 @@ one `all_reduce(SUM)` of 3N + 1 doubles (forces + energy; 2.4 MB at 100 000 atom
 completes it (`ShardedEvaluator`).  The reference has no counterpart (its calculator is
 single-process, forcefield/calculator.py:124-153).
 """
+import os
+
 import numpy as np
 
 
@@ -100,6 +102,9 @@ class ShardedEvaluator:
         on = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if on else 0
         self.world = dist.get_world_size(group) if on else 1
+        # profiling aid: UF3B_FAKE_WORLD=k makes a single process do the work of rank 0 of k
+        # (its share of the centres, no collective) so that one GPU shows the per-rank step
+        self.fake_world = int(os.environ.get("UF3B_FAKE_WORLD", "0")) if self.world == 1 else 0
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.engine = Engine(basis, device=self.device)
         self.engine.set_coefficients(coefficients)
@@ -112,7 +117,7 @@ class ShardedEvaluator:
             self.out = torch.empty(3 * n + 1, dtype=torch.float64, device=positions.device)
         stream = torch.cuda.current_stream().cuda_stream
         self.engine.build_neighbors_device(positions.data_ptr(), numbers.data_ptr(), n, images, stream,
-                                           centres=atom_range(n, self.rank, self.world))
+                                           centres=atom_range(n, self.rank, self.fake_world or self.world))
         self.engine.energy_forces_device(self.out[3 * n:].data_ptr(), self.out.data_ptr(), stream)
         all_reduce_partials(self.out, self.group)
         return self.out[3 * n], self.out[:3 * n].view(n, 3)

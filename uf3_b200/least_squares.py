@@ -62,7 +62,24 @@ def batched_moore_penrose(x, y, batch_size=2500):
 
 
 def lu_factorization(a, b):
+    """Host LAPACK LU solve, as the reference (least_squares.py:763-771)."""
     return np.linalg.solve(a, b)
+
+
+def device_solve(a, b, stream=None):
+    """The same solve on the GPU: cuSOLVER getrf + getrs behind the C ABI (`uf3b_solve`)."""
+    import ctypes as C
+    from uf3_b200 import _native
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    if a.ndim != 2 or a.shape[0] != a.shape[1] or b.shape[0] != a.shape[0]:
+        raise ValueError("device_solve expects a square matrix and a matching right-hand side")
+    rhs = np.ascontiguousarray(b.T if b.ndim == 2 else b)          # [n_rhs][n]
+    x = np.empty_like(rhs)
+    _native.check(_native.lib().uf3b_solve(C.c_void_p(a.ctypes.data), C.c_void_p(rhs.ctypes.data),
+                                           a.shape[0], 1 if b.ndim == 1 else b.shape[1],
+                                           C.c_void_p(x.ctypes.data), stream))
+    return x.T.copy() if b.ndim == 2 else x
 
 
 def calc_E_F_weights(n_e, n_f, std_e, std_f):
@@ -96,8 +113,9 @@ def mae_metric(predicted, actual):
 
 # ---------------------------------------------------------------- model
 class WeightedLinearModel:
-    def __init__(self, bspline_config, regularizer=None, data_coverage=None, **params):
+    def __init__(self, bspline_config, regularizer=None, data_coverage=None, solver="host", **params):
         self.coefficients = None
+        self.solver = solver        # "host" = numpy LAPACK as the reference; "cusolver" = on the GPU
         self.regularizer = regularizer
         self.bspline_config = bspline_config
         n_basis = int(np.sum(bspline_config.get_feature_partition_sizes()))
@@ -220,7 +238,8 @@ class WeightedLinearModel:
                                               self.frozen_c, self.col_idx)
         self.data_coverage = np.logical_or(self.data_coverage, coverage)
         reg = freeze_regularizer(self.regularizer, self.mask)
-        solution = lu_factorization(gram + np.dot(reg.T, reg), ordinate)
+        solve = device_solve if getattr(self, "solver", "host") == "cusolver" else lu_factorization
+        solution = solve(gram + np.dot(reg.T, reg), ordinate)
         self.coefficients = revert_frozen_coefficients(solution, self.n_feats, self.mask,
                                                        self.frozen_c, self.col_idx)
 
@@ -361,9 +380,16 @@ class GramAccumulator(GramStats):
         except Exception:
             pass
 
-    def add_force_rows_device(self, x_ptr, y_forces, rows, ld, stream=None):
+    def add_force_rows_device(self, x_ptr, y_forces, rows, ld, stream=None, y_moments=None):
         """x_ptr: device address of `rows` x n_feats float64 rows (row stride ld doubles);
-        y_forces: host targets in the same row order (fx_0.., fy_0.., fz_0..)."""
+        y_forces: host targets in the same row order (fx_0.., fy_0.., fz_0..) — or, with
+        `y_moments` = (sum, sum of squares) supplied by the caller, the DEVICE address of the
+        targets, so that nothing crosses PCIe per frame."""
+        if y_moments is not None:
+            self._native.check(self._lib.uf3b_gram_accumulate(
+                self._handle, C.c_void_p(x_ptr), C.c_void_p(int(y_forces)), int(rows), int(ld), 1, stream))
+            self.moments[3:6] += (rows, float(y_moments[0]), float(y_moments[1]))
+            return
         y = np.ascontiguousarray(y_forces, dtype=np.float64).reshape(-1)
         if len(y) != rows:
             raise ValueError("one target per force row is required")
