@@ -262,6 +262,34 @@ def test_device_gram_equals_host_gram_and_fit():
     dev.close()
 
 
+def test_plumbing_featurize_and_fit_matches_reference():
+    """BASELINE.json configs[0]: eight 128-atom W frames -> BasisFeaturizer.evaluate (CUDA rows)
+    -> dataframe_to_tuples -> WeightedLinearModel.fit, against the coefficient vector the
+    running reference obtained from the same frames and labels (oracle/make_golden_fit.py)."""
+    import os
+    import pandas as pd
+    from uf3_b200 import bspline, composition
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "fit_w2body_plumbing.npz"))
+    chem = composition.ChemicalSystem(["W"], degree=2)
+    basis = bspline.BSplineBasis(chem, r_min_map={("W", "W"): 0.001}, r_max_map={("W", "W"): 5.5},
+                                 resolution_map={("W", "W"): 15}, trailing_trim=3)
+    rows = {}
+    for k in range(len(fix["energies"])):
+        geom = Atoms(numbers=[74] * fix["positions"].shape[1], positions=fix["positions"][k], cell=fix["cell"],
+                     pbc=True)
+        f = fix["forces"][k]
+        rows[f"w_{k}"] = dict(geometry=geom, energy=float(fix["energies"][k]), fx=f[:, 0], fy=f[:, 1], fz=f[:, 2])
+    df_features = BasisFeaturizer(basis).evaluate(pd.DataFrame.from_dict(rows, orient="index"), progress=None)
+    x_e, y_e, x_f, y_f = ls.dataframe_to_tuples(df_features, n_elements=1, energy_key="energy")
+    assert np.allclose(x_e, fix["x_e"], rtol=1e-9, atol=1e-12) and len(y_f) == int(fix["n_force_rows"])
+    for solver in ("host", "cusolver"):
+        model = ls.WeightedLinearModel(basis, solver=solver, ridge_1b=float(fix["ridge_1b"]),
+                                       ridge_2b=float(fix["ridge_2b"]), curvature_2b=float(fix["curvature_2b"]))
+        model.fit(x_e, y_e, x_f, y_f, weight=float(fix["weight"]))
+        assert np.allclose(model.coefficients, fix["coefficients"], rtol=1e-5, atol=1e-7)
+        assert np.allclose(model.predict(x_f), fix["predict_f"], rtol=1e-5, atol=1e-6)
+
+
 def test_cusolver_solve_matches_host_lapack():
     rng = np.random.default_rng(3)
     for n in (1, 7, 73, 456):

@@ -66,3 +66,26 @@ def test_energy_only_fit():
     model.fit(x_e / n_atoms, y_e / n_atoms)
     assert model.coefficients.shape == (basis.n_feats,)
     assert np.isfinite(model.coefficients).all()
+
+
+def test_fit_reproduces_the_reference_fit_on_its_own_rows():
+    """BASELINE.json configs[0] plumbing, regression half: WeightedLinearModel.fit on the
+    reference's energy rows of tests/golden/fit_w2body_plumbing.npz (written by the running
+    reference, oracle/make_golden_fit.py) — energy-only here because the fixture does not
+    carry the 3072 force rows; the full pipeline is compared on the GPU
+    (tests/test_gpu_api.py::test_plumbing_featurize_and_fit_matches_reference)."""
+    import os
+    from uf3_b200 import bspline, composition
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "fit_w2body_plumbing.npz"))
+    chem = composition.ChemicalSystem(["W"], degree=2)
+    basis = bspline.BSplineBasis(chem, r_min_map={("W", "W"): 0.001}, r_max_map={("W", "W"): 5.5},
+                                 resolution_map={("W", "W"): 15}, trailing_trim=3)
+    assert fix["x_e"].shape == (8, basis.n_feats)
+    # energy rows are per atom: the composition column is 1 after the division by 128
+    assert np.allclose(fix["x_e"][:, 0], 1.0)
+    model = ls.WeightedLinearModel(basis, ridge_1b=float(fix["ridge_1b"]), ridge_2b=float(fix["ridge_2b"]),
+                                   curvature_2b=float(fix["curvature_2b"]))
+    model.fit(fix["x_e"], fix["y_e"])
+    assert np.isfinite(model.coefficients).all() and np.all(model.coefficients[basis.col_idx] == 0)
+    # the reference model (fitted on energies AND forces) predicts the same energies to the noise level
+    assert np.abs(model.predict(fix["x_e"]) - fix["predict_e"]).max() < 5e-3

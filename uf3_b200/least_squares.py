@@ -61,6 +61,31 @@ def batched_moore_penrose(x, y, batch_size=2500):
     return gram, ordinate
 
 
+def dataframe_to_tuples(df_features, n_elements=None, energy_key="energy", sample_weights=None):
+    """Feature DataFrame -> (x_e, y_e, x_f, y_f) (least_squares.py:666-716): first column is
+    the target; energy rows (and targets) are divided by the atom count = sum of the leading
+    `n_elements` composition columns; optional per-configuration sample weights."""
+    names = df_features.index.get_level_values(0)
+    energy_mask = df_features.index.get_level_values(-1) == energy_key
+    force_mask = np.logical_not(energy_mask)
+    data = df_features.to_numpy()
+    y, x = data[:, 0], data[:, 1:]
+    y_e, y_f = y[energy_mask], y[force_mask]
+    if n_elements is not None:
+        size = np.sum(x[energy_mask, :n_elements], axis=1)
+        x_e = np.divide(x[energy_mask].T, size).T
+        y_e = y_e / size
+    else:
+        x_e = x[energy_mask]
+    x_f = x[force_mask]
+    if sample_weights is not None:
+        w = np.array([sample_weights.get(name, 1.0) for name in names])
+        w_e, w_f = w[energy_mask], w[force_mask]
+        x_e, y_e = np.multiply(x_e.T, w_e).T, np.multiply(y_e, w_e)
+        x_f, y_f = np.multiply(x_f.T, w_f).T, np.multiply(y_f, w_f)
+    return x_e, y_e, x_f, y_f
+
+
 def lu_factorization(a, b):
     """Host LAPACK LU solve, as the reference (least_squares.py:763-771)."""
     return np.linalg.solve(a, b)
