@@ -173,12 +173,13 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     k_featurize (symmetry >= 2, rows <= 32), larger grids of symmetry 2 the plane path
     as the cooperative block-per-atom kernel (UF3B_PLANES forces it for small grids too,
     UF3B_NO_COOP selects the warp-per-atom plane path), else the per-triangle register-tile
-    path; UF3B_NO_LEGS / UF3B_NO_TILE force the next more general path."""
+    path; UF3B_NO_LEGS / UF3B_NO_TILE force the next more general path.  The leg-grouped path
+    reads its legs from the k_leg_cache records unless UF3B_NO_LEG_CACHE is set."""
     case = gu.Case(name)
     outs = []
     for env in ({}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"}, {"UF3B_PLANES": "1"},
-                {"UF3B_PLANES": "1", "UF3B_NO_COOP": "1"}):
-        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES", "UF3B_NO_COOP"):
+                {"UF3B_PLANES": "1", "UF3B_NO_COOP": "1"}, {"UF3B_NO_LEG_CACHE": "1"}):
+        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES", "UF3B_NO_COOP", "UF3B_NO_LEG_CACHE"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
@@ -190,7 +191,7 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     for xe, xf in outs:
         assert gu.rel_err(xe, case["x_energy"]) <= REL
         assert gu.rel_err(xf, case["x_forces"]) <= REL
-    for other in (0, 1, 3, 4):
+    for other in (0, 1, 3, 4, 5):
         assert gu.rel_err(outs[other][1], outs[2][1]) <= 1e-11
         assert gu.rel_err(outs[other][0], outs[2][0]) <= 1e-11
 

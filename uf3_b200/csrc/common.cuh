@@ -142,6 +142,7 @@ struct uf3b_basis {
     uf3b::DevBuf<double> stage;
     uf3b::DevBuf<double> stage_e;
     uf3b::DevBuf<double> gacc;     // global-memory accumulators for very wide rows
+    uf3b::DevBuf<unsigned char> leg_cache;   // k_leg_cache records of the current frame
 };
 
 struct uf3b_nlist {

@@ -234,6 +234,8 @@ struct TileGeom {
     int dim_m, dim_n;      // full grid extents of legs m, n
     int goff, col0, sym;
     int warp_bytes;        // shared memory per warp (accumulators + scratch)
+    const unsigned char *leg_cache;   // k_leg_cache records (cached leg-grouped path) or null
+    int cache_max3, cache_stride;     // L-record slots and records per centre
 };
 
 // Tile record: [flags][A B C][vl[4] dvl[4]][vm[ma] dvm[ma] vn[na] dvn[na]], dense by
@@ -725,6 +727,178 @@ __device__ __forceinline__ void plane_three_body(const BasisTab &B, const FrameV
     }
 }
 
+// ---------------------------------------------------------------- leg cache
+// Every leg of the 3-body terms is shared: the leg (i, x) of centre i by all triangles of i
+// through x, the leg (j, k) between two neighbours of i by centre i and by j and k in their
+// neighbour roles.  The owner-computes kernels above re-evaluate them per visiting atom
+// (574 leg evaluations per atom of bulk W against 105 distinct ones, 40 % of the
+// instructions of the demo-basis kernel).  k_leg_cache evaluates each leg ONCE, in the frame
+// of its real centre — the same positions and arithmetic the visiting atoms used, so the
+// values are bit-identical — into sparse 96-byte records in global memory (L2-resident:
+// 10 KB per atom); the cached leg-grouped path then only loads and densifies records.
+// Layout per centre i: records [0, max3) = legs (i, row entry), then the pair (j < k by row
+// position) at max3 + k (k - 1) / 2 + j, stored from j to k (unit vector j -> k).
+__global__ void __launch_bounds__(256)
+k_leg_cache(const BasisTab B, const FrameView f, const TileGeom g, int max3, int stride, unsigned char *cache) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_gw = (gridDim.x * blockDim.x) >> 5;
+    int dummy;
+    for (int i = gw; i < f.n; i += n_gw) {
+        const int row = __ldg(f.off3 + i), ni = __ldg(f.cnt3 + i);
+        const Vec3 pi = real_position(f, i);
+        unsigned char *mine = cache + (size_t)i * stride * SPL_REC;
+        const int n_legs = ni + ni * (ni - 1) / 2;
+        for (int t = lane; t < n_legs; t += 32) {
+            if (t < ni) {
+                eval_sparse_leg<false>(B, 0, pi, super_position(f, __ldg(f.idx3 + row + t), dummy), g.l0,
+                                       mine + (size_t)t * SPL_REC);
+            } else {
+                int qj, qk;
+                unrank_pair(t - ni, qj, qk);
+                eval_sparse_leg<false>(B, 2, super_position(f, __ldg(f.idx3 + row + qj), dummy),
+                                       super_position(f, __ldg(f.idx3 + row + qk), dummy), g.n0,
+                                       mine + (size_t)(max3 + t - ni) * SPL_REC);
+            }
+        }
+    }
+}
+
+// Cached sparse record (global) -> dense leg arrays in shared memory: `stride` values,
+// `stride` derivatives, unit vector (times `sign`), as eval_dense_leg writes them.
+__device__ __forceinline__ void load_dense_leg(const unsigned char *rec, int xa, int stride, double sign,
+                                               unsigned char *out) {
+    const double2 *gp = reinterpret_cast<const double2 *>(rec);
+    const double2 v01 = __ldg(gp), v23 = __ldg(gp + 1), d01 = __ldg(gp + 2), d23 = __ldg(gp + 3);
+    const double2 u01 = __ldg(gp + 4), u2t = __ldg(gp + 5);
+    const int rel = (int)__double_as_longlong(u2t.y);
+    double *val = reinterpret_cast<double *>(out), *der = val + stride, *uv = der + stride;
+    for (int k = 0; k < stride; ++k) { val[k] = 0.0; der[k] = 0.0; }
+    const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = rel + p;
+        if (x >= 0 && x < xa) { val[x] = v[p]; der[x] = dv[p]; }
+    }
+    uv[0] = sign * u01.x;
+    uv[1] = sign * u01.y;
+    uv[2] = sign * u2t.x;
+}
+
+// legs_three_body with every leg evaluation replaced by a load from the leg cache.
+__device__ __forceinline__ void legs_three_body_cached(const BasisTab &B, const FrameView &f, const TileGeom &g,
+                                                       const unsigned char *cache, int max3, int stride,
+                                                       int a, unsigned char *scratch, unsigned scratch_s,
+                                                       Tile<1> &tile, int lane, bool want_e, bool want_f) {
+    const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
+    if (n3a < 1) return;
+    const unsigned lm_s = scratch_s, nn_s = scratch_s + LG_N_BASE;
+    unsigned char *lm = scratch, *nn = scratch + LG_N_BASE;
+    const int cell = lane < g.ma * g.na ? lane : 0;
+    const unsigned off_m = 8u * (unsigned)(cell / g.na), off_n = 8u * (unsigned)(cell % g.na);
+    const unsigned char *mine = cache + (size_t)a * stride * SPL_REC;
+
+    // ---- (i) `a` as the centre
+    if (lane < n3a) load_dense_leg(mine + (size_t)lane * SPL_REC, g.la, 4, 1.0, lm + lane * LG_LM);
+    __syncwarp();
+    const int np = n3a - 1;                       // partners per group
+    const int per_pass = np > 0 ? 32 / np : 32;   // groups per pass (n3a <= 32)
+    for (int g0 = 0; g0 < n3a && np > 0; g0 += per_pass) {
+        {   // phase A: legs (j, k) of up to per_pass groups, one per lane
+            const int gi = lane / np, s = lane - gi * np, j = g0 + gi;
+            if (gi < per_pass && j < n3a) {
+                const int k = s + (s >= j);
+                const int lo = j < k ? j : k, hi = j < k ? k : j;
+                load_dense_leg(mine + (size_t)(max3 + hi * (hi - 1) / 2 + lo) * SPL_REC, g.na, 12, 1.0,
+                               nn + lane * LG_N);       // only the values are used in this role
+            }
+        }
+        __syncwarp();
+        for (int gi = 0; gi < per_pass && g0 + gi < n3a; ++gi) {      // phase B: one group at a time
+            const int j = g0 + gi;
+            double P = 0.0, Pe = 0.0;
+            for (int s = 0; s < np; ++s) {
+                const int k = s + (s >= j);
+                const double vm = lds64(lm_s + (unsigned)k * LG_LM + off_m);
+                const double vn = lds64(nn_s + (unsigned)(gi * np + s) * LG_N + off_n);
+                P = fma(vm, vn, P);
+                if (k > j) Pe = fma(vm, vn, Pe);       // each unordered pair once for the energy row
+            }
+            const unsigned lj = lm_s + (unsigned)j * LG_LM;
+            const double2 u01 = lds128(lj + 64);
+            const double u2 = lds64(lj + 80);
+#pragma unroll
+            for (int l = 0; l < RT_LA; ++l) {
+                if (l < g.la) {
+                    const double v = lds64(lj + 8 * l), dP = lds64(lj + 32 + 8 * l) * P;
+                    if (want_e) tile.acc[0][l][0] = fma(v, Pe, tile.acc[0][l][0]);
+                    tile.acc[0][l][1] = fma(u01.x, dP, tile.acc[0][l][1]);
+                    tile.acc[0][l][2] = fma(u01.y, dP, tile.acc[0][l][2]);
+                    tile.acc[0][l][3] = fma(u2, dP, tile.acc[0][l][3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (!want_f) return;
+
+    // ---- (ii) `a` as a neighbour of every centre i in its list
+    for (int e = 0; e < n3a; ++e) {
+        const int m = __ldg(f.idx3 + row0 + e);
+        const int gimg = image_of(f, m);
+        const int ci = m - gimg * f.n;
+        const int apr = __ldg(f.img_inv + gimg) * f.n + a;
+        const int rowi = __ldg(f.off3 + ci), ni = __ldg(f.cnt3 + ci);
+        const int its = lane < ni ? __ldg(f.idx3 + rowi + lane) : -1;
+        const unsigned hit = __ballot_sync(FULL, its == apr);
+        if (!hit) continue;                       // one-ulp asymmetry of the list criterion
+        const int qa = __ffs(hit) - 1;
+        const unsigned char *theirs = cache + (size_t)ci * stride * SPL_REC;
+        // phase A: legs (i, x) for the whole row of i, then legs (a', k) for k != a'
+        const int n_items = 2 * ni - 1;
+        for (int it0 = 0; it0 < n_items; it0 += 32) {
+            const int it = it0 + lane;
+            if (it < n_items) {
+                if (it < ni) {
+                    load_dense_leg(theirs + (size_t)it * SPL_REC, g.la, 4, 1.0, lm + it * LG_LM);
+                } else {
+                    const int s = it - ni, k = s + (s >= qa);
+                    const int lo = qa < k ? qa : k, hi = qa < k ? k : qa;
+                    load_dense_leg(theirs + (size_t)(max3 + hi * (hi - 1) / 2 + lo) * SPL_REC, g.na, 12,
+                                   qa < k ? 1.0 : -1.0, nn + s * LG_N);      // unit vector a' -> k
+                }
+            }
+        }
+        __syncwarp();
+        double P = 0.0, Qx = 0.0, Qy = 0.0, Qz = 0.0;
+        for (int s = 0; s < ni - 1; ++s) {
+            const int k = s + (s >= qa);
+            const unsigned ns = nn_s + (unsigned)s * LG_N;
+            const double vm = lds64(lm_s + (unsigned)k * LG_LM + off_m);
+            const double vn = lds64(ns + off_n), dvn = lds64(ns + 96 + off_n);
+            const double2 w01 = lds128(ns + 192);
+            const double w2 = lds64(ns + 208);
+            P = fma(vm, vn, P);
+            const double t3 = vm * dvn;
+            Qx = fma(w01.x, t3, Qx);
+            Qy = fma(w01.y, t3, Qy);
+            Qz = fma(w2, t3, Qz);
+        }
+        const unsigned la_s = lm_s + (unsigned)qa * LG_LM;
+        const double2 u01 = lds128(la_s + 64);
+        const double u2 = lds64(la_s + 80);
+#pragma unroll
+        for (int l = 0; l < RT_LA; ++l) {
+            if (l < g.la) {
+                const double v = lds64(la_s + 8 * l), dP = lds64(la_s + 32 + 8 * l) * P;
+                tile.acc[0][l][1] += v * Qx - u01.x * dP;
+                tile.acc[0][l][2] += v * Qy - u01.y * dP;
+                tile.acc[0][l][3] += v * Qz - u2 * dP;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // 2-body rows of atom `a` (bspline.py:810-895) added into acc[4 * col + (e, fx, fy, fz)]:
 // lanes evaluate 32 pairs at a time into `prec`, then every lane gathers the records that
 // touch ITS feature column.
@@ -789,7 +963,8 @@ __device__ __forceinline__ void two_body_rows(const BasisTab &B, const FrameView
 // (L1/L2 resident) instead of shared memory — the path for bases whose rows do not fit
 // (e.g. 18 trio interactions of a ternary system, F ~ 7000).
 // KP = 1, 2 selects the register-tile path with KP (m, n) cells per lane; KP = 3 the
-// leg-grouped tile path; KP = 4, 5, 6 the plane path with 1, 2, 4 chunks of 32 (m, n) cells.
+// leg-grouped tile path (KP = 7: with the leg cache); KP = 4, 5, 6 the plane path with
+// 1, 2, 4 chunks of 32 (m, n) cells.
 template <bool GLOBAL_ACC, int KP>
 __global__ void __launch_bounds__(256, 2)
 k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__restrict__ xf, long long ld,
@@ -811,7 +986,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
 
     for (int k = lane; k < 4 * F; k += 32) acc[k] = 0.0;
     __syncwarp();
-    constexpr bool LEGS = KP == 3, PLANES = KP >= 4;
+    constexpr bool LEGS = KP == 3 || KP == 7, CACHED = KP == 7, PLANES = KP >= 4 && KP <= 6;
     constexpr int KC = KP == 4 ? 1 : (KP == 5 ? 2 : 4);
     Tile<((KP == 1 || KP == 2) ? KP : 1)> tile;
     if constexpr (KP > 0 && !PLANES) tile.init(tg, lane);
@@ -840,6 +1015,9 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
         // ------------------------------------------------ 3-body (angles.py:17-286)
         if constexpr (PLANES) {
             plane_three_body<KC>(B, f, tg, a, pa, scratch, recs_s, acc_rw.base, bin0, lane, want_e, want_f);
+        } else if constexpr (CACHED) {
+            legs_three_body_cached(B, f, tg, tg.leg_cache, tg.cache_max3, tg.cache_stride, a, scratch, recs_s,
+                                   tile, lane, want_e, want_f);
         } else if constexpr (LEGS) {
             legs_three_body(B, f, tg, a, pa, scratch, recs_s, tile, lane, want_e, want_f);
         } else if (B.n_trios > 0) {
@@ -1338,7 +1516,20 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
             kp = tg.ma * tg.na <= 32 ? 4 : (tg.ma * tg.na <= 64 ? 5 : 6);
     }
     // cooperative plane kernel: one block per atom, thread = (m, n) cell, registers hold the l axis
-    const bool coop = kp >= 4 && tg.la <= CO_LA && !getenv("UF3B_NO_COOP");
+    // leg cache for the leg-grouped path: every distinct leg evaluated once by k_leg_cache
+    if (kp == 3 && x_forces && !getenv("UF3B_NO_LEG_CACHE")) {
+        const int max3 = std::max(nl->max3, 1);
+        const long long stride = max3 + (long long)max3 * (max3 - 1) / 2;
+        const size_t bytes = (size_t)n * (size_t)stride * SPL_REC;
+        if (bytes <= ((size_t)2 << 30)) {
+            UF3B_CUDA(basis->leg_cache.reserve(bytes));
+            tg.leg_cache = basis->leg_cache.p;
+            tg.cache_max3 = max3;
+            tg.cache_stride = (int)stride;
+            kp = 7;
+        }
+    }
+    const bool coop = kp >= 4 && kp <= 6 && tg.la <= CO_LA && !getenv("UF3B_NO_COOP");
     if (coop) {
         CoopGeom cg = {};
         cg.g = tg;
@@ -1392,7 +1583,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
             return finish_featurize(basis, x_energy, x_forces, ld, d_xe, d_xf, F, n, e_dev, f_dev, stream, ev0, ev1);
         }
     }
-    const size_t scratch_bytes = kp >= 4 ? plane_scratch_bytes(tg.ma * tg.na) : ((WARP_SCRATCH + 15) & ~size_t(15));
+    const size_t scratch_bytes = (kp >= 4 && kp <= 6) ? plane_scratch_bytes(tg.ma * tg.na) : ((WARP_SCRATCH + 15) & ~size_t(15));
     const size_t per_warp = featurize_acc_bytes(F, global_acc) + scratch_bytes;
     tg.warp_bytes = (int)per_warp;
     // warps per block: the count that keeps most warps resident (128 registers per thread
@@ -1414,6 +1605,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         case 4: kernel = k_featurize<false, 4>; break;
         case 5: kernel = k_featurize<false, 5>; break;
         case 6: kernel = k_featurize<false, 6>; break;
+        case 7: kernel = k_featurize<false, 7>; break;
         default: break;
     }
     UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1451,6 +1643,9 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         UF3B_CUDA(cudaEventRecord(ev0, stream));
     }
     if (global_acc) UF3B_CUDA(basis->gacc.reserve((size_t)n_gw * 4 * F));
+    if (kp == 7)
+        UF3B_LAUNCH(k_leg_cache, std::min((n + 7) / 8, sm_count() * 8), 256, 0, stream, basis->tab, view, tg,
+                    tg.cache_max3, tg.cache_stride, basis->leg_cache.p);
     UF3B_LAUNCH(kernel, grid, warps * 32, smem, stream, basis->tab, view, tg, d_xf, d_ld,
                 basis->partials.p, basis->gacc.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
