@@ -764,24 +764,35 @@ k_leg_cache(const BasisTab B, const FrameView f, const TileGeom g, int max3, int
 }
 
 // Cached sparse record (global) -> dense leg arrays in shared memory: `stride` values,
-// `stride` derivatives, unit vector (times `sign`), as eval_dense_leg writes them.
+// `stride` derivatives, unit vector (times `sign`), as eval_dense_leg writes them (stride
+// even, `out` 16-byte aligned).  VALUES_ONLY skips the derivatives and the unit vector.
+template <bool VALUES_ONLY>
 __device__ __forceinline__ void load_dense_leg(const unsigned char *rec, int xa, int stride, double sign,
                                                unsigned char *out) {
     const double2 *gp = reinterpret_cast<const double2 *>(rec);
-    const double2 v01 = __ldg(gp), v23 = __ldg(gp + 1), d01 = __ldg(gp + 2), d23 = __ldg(gp + 3);
-    const double2 u01 = __ldg(gp + 4), u2t = __ldg(gp + 5);
+    const double2 v01 = __ldg(gp), v23 = __ldg(gp + 1);
+    double2 d01 = make_double2(0.0, 0.0), d23 = d01, u01 = d01;
+    const double2 u2t = __ldg(gp + 5);
+    if (!VALUES_ONLY) { d01 = __ldg(gp + 2); d23 = __ldg(gp + 3); u01 = __ldg(gp + 4); }
     const int rel = (int)__double_as_longlong(u2t.y);
     double *val = reinterpret_cast<double *>(out), *der = val + stride, *uv = der + stride;
-    for (int k = 0; k < stride; ++k) { val[k] = 0.0; der[k] = 0.0; }
+    double2 *z = reinterpret_cast<double2 *>(out);
+    const int n16 = VALUES_ONLY ? stride / 2 : stride;
+    for (int k = 0; k < n16; ++k) z[k] = make_double2(0.0, 0.0);
     const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int x = rel + p;
-        if (x >= 0 && x < xa) { val[x] = v[p]; der[x] = dv[p]; }
+        if (x >= 0 && x < xa) {
+            val[x] = v[p];
+            if (!VALUES_ONLY) der[x] = dv[p];
+        }
     }
-    uv[0] = sign * u01.x;
-    uv[1] = sign * u01.y;
-    uv[2] = sign * u2t.x;
+    if (!VALUES_ONLY) {
+        uv[0] = sign * u01.x;
+        uv[1] = sign * u01.y;
+        uv[2] = sign * u2t.x;
+    }
 }
 
 // legs_three_body with every leg evaluation replaced by a load from the leg cache.
@@ -798,7 +809,7 @@ __device__ __forceinline__ void legs_three_body_cached(const BasisTab &B, const 
     const unsigned char *mine = cache + (size_t)a * stride * SPL_REC;
 
     // ---- (i) `a` as the centre
-    if (lane < n3a) load_dense_leg(mine + (size_t)lane * SPL_REC, g.la, 4, 1.0, lm + lane * LG_LM);
+    if (lane < n3a) load_dense_leg<false>(mine + (size_t)lane * SPL_REC, g.la, 4, 1.0, lm + lane * LG_LM);
     __syncwarp();
     const int np = n3a - 1;                       // partners per group
     const int per_pass = np > 0 ? 32 / np : 32;   // groups per pass (n3a <= 32)
@@ -808,8 +819,8 @@ __device__ __forceinline__ void legs_three_body_cached(const BasisTab &B, const 
             if (gi < per_pass && j < n3a) {
                 const int k = s + (s >= j);
                 const int lo = j < k ? j : k, hi = j < k ? k : j;
-                load_dense_leg(mine + (size_t)(max3 + hi * (hi - 1) / 2 + lo) * SPL_REC, g.na, 12, 1.0,
-                               nn + lane * LG_N);       // only the values are used in this role
+                load_dense_leg<true>(mine + (size_t)(max3 + hi * (hi - 1) / 2 + lo) * SPL_REC, g.na, 12, 1.0,
+                                     nn + lane * LG_N);       // only the values are used in this role
             }
         }
         __syncwarp();
@@ -842,16 +853,23 @@ __device__ __forceinline__ void legs_three_body_cached(const BasisTab &B, const 
     if (!want_f) return;
 
     // ---- (ii) `a` as a neighbour of every centre i in its list
-    for (int e = 0; e < n3a; ++e) {
-        const int m = __ldg(f.idx3 + row0 + e);
+    // lane e resolves entry e up front (centre, its row length, the position qa of `a` in its
+    // row), so that the per-centre loop below starts with the record loads
+    int my_ci = 0, my_ni = 0, my_qa = -1;
+    if (lane < n3a) {
+        const int m = __ldg(f.idx3 + row0 + lane);
         const int gimg = image_of(f, m);
-        const int ci = m - gimg * f.n;
+        my_ci = m - gimg * f.n;
         const int apr = __ldg(f.img_inv + gimg) * f.n + a;
-        const int rowi = __ldg(f.off3 + ci), ni = __ldg(f.cnt3 + ci);
-        const int its = lane < ni ? __ldg(f.idx3 + rowi + lane) : -1;
-        const unsigned hit = __ballot_sync(FULL, its == apr);
-        if (!hit) continue;                       // one-ulp asymmetry of the list criterion
-        const int qa = __ffs(hit) - 1;
+        const int rowi = __ldg(f.off3 + my_ci);
+        my_ni = __ldg(f.cnt3 + my_ci);
+        for (int k = 0; k < my_ni; ++k)
+            if (__ldg(f.idx3 + rowi + k) == apr) my_qa = k;
+    }
+    for (int e = 0; e < n3a; ++e) {
+        const int ci = __shfl_sync(FULL, my_ci, e), ni = __shfl_sync(FULL, my_ni, e);
+        const int qa = __shfl_sync(FULL, my_qa, e);
+        if (qa < 0) continue;                     // one-ulp asymmetry of the list criterion
         const unsigned char *theirs = cache + (size_t)ci * stride * SPL_REC;
         // phase A: legs (i, x) for the whole row of i, then legs (a', k) for k != a'
         const int n_items = 2 * ni - 1;
@@ -859,12 +877,12 @@ __device__ __forceinline__ void legs_three_body_cached(const BasisTab &B, const 
             const int it = it0 + lane;
             if (it < n_items) {
                 if (it < ni) {
-                    load_dense_leg(theirs + (size_t)it * SPL_REC, g.la, 4, 1.0, lm + it * LG_LM);
+                    load_dense_leg<false>(theirs + (size_t)it * SPL_REC, g.la, 4, 1.0, lm + it * LG_LM);
                 } else {
                     const int s = it - ni, k = s + (s >= qa);
                     const int lo = qa < k ? qa : k, hi = qa < k ? k : qa;
-                    load_dense_leg(theirs + (size_t)(max3 + hi * (hi - 1) / 2 + lo) * SPL_REC, g.na, 12,
-                                   qa < k ? 1.0 : -1.0, nn + s * LG_N);      // unit vector a' -> k
+                    load_dense_leg<false>(theirs + (size_t)(max3 + hi * (hi - 1) / 2 + lo) * SPL_REC, g.na, 12,
+                                          qa < k ? 1.0 : -1.0, nn + s * LG_N);      // unit vector a' -> k
                 }
             }
         }
