@@ -151,6 +151,11 @@ struct uf3b_nlist {
     int64_t total2 = 0, total3 = 0;
     int max3 = 0;                  // longest row of the 3-body list
     int c_first = 0, c_count = 0;  // centre range of the last build
+    // 16 doubles of pinned, device-mapped host memory: the two small read-backs of a build
+    // (bounding box, list totals) are WRITTEN there by a kernel instead of being copied, so
+    // they never queue behind a large device->host row copy on the copy engine
+    double *h_mapped = nullptr;
+    ~uf3b_nlist() { if (h_mapped) cudaFreeHost(h_mapped); }
     uf3b::DevBuf<double> pos, img_off;
     uf3b::DevBuf<int> z, spec, img_inv;
     uf3b::DevBuf<int> off2, off3, cnt2, cnt3, idx2, idx3, scratch2, scratch3;

@@ -1096,7 +1096,7 @@ k_featurize(const BasisTab B, const FrameView f, const TileGeom tg, double *__re
             for (int col = lane; col < F; col += 32) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    xf[((long long)c * f.n + a) * ld + col] = acc[4 * col + 1 + c];
+                    __stcs(xf + ((long long)c * f.n + a) * ld + col, acc[4 * col + 1 + c]);   // written once: streaming
                     acc[4 * col + 1 + c] = 0.0;
                 }
             }
@@ -1181,6 +1181,18 @@ __device__ __forceinline__ void publish_group_leg(unsigned src, unsigned dst, in
     }
 }
 
+// Cached sparse record (global) -> the same record in shared memory; `sign` scales the unit
+// vector (the cache stores a pair's leg from the lower to the higher row position).
+__device__ __forceinline__ void copy_leg_record(const unsigned char *rec, double sign, unsigned char *out) {
+    const double2 *gp = reinterpret_cast<const double2 *>(rec);
+    const double2 a0 = __ldg(gp), a1 = __ldg(gp + 1), a2 = __ldg(gp + 2), a3 = __ldg(gp + 3);
+    const double2 u01 = __ldg(gp + 4), u2t = __ldg(gp + 5);
+    double2 *o = reinterpret_cast<double2 *>(out);
+    o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+    o[4] = make_double2(sign * u01.x, sign * u01.y);
+    o[5] = make_double2(sign * u2t.x, u2t.y);
+}
+
 // One published group added to the thread's registers: the 4 l values IL..IL+3 of the
 // group's leg, statically indexed (the switch in add_group picks IL = idx - l0).
 template <int LA, int IL, bool CENTRE>
@@ -1260,7 +1272,6 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
         for (int k = lane; k < (2 * cg.plane_bytes + 32) / 16; k += 32) z[k] = make_double2(0.0, 0.0);
     }
     __syncthreads();
-    int dummy;
 
     for (int a = blockIdx.x; a < f.n; a += gridDim.x) {
         const int sa = __ldg(f.spec + a);
@@ -1273,17 +1284,16 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
         const int c0 = 1 + (want_f ? n3a : 0);        // first centre-role slot
         const int n_slots = c0 + (n3a > 1 ? n3a : 0);
         const bool early = c0 < W;
+        const unsigned char *mine_c = g.leg_cache + (size_t)a * g.cache_stride * SPL_REC;
         if (early) {
             if (warp == 0 && lane < n3a)
-                eval_sparse_leg<false>(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0,
-                                       smem + cg.off_ltab + lane * SPL_REC);
+                copy_leg_record(mine_c + (size_t)lane * SPL_REC, 1.0, smem + cg.off_ltab + lane * SPL_REC);
             __syncthreads();
         }
         for (int g0 = 0; g0 < n_slots; g0 += W) {
             const int slot = g0 + warp;
             if (!early && slot == (W > 1 ? 1 : 0) && lane < n3a)
-                eval_sparse_leg<false>(B, 0, pa, super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.l0,
-                                       smem + cg.off_ltab + lane * SPL_REC);
+                copy_leg_record(mine_c + (size_t)lane * SPL_REC, 1.0, smem + cg.off_ltab + lane * SPL_REC);
             if (slot == 0) {
                 if (lane == 0) acc[4 * sa] += 1.0;      // composition column n_el (composition.py:96-111)
                 __syncwarp();
@@ -1297,15 +1307,17 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
                 // ---- `a` is the centre, the group is its leg to neighbour j
                 const int j = gs;
                 if (n3a > 1) {
-                    if (lane < n3a && lane != j)
-                        eval_n_leg(B, super_position(f, __ldg(f.idx3 + row0 + j), dummy),
-                                   super_position(f, __ldg(f.idx3 + row0 + lane), dummy), g.n0, nn + lane * SPL_REC);
+                    if (lane < n3a && lane != j) {     // leg (j, k = lane): only its values are used here
+                        const int lo = j < lane ? j : lane, hi = j < lane ? lane : j;
+                        copy_leg_record(mine_c + (size_t)(g.cache_max3 + hi * (hi - 1) / 2 + lo) * SPL_REC, 1.0,
+                                        nn + lane * SPL_REC);
+                    }
                     __syncwarp();
                     for (int k0 = 0; k0 < n3a; k0 += 2) {     // two partners per pass, one per half-warp
                         const int k = min(k0 + half, n3a - 1);
                         const unsigned lk = ltab_s + (unsigned)k * SPL_REC, ns = nn_s + (unsigned)k * SPL_REC;
                         const unsigned mrel = (unsigned)(lds32(lk + SPL_IDX) + p);
-                        const unsigned nrel = (unsigned)(k == j ? SP_DEAD : lds32(ns + 64) + q);
+                        const unsigned nrel = (unsigned)(k == j ? SP_DEAD : lds32(ns + SPL_IDX) + q);
                         const bool ok = mrel < ma && nrel < na && k0 + half < n3a;
                         const unsigned ad = ok ? (half ? pl_b : pl_a) + 8u * (mrel * nap + nrel) : dummy_s;
                         sts64(ad, fma(lds64(lk + 8 * p), lds64(ns + 8 * q), lds64(ad)));
@@ -1325,32 +1337,37 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
                 const unsigned hit = __ballot_sync(FULL, its == apr);
                 if (hit) {                        // (a miss: one-ulp asymmetry of the list criterion)
                     const int qa = __ffs(hit) - 1;
-                    const Vec3 pi = real_position(f, ci), pap = super_position(f, apr, dummy);
+                    const unsigned char *theirs = g.leg_cache + (size_t)ci * g.cache_stride * SPL_REC;
                     for (int it0 = 0; it0 < 2 * ni_; it0 += 32) {
                         const int it = it0 + lane;
                         const bool centre_leg = it < ni_;
                         const int k = centre_leg ? it : it - ni_;
                         if (it < 2 * ni_ && (centre_leg || k != qa)) {
-                            const Vec3 pk = super_position(f, __ldg(f.idx3 + rowi + k), dummy);
-                            if (centre_leg) eval_sparse_leg<false>(B, 0, pi, pk, g.l0, lm + k * SPL_REC);
-                            else eval_n_leg(B, pap, pk, g.n0, nn + k * SPL_REC);
+                            if (centre_leg) {
+                                copy_leg_record(theirs + (size_t)k * SPL_REC, 1.0, lm + k * SPL_REC);
+                            } else {              // leg (a', k), unit vector a' -> k
+                                const int lo = qa < k ? qa : k, hi = qa < k ? k : qa;
+                                copy_leg_record(theirs + (size_t)(g.cache_max3 + hi * (hi - 1) / 2 + lo) * SPL_REC,
+                                                qa < k ? 1.0 : -1.0, nn + k * SPL_REC);
+                            }
                         }
                     }
                     __syncwarp();
                     const unsigned off_x = 32u * (unsigned)half + 8u * (unsigned)q;      // v[q] | dv[q]
-                    const unsigned off_w = 64u + 16u * (unsigned)half;                   // (idx, wx) | (wy, wz)
+                    const unsigned off_w = 64u + 8u * (unsigned)half;                    // wx | wy
                     const unsigned pl = half ? pl_b : pl_a;
                     for (int k = 0; k < ni_; ++k) {           // lanes 0-15 own (P, Qx), lanes 16-31 (Qy, Qz)
                         if (k == qa) continue;
                         const unsigned lk = lm_s + (unsigned)k * SPL_REC, ns = nn_s + (unsigned)k * SPL_REC;
-                        const unsigned mrel = (unsigned)(lds32(lk + SPL_IDX) + p), nrel = (unsigned)(lds32(ns + 64) + q);
+                        const unsigned mrel = (unsigned)(lds32(lk + SPL_IDX) + p);
+                        const unsigned nrel = (unsigned)(lds32(ns + SPL_IDX) + q);
                         const bool ok = mrel < ma && nrel < na;
                         const unsigned ad = ok ? pl + 16u * (mrel * nap + nrel) : dummy_s;
                         const double vm = lds64(lk + 8 * p), x = lds64(ns + off_x), dvn = lds64(ns + 32 + 8 * q);
-                        const double2 w = lds128(ns + off_w);
+                        const double wa = lds64(ns + off_w), wz = lds64(ns + 80);
                         double2 c = lds128(ad);
-                        c.x = fma(vm * x, half ? w.x : 1.0, c.x);      // P += vm vn       | Qy += wy vm dvn
-                        c.y = fma(vm * dvn, w.y, c.y);                 // Qx += wx vm dvn  | Qz += wz vm dvn
+                        c.x = fma(vm * x, half ? wa : 1.0, c.x);       // P += vm vn       | Qy += wy vm dvn
+                        c.y = fma(vm * dvn, half ? wz : wa, c.y);      // Qx += wx vm dvn  | Qz += wz vm dvn
                         sts128(ad, c);
                         __syncwarp();
                     }
@@ -1420,7 +1437,7 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
             for (int col = tid; col < F; col += blockDim.x) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    xf[((long long)c * f.n + a) * ld + col] = acc[4 * col + 1 + c];
+                    __stcs(xf + ((long long)c * f.n + a) * ld + col, acc[4 * col + 1 + c]);   // written once: streaming
                     acc[4 * col + 1 + c] = 0.0;
                 }
             }
@@ -1547,7 +1564,20 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
             kp = 7;
         }
     }
-    const bool coop = kp >= 4 && kp <= 6 && tg.la <= CO_LA && !getenv("UF3B_NO_COOP");
+    bool coop = kp >= 4 && kp <= 6 && tg.la <= CO_LA && !getenv("UF3B_NO_COOP");
+    if (coop) {         // the cooperative kernel reads every leg from the leg cache
+        const int max3 = std::max(nl->max3, 1);
+        const long long stride = max3 + (long long)max3 * (max3 - 1) / 2;
+        const size_t bytes = (size_t)n * (size_t)stride * SPL_REC;
+        if (bytes <= ((size_t)2 << 30)) {
+            UF3B_CUDA(basis->leg_cache.reserve(bytes));
+            tg.leg_cache = basis->leg_cache.p;
+            tg.cache_max3 = max3;
+            tg.cache_stride = (int)stride;
+        } else {
+            coop = false;
+        }
+    }
     if (coop) {
         CoopGeom cg = {};
         cg.g = tg;
@@ -1592,6 +1622,8 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                 UF3B_CUDA(cudaEventCreate(&ev1));
                 UF3B_CUDA(cudaEventRecord(ev0, stream));
             }
+            UF3B_LAUNCH(k_leg_cache, std::min((n + 7) / 8, sm_count() * 8), 256, 0, stream, basis->tab, view, tg,
+                        tg.cache_max3, tg.cache_stride, basis->leg_cache.p);
             UF3B_LAUNCH(kc, grid, cg.warps * 32, smem_c, stream, basis->tab, view, cg, d_xf, d_ld,
                         basis->partials.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
             if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));

@@ -488,6 +488,12 @@ FrameView uf3b_nlist::view() const {
     return f;
 }
 
+// n 8-byte words device -> device-mapped host memory (see uf3b_nlist::h_mapped)
+__global__ void k_post_small(const double *__restrict__ src, volatile double *dst, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
 extern "C" {
 
 int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *positions,
@@ -566,9 +572,11 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     const int prep_blocks = std::min((n + 1023) / 1024, sm_count());
     UF3B_LAUNCH(k_prepare, prep_blocks, 1024, 0, stream, n, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
                 nl->spec.p, nl->misc.p, d_err);
+    if (!nl->h_mapped) UF3B_CUDA(cudaHostAlloc((void **)&nl->h_mapped, 16 * sizeof(double), cudaHostAllocMapped));
     double h_misc[7];
-    UF3B_CUDA(cudaMemcpyAsync(h_misc, nl->misc.p, sizeof h_misc, cudaMemcpyDeviceToHost, stream));
+    UF3B_LAUNCH(k_post_small, 1, 32, 0, stream, nl->misc.p, nl->h_mapped, 7);
     UF3B_CUDA(cudaStreamSynchronize(stream));
+    memcpy(h_misc, nl->h_mapped, sizeof h_misc);
     int h_err;
     memcpy(&h_err, &h_misc[6], sizeof h_err);
     if (h_err) return fail(UF3B_ERR_ELEMENT, "configuration holds an element outside the basis");
@@ -629,8 +637,9 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
         UF3B_LAUNCH(k_neighbors, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G, nl->slots.p,
                     nl->cell_start.p, nl->c_first, nl->c_count, nl->off2.p, nl->cnt2.p, nl->off3.p, nl->cnt3.p, nl->idx2.p,
                     nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status);
-        UF3B_CUDA(cudaMemcpyAsync(h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, stream));
+        UF3B_LAUNCH(k_post_small, 1, 32, 0, stream, (const double *)status, nl->h_mapped + 8, 2);
         UF3B_CUDA(cudaStreamSynchronize(stream));
+        memcpy(h_status, nl->h_mapped + 8, sizeof h_status);
         if (h_status[0] < 0 || h_status[1] < 0)
             return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
         if (!h_status[2]) break;
