@@ -27,6 +27,10 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "bulk bcc W 10x20x25 cells (10000 atoms/frame), sigma=0.05 A, 2+3-body featurization"
 N_POOL = 8          # distinct frames (inputs AND output row buffers) per rank, cycled
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the
+# `ncu --set full` captures summarised under profiles/ (r01_k_featurize_v20_legcache_details.txt,
+# r01_k_featurize_coop_manuscript_v20_details.txt); the leg-cache reads are in it
+NCU_TRAFFIC_BYTES = {"demo": 113.1e6 + 9.5e6, "manuscript": 116.7e6 + 79.1e6}
 
 
 def load_peaks():
@@ -413,7 +417,9 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_featurize", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes},
+                     "traffic": NCU_TRAFFIC_BYTES.get(args.basis), "traffic_source": "ncu --set full, profiles/ (v20)",
+                     "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
+                     "kernel_note": "k_leg_cache + the featurize kernel, timed together"},
         "roofline_fp64": {"peak_tflops": fp64_peak, "peak_source": "uf3b_probe_fp64_tflops (DFMA chains)",
                           "note": "3-body rows are FP64-bound, see DESIGN.md"},
         "cpu_baseline": cpu,

@@ -1449,30 +1449,44 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
 }
 
 // Energy row = element counts (composition.py:96-111) + fixed-order sum of the warps'
-// partial rows.  One block per 32 feature columns: warp w sums rows w, w+8, ... with
-// coalesced reads, then the eight per-warp sums are added in a fixed order.
+// partial rows, in two stages so that the sum over thousands of rows is spread over the
+// chip: block (x, y) sums rows [y * rows_per_block, ...) of 32 feature columns into
+// out[y][col] — warp w takes rows w, w+8, ... with coalesced reads, then the eight per-warp
+// sums are added in a fixed order; a second launch folds the ER_SPLIT intermediate rows.
+constexpr int ER_SPLIT = 32;
 __global__ void __launch_bounds__(256)
-k_energy_row(const double *__restrict__ partials, int n_rows, int n_feats, int ne,
-             const int *__restrict__ spec, int n, double *__restrict__ xe) {
+k_energy_row(const double *__restrict__ partials, int n_rows, int rows_per_block, int n_feats,
+             double *__restrict__ out) {
     __shared__ double red[8][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + lane;
+    const int r_begin = blockIdx.y * rows_per_block;
+    const int r_end = min(n_rows, r_begin + rows_per_block);
     double s = 0.0;
     if (col < n_feats)      // the element-count columns were accumulated by k_featurize as well
-        for (int r = warp; r < n_rows; r += 8) s += partials[(size_t)r * n_feats + col];
+        for (int r = r_begin + warp; r < r_end; r += 8) s += partials[(size_t)r * n_feats + col];
     red[warp][lane] = s;
     __syncthreads();
     if (warp == 0 && col < n_feats) {
         double t = red[0][lane];
 #pragma unroll
         for (int w = 1; w < 8; ++w) t += red[w][lane];
-        xe[col] = t;
+        out[(size_t)blockIdx.y * n_feats + col] = t;
     }
 }
 
 }  // namespace uf3b
 
 using namespace uf3b;
+
+// partials [n_rows][F] (+ ER_SPLIT scratch rows behind them) -> energy row d_xe
+static int launch_energy_row(double *partials, int n_rows, int F, double *d_xe, cudaStream_t stream) {
+    double *mid = partials + (size_t)n_rows * F;
+    const int per = (n_rows + ER_SPLIT - 1) / ER_SPLIT;
+    UF3B_LAUNCH(k_energy_row, dim3((F + 31) / 32, ER_SPLIT), 256, 0, stream, partials, n_rows, per, F, mid);
+    UF3B_LAUNCH(k_energy_row, dim3((F + 31) / 32, 1), 256, 0, stream, mid, ER_SPLIT, ER_SPLIT, F, d_xe);
+    return UF3B_OK;
+}
 
 // Copies to host buffers (if any), synchronisation and kernel timing shared by the launch paths.
 static int finish_featurize(uf3b_basis *basis, double *x_energy, double *x_forces, int64_t ld, double *d_xe,
@@ -1609,7 +1623,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
             }
             double *d_xe = x_energy;
             if (x_energy) {
-                UF3B_CUDA(basis->partials.reserve((size_t)grid * F));
+                UF3B_CUDA(basis->partials.reserve((size_t)(grid + ER_SPLIT) * F));
                 if (!e_dev) {
                     UF3B_CUDA(basis->stage_e.reserve(F));
                     d_xe = basis->stage_e.p;
@@ -1628,8 +1642,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                         basis->partials.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
             if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
             if (x_energy)
-                UF3B_LAUNCH(k_energy_row, (F + 31) / 32, 256, 0, stream, basis->partials.p, grid, F, basis->tab.ne,
-                            view.spec, n, d_xe);
+                if (int rc = launch_energy_row(basis->partials.p, grid, F, d_xe, stream)) return rc;
             return finish_featurize(basis, x_energy, x_forces, ld, d_xe, d_xf, F, n, e_dev, f_dev, stream, ev0, ev1);
         }
     }
@@ -1679,7 +1692,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     }
     double *d_xe = x_energy;
     if (x_energy) {
-        UF3B_CUDA(basis->partials.reserve((size_t)n_gw * F));
+        UF3B_CUDA(basis->partials.reserve((size_t)(n_gw + ER_SPLIT) * F));
         if (!e_dev) {
             UF3B_CUDA(basis->stage_e.reserve(F));
             d_xe = basis->stage_e.p;
@@ -1700,7 +1713,6 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                 basis->partials.p, basis->gacc.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (x_energy)
-        UF3B_LAUNCH(k_energy_row, (F + 31) / 32, 256, 0, stream, basis->partials.p, n_gw, F, basis->tab.ne,
-                    view.spec, n, d_xe);
+        if (int rc = launch_energy_row(basis->partials.p, n_gw, F, d_xe, stream)) return rc;
     return finish_featurize(basis, x_energy, x_forces, ld, d_xe, d_xf, F, n, e_dev, f_dev, stream, ev0, ev1);
 }
