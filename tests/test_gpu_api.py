@@ -192,6 +192,10 @@ def test_centre_ranges_sum_to_the_full_frame(name):
         assert gu.rel_err(f_sum, f_full) <= 1e-12 and gu.rel_err(w_sum, w_full) <= 1e-12
     assert abs(e_full - float(case["energy"])) <= 1e-6 * abs(float(case["energy"]))
     assert gu.rel_err(f_full, case["forces"]) <= 1e-6
+    # a rank without centres (more ranks than atoms) contributes exact zeros
+    eng.build_neighbors(positions, numbers, images=images, centres=(n, 0))
+    e, f, w = eng.energy_forces(virial=True)
+    assert e == 0.0 and not f.any() and not w.any() and eng.neighbor_count(2) == 0
     eng.close()
 
 

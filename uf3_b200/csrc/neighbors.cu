@@ -46,9 +46,11 @@ __device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
     } while (assumed != old);
 }
 
-// species lookup + bounding box of the real atoms.  bbox must hold (+inf x3, -inf x3) on
+// species lookup for every atom + bounding box of the CENTRES [c_first, c_first + c_count)
+// (all real atoms unless the frame is split over ranks: the grid only has to hold what lies
+// within the search radius of this rank's centres).  bbox must hold (+inf x3, -inf x3) on
 // entry; every block folds its partial box in with six atomics.
-__global__ void __launch_bounds__(1024) k_prepare(int n, const int *__restrict__ z,
+__global__ void __launch_bounds__(1024) k_prepare(int n, int c_first, int c_count, const int *__restrict__ z,
                                                   const int *__restrict__ z_to_spec,
                                                   const double *__restrict__ pos,
                                                   int *__restrict__ spec, double *__restrict__ bbox,
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(1024) k_prepare(int n, const int *__restrict__
         const int s = (zz >= 0 && zz < 128) ? z_to_spec[zz] : -1;
         spec[a] = s < 0 ? 0 : s;
         if (s < 0) bad = 1;
+        if ((unsigned)(a - c_first) >= (unsigned)c_count) continue;
         for (int c = 0; c < 3; ++c) {
             const double v = pos[3 * a + c];
             lo[c] = fmin(lo[c], v);
@@ -570,7 +573,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     static const double bbox_init[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0};
     UF3B_CUDA(cudaMemcpyAsync(nl->misc.p, bbox_init, sizeof bbox_init, cudaMemcpyHostToDevice, stream));
     const int prep_blocks = std::min((n + 1023) / 1024, sm_count());
-    UF3B_LAUNCH(k_prepare, prep_blocks, 1024, 0, stream, n, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
+    UF3B_LAUNCH(k_prepare, prep_blocks, 1024, 0, stream, n, nl->c_first, nl->c_count, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
                 nl->spec.p, nl->misc.p, d_err);
     if (!nl->h_mapped) UF3B_CUDA(cudaHostAlloc((void **)&nl->h_mapped, 16 * sizeof(double), cudaHostAllocMapped));
     double h_misc[7];
@@ -580,6 +583,19 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     int h_err;
     memcpy(&h_err, &h_misc[6], sizeof h_err);
     if (h_err) return fail(UF3B_ERR_ELEMENT, "configuration holds an element outside the basis");
+    if (nl->c_count == 0) {         // a rank without centres: empty rows, nothing to bin
+        UF3B_CUDA(nl->cnt2.reserve((size_t)n + 1));
+        UF3B_CUDA(nl->cnt3.reserve((size_t)n + 1));
+        UF3B_CUDA(cudaMemsetAsync(nl->cnt2.p, 0, sizeof(int) * n, stream));
+        UF3B_CUDA(cudaMemsetAsync(nl->cnt3.p, 0, sizeof(int) * n, stream));
+        UF3B_CUDA(cudaMemsetAsync(nl->off2.p, 0, sizeof(int) * n, stream));
+        UF3B_CUDA(cudaMemsetAsync(nl->off3.p, 0, sizeof(int) * n, stream));
+        if (nl->idx2.cap == 0) UF3B_CUDA(nl->idx2.reserve(64));
+        if (nl->idx3.cap == 0) UF3B_CUDA(nl->idx3.reserve(64));
+        guard.armed = false;
+        *inout = nl;
+        return UF3B_OK;
+    }
     for (int c = 0; c < 6; ++c)
         if (!std::isfinite(h_misc[c])) return fail(UF3B_ERR_INVALID, "non-finite position");
 
