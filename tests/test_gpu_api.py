@@ -233,8 +233,15 @@ def test_forces_are_minus_energy_gradient():
     assert np.abs(forces.sum(axis=0)).max() < 1e-8      # Newton's third law
 
 
-def test_device_gram_equals_host_gram_and_fit():
+@pytest.mark.parametrize("kernels", ["cublas", "own"])
+def test_device_gram_equals_host_gram_and_fit(kernels, monkeypatch):
+    """Both device paths of the normal-equation accumulation (the hand-written k_gram /
+    k_ordinate, and cuBLAS dsyrk + dgemv selected by UF3B_GRAM_KERNEL=cublas) against numpy."""
     import torch
+    if kernels == "cublas":
+        monkeypatch.setenv("UF3B_GRAM_KERNEL", "cublas")
+    else:
+        monkeypatch.delenv("UF3B_GRAM_KERNEL", raising=False)
     case = gu.Case("syn_w128_demo")
     basis = case.basis()
     feat = BasisFeaturizer(basis)
