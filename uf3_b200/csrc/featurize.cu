@@ -738,20 +738,20 @@ __device__ __forceinline__ void plane_three_body(const BasisTab &B, const FrameV
 // 10 KB per atom); the cached leg-grouped path then only loads and densifies records.
 // Layout per centre i: records [0, max3) = legs (i, row entry), then the pair (j < k by row
 // position) at max3 + k (k - 1) / 2 + j, stored from j to k (unit vector j -> k).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_leg_cache(const BasisTab B, const FrameView f, const TileGeom g, int max3, int stride, unsigned char *cache) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_gw = (gridDim.x * blockDim.x) >> 5;
+    // block = one centre, thread = one leg (105 per W atom): the evaluation is a chain of
+    // dependent gathers (list entry -> position -> knots -> piece), so the parallelism has to
+    // come from many short threads rather than from a warp looping over an atom's legs
     int dummy;
-    for (int i = gw; i < f.n; i += n_gw) {
+    for (int i = blockIdx.x; i < f.n; i += gridDim.x) {
         const int row = __ldg(f.off3 + i), ni = __ldg(f.cnt3 + i);
-        const Vec3 pi = real_position(f, i);
         unsigned char *mine = cache + (size_t)i * stride * SPL_REC;
         const int n_legs = ni + ni * (ni - 1) / 2;
-        for (int t = lane; t < n_legs; t += 32) {
+        for (int t = threadIdx.x; t < n_legs; t += blockDim.x) {
             if (t < ni) {
-                eval_sparse_leg<false>(B, 0, pi, super_position(f, __ldg(f.idx3 + row + t), dummy), g.l0,
-                                       mine + (size_t)t * SPL_REC);
+                eval_sparse_leg<false>(B, 0, real_position(f, i), super_position(f, __ldg(f.idx3 + row + t), dummy),
+                                       g.l0, mine + (size_t)t * SPL_REC);
             } else {
                 int qj, qk;
                 unrank_pair(t - ni, qj, qk);
@@ -1636,7 +1636,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                 UF3B_CUDA(cudaEventCreate(&ev1));
                 UF3B_CUDA(cudaEventRecord(ev0, stream));
             }
-            UF3B_LAUNCH(k_leg_cache, std::min((n + 7) / 8, sm_count() * 8), 256, 0, stream, basis->tab, view, tg,
+            UF3B_LAUNCH(k_leg_cache, n, 128, 0, stream, basis->tab, view, tg,
                         tg.cache_max3, tg.cache_stride, basis->leg_cache.p);
             UF3B_LAUNCH(kc, grid, cg.warps * 32, smem_c, stream, basis->tab, view, cg, d_xf, d_ld,
                         basis->partials.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
@@ -1707,7 +1707,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     }
     if (global_acc) UF3B_CUDA(basis->gacc.reserve((size_t)n_gw * 4 * F));
     if (kp == 7)
-        UF3B_LAUNCH(k_leg_cache, std::min((n + 7) / 8, sm_count() * 8), 256, 0, stream, basis->tab, view, tg,
+        UF3B_LAUNCH(k_leg_cache, n, 128, 0, stream, basis->tab, view, tg,
                     tg.cache_max3, tg.cache_stride, basis->leg_cache.p);
     UF3B_LAUNCH(kernel, grid, warps * 32, smem, stream, basis->tab, view, tg, d_xf, d_ld,
                 basis->partials.p, basis->gacc.p, x_energy ? 1 : 0, x_forces ? 1 : 0);
