@@ -248,6 +248,51 @@ def test_headline_frame_10k_atoms_matches_oracle():
     eng.close()
 
 
+def test_headline_frame_10k_atoms_manuscript_basis_matches_oracle():
+    """configs[1] with the 456-column manuscript basis: the cooperative plane kernel + leg cache
+    at full size against the oracle, plus translation invariance and bit reproducibility."""
+    from uf3_b200 import synthetic
+    basis = synthetic.w_basis("manuscript")
+    pos, numbers, cell, pbc = synthetic.bcc_w((10, 20, 25), seed=1)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    packed = orc.PackedBasis(basis)
+    eng = Engine(basis)
+    eng.build_neighbors(pos, numbers, images=images)
+    xe, xf = eng.featurize()
+    want_e, want_f = orc.featurize(packed, pos, numbers, images[1])
+    assert gu.rel_err(xe, want_e) <= REL and gu.rel_err(xf, want_f) <= REL
+    n = len(pos)
+    assert np.abs(xf.reshape(3, n, -1).sum(axis=1)).max() <= 1e-9 * np.abs(xf).max() * n
+    xe2, xf2 = eng.featurize()
+    assert np.array_equal(xe, xe2) and np.array_equal(xf, xf2)
+    eng.close()
+
+
+@pytest.mark.parametrize("kind,a,sigma,expect", [
+    ("demo", 2.45, 0.04, "rows of ~26 entries: leg cache with long rows"),
+    ("manuscript", 2.95, 0.05, "rows of ~26 entries: cooperative kernel with 28-32 record slots"),
+    ("demo", 2.10, 0.03, "rows above 32 entries: per-triangle fallback path"),
+    ("manuscript", 3.165, 0.30, "strongly rattled: ragged rows, legs outside the knot range"),
+])
+def test_dense_and_ragged_lattices_match_oracle(kind, a, sigma, expect):
+    """The kernel paths are chosen from the basis AND from the longest 3-body row of the frame;
+    compressed / strongly rattled lattices walk through the long-row variants and the fallback."""
+    from uf3_b200 import synthetic
+    basis = synthetic.w_basis(kind)
+    pos, numbers, cell, pbc = synthetic.bcc_w((5, 5, 6), a=a, sigma=sigma, seed=12)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    packed = orc.PackedBasis(basis)
+    eng = Engine(basis)
+    eng.build_neighbors(pos, numbers, images=images)
+    off3, _ = eng.neighbor_list(3)
+    longest = int(np.diff(off3).max())
+    assert (longest > 32) == ("above 32" in expect), (longest, expect)
+    xe, xf = eng.featurize()
+    want_e, want_f = orc.featurize(packed, pos, numbers, images[1])
+    assert gu.rel_err(xe, want_e) <= REL and gu.rel_err(xf, want_f) <= REL
+    eng.close()
+
+
 def test_nexe_50k_inference_matches_oracle():
     """configs[2]: Ne/Xe binary, 50 000 atoms, 2-body energy + forces."""
     from uf3_b200 import synthetic
