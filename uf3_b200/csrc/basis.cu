@@ -222,6 +222,8 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     T.pair_col = (const int *)(base + o_pair_col);
     T.pair_lo = (const double *)(base + o_pair_lo);
     T.pair_hi = (const double *)(base + o_pair_hi);
+    b->n_knots2 = (int)knots2.size(); b->n_poly2 = (int)poly2.size();
+    b->n_knots3 = (int)knots3.size(); b->n_poly3 = (int)poly3.size();
     T.knots2 = (const double *)(base + o_knots2);
     T.poly2 = (const double *)(base + o_poly2);
     T.trio_nk = (const int *)(base + o_trio_nk);

@@ -131,6 +131,7 @@ struct uf3b_basis {
     double *c_grid = nullptr;      // [n_bins]
     int n_bins = 0;
     int n_feats = 0;
+    int n_knots2 = 0, n_poly2 = 0, n_knots3 = 0, n_poly3 = 0;   // doubles in the spline tables
     bool has_coeff = false;
     int device = 0;
     std::vector<int> h_trio_goff, h_bin_col, h_trio_col, h_trio_sym, h_trio_dims;   // dims: [3*t + leg]

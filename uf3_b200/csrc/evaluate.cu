@@ -65,16 +65,39 @@ constexpr int EV_WARPS = 4;
 // the analytic form of what the reference obtains by finite differences over strained
 // cells (calculator.py:399-404).  Six per-lane accumulators, written next to the per-warp
 // energies: e_partials[n_gw * (1 + c) + gw], c = xx, yy, zz, yz, xz, xy.
+// Table sizes (doubles) for staging the spline tables in shared memory; 0 = leave in global.
+struct EvalStage { int knots2, poly2, knots3, poly3; };
+
 template <bool NEWTON, bool VIRIAL>
 __global__ void __launch_bounds__(EV_WARPS * 32, 4)
-k_energy_forces(const BasisTab B, const FrameView f, double *forces,
-                double *__restrict__ e_partials, int want_e_, int want_f_, int n_grid, int grid_in_smem) {
+k_energy_forces(const BasisTab B_, const FrameView f, double *forces,
+                double *__restrict__ e_partials, int want_e_, int want_f_, int n_grid, int grid_in_smem,
+                const EvalStage st) {
     __shared__ RoleViews s_views[EV_WARPS];
+    __shared__ double4 s_nbr[EV_WARPS * 32];
     extern __shared__ __align__(16) double s_grid[];
-    if (grid_in_smem) {
-        for (int k = threadIdx.x; k < n_grid; k += blockDim.x) s_grid[k] = B.c_grid[k];
-        __syncthreads();
+    // knots and polynomial pieces are read ~14 times per leg: staged in shared memory next to
+    // the coefficient grids (the capture of the global-table version showed long-scoreboard
+    // stalls of 7.7 cycles per issued instruction; most of the rest is the position gathers)
+    BasisTab B = B_;
+    {
+        double *dst = s_grid + (grid_in_smem ? ((n_grid + 1) & ~1) : 0);
+        if (st.knots2 > 0) {
+            for (int k = threadIdx.x; k < st.knots2; k += blockDim.x) dst[k] = B_.knots2[k];
+            B.knots2 = dst; dst += (st.knots2 + 1) & ~1;
+            for (int k = threadIdx.x; k < st.poly2; k += blockDim.x) dst[k] = B_.poly2[k];
+            B.poly2 = dst; dst += (st.poly2 + 1) & ~1;
+        }
+        if (st.knots3 > 0) {
+            for (int k = threadIdx.x; k < st.knots3; k += blockDim.x) dst[k] = B_.knots3[k];
+            B.knots3 = dst; dst += (st.knots3 + 1) & ~1;
+            for (int k = threadIdx.x; k < st.poly3; k += blockDim.x) dst[k] = B_.poly3[k];
+            B.poly3 = dst; dst += (st.poly3 + 1) & ~1;
+        }
     }
+    if (grid_in_smem)
+        for (int k = threadIdx.x; k < n_grid; k += blockDim.x) s_grid[k] = B.c_grid[k];
+    __syncthreads();
     const double *c_grid = grid_in_smem ? s_grid : B.c_grid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * EV_WARPS + warp, n_gw = gridDim.x * EV_WARPS;
@@ -102,7 +125,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
             const double d = dist_rn(pa, pj);
             const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
             double v[4], dv[4];
-            const int idx = eval_leg(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
+            const int idx = eval_leg<false>(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
                                      B.poly2 + __ldg(B.pair_poff + pr), d, 0, 0, v, dv);
             if (idx < 0) continue;
             const double *c = B.coeff + __ldg(B.pair_col + pr) + idx;
@@ -125,12 +148,31 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
         if (B.n_trios > 0) {
             const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
             const int n_tri = n3a * (n3a - 1) / 2;
+            // the centre's neighbours (position, parent atom, species) once per centre in a
+            // per-warp table: a triangle then reads two entries instead of gathering two list
+            // entries, two positions and two image offsets from global memory
+            const bool staged = n3a <= 32;
+            double4 *nb = s_nbr + warp * 32;
+            if (staged && lane < n3a) {
+                int aj;
+                const Vec3 pj = super_position(f, __ldg(f.idx3 + row0 + lane), aj);
+                nb[lane] = make_double4(pj.x, pj.y, pj.z,
+                                        __longlong_as_double(((long long)__ldg(f.spec + aj) << 32) | (unsigned)aj));
+            }
+            __syncwarp();
             for (int t = lane; t < n_tri; t += 32) {
                 int qj, qk;
                 unrank_pair(t, qj, qk);
                 Triangle T;
-                if (!eval_triangle(B, f, pa, sa, __ldg(f.idx3 + row0 + qj), __ldg(f.idx3 + row0 + qk), 0,
-                                   0, 0, T))
+                if (staged) {
+                    const double4 ej = nb[qj], ek = nb[qk];
+                    const long long tj = __double_as_longlong(ej.w), tk = __double_as_longlong(ek.w);
+                    const Vec3 pj = {ej.x, ej.y, ej.z}, pk = {ek.x, ek.y, ek.z};
+                    if (!eval_triangle_at<false>(B, pa, sa, pj, (int)(tj & 0xffffffff), (int)(tj >> 32), pk,
+                                                 (int)(tk & 0xffffffff), (int)(tk >> 32), 0, 0, 0, T))
+                        continue;
+                } else if (!eval_triangle<false>(B, f, pa, sa, __ldg(f.idx3 + row0 + qj), __ldg(f.idx3 + row0 + qk), 0,
+                                                 0, 0, T))
                     continue;
                 double val, gl, gm, gn;
                 contract(c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
@@ -166,7 +208,7 @@ k_energy_forces(const BasisTab B, const FrameView f, double *forces,
                         if (mk == apr) continue;
                         const bool first = apr < mk;
                         Triangle T;
-                        if (!eval_triangle(B, f, real_position(f, ci), __ldg(f.spec + ci), first ? apr : mk,
+                        if (!eval_triangle<false>(B, f, real_position(f, ci), __ldg(f.spec + ci), first ? apr : mk,
                                            first ? mk : apr, first ? 1 : 2, 0, 0, T))
                             continue;
                         double val, gl, gm, gn;
@@ -259,7 +301,17 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     const int n_grid = basis->n_bins;
     const size_t grid_bytes = sizeof(double) * (size_t)n_grid;
     const int grid_in_smem = (n_grid > 0 && grid_bytes <= 48 * 1024) ? 1 : 0;
-    const size_t smem = grid_in_smem ? grid_bytes : 0;
+    size_t smem = grid_in_smem ? sizeof(double) * (size_t)((n_grid + 1) & ~1) : 0;
+    EvalStage st = {0, 0, 0, 0};
+    {   // spline tables next to the coefficient grids while the block stays under 56 KB
+        const size_t pair_b = sizeof(double) * (size_t)(((basis->n_knots2 + 1) & ~1) + ((basis->n_poly2 + 1) & ~1));
+        const size_t trio_b = sizeof(double) * (size_t)(((basis->n_knots3 + 1) & ~1) + ((basis->n_poly3 + 1) & ~1));
+        if (smem + pair_b <= 56 * 1024) { st.knots2 = basis->n_knots2; st.poly2 = basis->n_poly2; smem += pair_b; }
+        if (basis->tab.n_trios > 0 && smem + trio_b <= 56 * 1024) {
+            st.knots3 = basis->n_knots3; st.poly3 = basis->n_poly3; smem += trio_b;
+        }
+    }
+    if (smem > 48 * 1024) UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EV_WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
@@ -289,7 +341,7 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     }
     if (newton && forces) UF3B_CUDA(cudaMemsetAsync(d_f, 0, sizeof(double) * 3 * (size_t)n, stream));
     UF3B_LAUNCH(kernel, grid, EV_WARPS * 32, smem, stream, basis->tab, view, d_f,
-                basis->partials.p, energy ? 1 : 0, forces ? 1 : 0, n_grid, grid_in_smem);
+                basis->partials.p, energy ? 1 : 0, forces ? 1 : 0, n_grid, grid_in_smem, st);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (energy || virial)
         UF3B_LAUNCH(k_energy_sum, virial ? 7 : 1, 256, 0, stream, basis->partials.p, n_gw, d_e);

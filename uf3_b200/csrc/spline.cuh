@@ -39,12 +39,15 @@ UF3B_HD int find_interval(const double *t, int nk, double scale, double r) {
 
 // Values and first derivatives of basis functions i-3..i at r (piece = poly + 16*(i-3)).
 // Pieces are 32-byte aligned (16 doubles each in a 32-byte aligned table).
+// NC: read through the non-coherent global path (__ldg); false for tables staged in shared memory.
+template <bool NC = true>
 UF3B_HD void eval_piece(const double *piece, double u, double v[4], double dv[4]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #if defined(__CUDA_ARCH__)
-        const double2 lo = __ldg(reinterpret_cast<const double2 *>(piece) + 2 * q);
-        const double2 hi = __ldg(reinterpret_cast<const double2 *>(piece) + 2 * q + 1);
+        const double2 *p2 = reinterpret_cast<const double2 *>(piece) + 2 * q;
+        const double2 lo = NC ? __ldg(p2) : p2[0];
+        const double2 hi = NC ? __ldg(p2 + 1) : p2[1];
         const double c0 = lo.x, c1 = lo.y, c2 = hi.x, c3 = hi.y;
 #else
         const double c0 = piece[4 * q + 0], c1 = piece[4 * q + 1];
@@ -57,11 +60,12 @@ UF3B_HD void eval_piece(const double *piece, double u, double v[4], double dv[4]
 
 // Full leg evaluation with trims (angles.py:554-565, bspline.py:840): returns the
 // first basis index or -1; basis indices outside [n_lead, n_basis - n_trail) give 0.
+template <bool NC = true>
 UF3B_HD int eval_leg(const double *t, int nk, double scale, const double *poly, double r, int n_lead,
                      int n_trail, double v[4], double dv[4]) {
     const int i = find_interval(t, nk, scale, r);
     if (i < 0) return -1;
-    eval_piece(poly + 16 * (i - 3), r - t[i], v, dv);
+    eval_piece<NC>(poly + 16 * (i - 3), r - t[i], v, dv);
     const int idx = i - 3, nb = nk - 4;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

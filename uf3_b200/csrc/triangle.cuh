@@ -33,13 +33,13 @@ struct Triangle {
 // role: 0 = `a` is the centre, 1 = `a` is the neighbour with supercell index mj,
 // 2 = `a` is the neighbour with index mk (mj < mk).  Returns false when the triangle
 // contributes nothing.
-__device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView &f, const Vec3 &pc,
-                                              int sc, int mj, int mk, int role, int n_lead,
-                                              int n_trail, Triangle &T) {
-    int aj, ak;
-    Vec3 pj = super_position(f, mj, aj), pk = super_position(f, mk, ak);
+// Same with the two neighbours given by position, parent atom and species (mj < mk by
+// supercell index, as in the centre's sorted list).
+template <bool NC = true>
+__device__ __forceinline__ bool eval_triangle_at(const BasisTab &B, const Vec3 &pc, int sc, Vec3 pj, int aj,
+                                                 int sj, Vec3 pk, int ak, int sk, int role, int n_lead,
+                                                 int n_trail, Triangle &T) {
     double dij = dist_rn(pc, pj), dik = dist_rn(pc, pk);
-    int sj = __ldg(f.spec + aj), sk = __ldg(f.spec + ak);
     if (sj > sk) {                              // angles.py:482-488 (stable by atomic number)
         Vec3 tp = pj; pj = pk; pk = tp;
         double td = dij; dij = dik; dik = td;
@@ -57,9 +57,9 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
     if (!(dij >= tl[0] && dij <= tl[nkl - 1])) return false;      // angles.py:502-508
     if (!(dik >= tm[0] && dik <= tm[nkm - 1])) return false;
     if (!(djk >= tn[0] && djk <= tn[nkn - 1])) return false;
-    T.il = eval_leg(tl, nkl, __ldg(B.trio_scale + 3 * t), B.poly3 + __ldg(B.trio_poff + 3 * t), dij, n_lead, n_trail, T.v[0], T.dv[0]);
-    T.im = eval_leg(tm, nkm, __ldg(B.trio_scale + 3 * t + 1), B.poly3 + __ldg(B.trio_poff + 3 * t + 1), dik, n_lead, n_trail, T.v[1], T.dv[1]);
-    T.in = eval_leg(tn, nkn, __ldg(B.trio_scale + 3 * t + 2), B.poly3 + __ldg(B.trio_poff + 3 * t + 2), djk, n_lead, n_trail, T.v[2], T.dv[2]);
+    T.il = eval_leg<NC>(tl, nkl, __ldg(B.trio_scale + 3 * t), B.poly3 + __ldg(B.trio_poff + 3 * t), dij, n_lead, n_trail, T.v[0], T.dv[0]);
+    T.im = eval_leg<NC>(tm, nkm, __ldg(B.trio_scale + 3 * t + 1), B.poly3 + __ldg(B.trio_poff + 3 * t + 1), dik, n_lead, n_trail, T.v[1], T.dv[1]);
+    T.in = eval_leg<NC>(tn, nkn, __ldg(B.trio_scale + 3 * t + 2), B.poly3 + __ldg(B.trio_poff + 3 * t + 2), djk, n_lead, n_trail, T.v[2], T.dv[2]);
     if (T.il < 0 || T.im < 0 || T.in < 0) return false;           // r exactly on the first knot
     T.trio = t;
     T.dim_m = nkm - 4;
@@ -91,6 +91,16 @@ __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView
         T.C[c] = role == 0 ? 0.0 : (role == 1 ? ujk[c] : -ujk[c]);
     }
     return true;
+}
+
+template <bool NC = true>
+__device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView &f, const Vec3 &pc,
+                                              int sc, int mj, int mk, int role, int n_lead,
+                                              int n_trail, Triangle &T) {
+    int aj, ak;
+    const Vec3 pj = super_position(f, mj, aj), pk = super_position(f, mk, ak);
+    return eval_triangle_at<NC>(B, pc, sc, pj, aj, __ldg(f.spec + aj), pk, ak, __ldg(f.spec + ak), role, n_lead,
+                                n_trail, T);
 }
 
 // t in [0, n(n-1)/2)  ->  (qj < qk), enumerated qk-major.
