@@ -1140,30 +1140,6 @@ struct CoopGeom {
     int plane_bytes;        // of one plane array
 };
 
-// n leg record for the cooperative kernel (96 B): v[4] dv[4] {idx - x0 bits, wx} {wy, wz}
-__device__ __forceinline__ void eval_n_leg(const BasisTab &B, const Vec3 &from, const Vec3 &to, int x0,
-                                           unsigned char *out) {
-    double v[4] = {0.0, 0.0, 0.0, 0.0}, dv[4] = {0.0, 0.0, 0.0, 0.0};
-    const double d = dist_rn(from, to);
-    const int nk = __ldg(B.trio_nk + 2);
-    const double *t = B.knots3 + __ldg(B.trio_koff + 2);
-    double inv = 0.0;
-    int rel = SP_DEAD;
-    if (d >= t[0] && d <= t[nk - 1]) {
-        const int idx = eval_leg(t, nk, __ldg(B.trio_scale + 2), B.poly3 + __ldg(B.trio_poff + 2), d,
-                                 B.lead3, B.trail3, v, dv);
-        if (idx >= 0) rel = idx - x0;
-        inv = fast_rcp(d);
-    }
-    double2 *o = reinterpret_cast<double2 *>(out);
-    o[0] = make_double2(v[0], v[1]);
-    o[1] = make_double2(v[2], v[3]);
-    o[2] = make_double2(dv[0], dv[1]);
-    o[3] = make_double2(dv[2], dv[3]);
-    o[4] = make_double2(__longlong_as_double((long long)(unsigned)rel), (to.x - from.x) * inv);
-    o[5] = make_double2((to.y - from.y) * inv, (to.z - from.z) * inv);
-}
-
 // Publish the group's own leg (sparse record `src`) densely for the consumers.
 __device__ __forceinline__ void publish_group_leg(unsigned src, unsigned dst, int role, int lane) {
     const int rel = lds32(src + SPL_IDX);
