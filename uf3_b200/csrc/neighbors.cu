@@ -10,6 +10,7 @@
 // produced per centre, both sorted by supercell index (image_rank * n_atoms + atom):
 //   list 2:  max(r_min,0) < d < r_max  of the pair's own bounds    (distances.py:60-66)
 //   list 3:  r3min < d <= r3max                                      (angles.py:340)
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -313,6 +314,8 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 }
 
 constexpr int NL_BUF2 = 160, NL_BUF3 = 96;     // hits buffered per centre before the row is placed
+constexpr int NL_REGIONS = 128;                // independent claim regions per list
+constexpr int NL_PAIRS = 36;                   // pair bounds staged in shared memory (up to 8 elements)
 
 // Block = one cell, warp = one real centre of that cell.  The slots of the 3x3x3 block of
 // cells around it are 9 contiguous z-runs in the binned array; one thread stages them into
@@ -322,17 +325,24 @@ constexpr int NL_BUF2 = 160, NL_BUF3 = 96;     // hits buffered per centre befor
 // per list, and the row is written sorted by supercell index.  Rows are contiguous but
 // appear in claim order: the lists are (start, count) per centre.  If the arrays are too
 // small the claims still count, `status[2]` is raised and the host grows them and reruns.
-//   status: [0] entries claimed in list 2, [1] in list 3, [2] overflow, [3] longest list-3 row
+// Claims go to NL_REGIONS independent regions of the index arrays (region = block % NL_REGIONS,
+// one counter each): with a single counter per list the 10^5 same-address atomics of a frame
+// serialised in the L2 and the warps spent 41 % of the kernel waiting for their claim.
+//   claims: [r] entries claimed in region r of list 2, [NL_REGIONS + r] of list 3
+//   status: [2] overflow, [3] longest list-3 row   ([0], [1], [4], [5] are filled by
+//           k_post_status: totals of both lists and the fullest region of each)
 __global__ void __launch_bounds__(NL_WARPS * 32)
 k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots,
             const int *__restrict__ cell_start, int c_first, int c_count, int *__restrict__ off2,
             int *__restrict__ cnt2, int *__restrict__ off3, int *__restrict__ cnt3,
             int *__restrict__ idx2, int *__restrict__ idx3, int *__restrict__ scratch2,
-            int *__restrict__ scratch3, int cap2, int cap3, int *__restrict__ status) {
+            int *__restrict__ scratch3, int cap2, int cap3, int *__restrict__ status,
+            int *__restrict__ claims) {
     __shared__ __align__(128) Slot tile[NL_TILE];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int run_lo[9], run_n[9], n_cand;
     __shared__ int hit2[NL_WARPS][NL_BUF2], hit3[NL_WARPS][NL_BUF3];
+    __shared__ double s_lo[NL_PAIRS], s_hi[NL_PAIRS];     // strict pair bounds (global beyond NL_PAIRS)
     const int cell = blockIdx.x;
     const int s0 = cell_start[cell], s1 = cell_start[cell + 1];
     if (s0 == s1) return;
@@ -342,6 +352,10 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
     for (int s = s0 + (int)threadIdx.x; s < s1; s += NL_WARPS * 32) real_here |= (unsigned)(slots[s].m - c_first) < (unsigned)c_count;
     if (!__syncthreads_or(real_here)) return;
 
+    const bool bounds_staged = B.n_pairs <= NL_PAIRS;
+    if (bounds_staged)
+        for (int p = threadIdx.x; p < B.n_pairs; p += NL_WARPS * 32) { s_lo[p] = B.pair_lo[p]; s_hi[p] = B.pair_hi[p]; }
+    const double *pair_lo = bounds_staged ? s_lo : B.pair_lo, *pair_hi = bounds_staged ? s_hi : B.pair_hi;
     const int cz = cell % G.nz, cy = (cell / G.nz) % G.ny, cx = cell / (G.nz * G.ny);
     if (threadIdx.x == 0) {
         int total = 0, k = 0;
@@ -380,6 +394,7 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
 
     const unsigned lt = (1u << lane) - 1u;
     const bool has3 = B.n_trios > 0;
+    const int region = cell % NL_REGIONS;
     for (int s = s0 + warp; s < s1; s += NL_WARPS) {
         const Slot c = slots[s];
         if ((unsigned)(c.m - c_first) >= (unsigned)c_count) continue;   // ghosts (and real atoms of
@@ -401,7 +416,7 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
                         const Vec3 pt = {t.x, t.y, t.z};
                         const double d = dist_rn(pc, pt);
                         const int p = pair_index(B.ne, c.spec, t.spec);
-                        k2 = d > B.pair_lo[p] && d < B.pair_hi[p];
+                        k2 = d > pair_lo[p] && d < pair_hi[p];
                         k3 = has3 && d > B.r3min && d <= B.r3max;
                         m = t.m;
                     }
@@ -426,13 +441,15 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
             if (pass == 1) break;
             // claim the rows
             if (lane == 0) {
-                base2 = atomicAdd(status + 0, n2);
-                base3 = atomicAdd(status + 1, n3);
+                base2 = atomicAdd(claims + region, n2);
+                base3 = atomicAdd(claims + NL_REGIONS + region, n3);
                 atomicMax(status + 3, n3);
             }
             base2 = __shfl_sync(FULL, base2, 0);
             base3 = __shfl_sync(FULL, base3, 0);
-            placed = base2 + n2 <= cap2 && base3 + n3 <= cap3;
+            placed = base2 + n2 <= cap2 && base3 + n3 <= cap3;     // cap: entries per region
+            base2 += region * cap2;
+            base3 += region * cap3;
             if (!placed && lane == 0) status[2] = 1;
             fits = n2 <= NL_BUF2 && n3 <= NL_BUF3;
             if (fits || !placed) break;
@@ -497,6 +514,31 @@ __global__ void k_post_small(const double *__restrict__ src, volatile double *ds
     __threadfence_system();
 }
 
+// totals and fullest region of both lists -> status[0], [1], [4], [5]; status -> mapped host memory
+__global__ void k_post_status(const int *__restrict__ claims, int *__restrict__ status, volatile int *dst) {
+    const int lane = threadIdx.x;
+    long long t2 = 0, t3 = 0;
+    int m2 = 0, m3 = 0;
+    for (int r = lane; r < NL_REGIONS; r += 32) {
+        const int a = claims[r], b = claims[NL_REGIONS + r];
+        t2 += a; t3 += b;
+        m2 = max(m2, a); m3 = max(m3, b);
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        t2 += __shfl_xor_sync(FULL, t2, s); t3 += __shfl_xor_sync(FULL, t3, s);
+        m2 = max(m2, __shfl_xor_sync(FULL, m2, s)); m3 = max(m3, __shfl_xor_sync(FULL, m3, s));
+    }
+    if (lane == 0) {
+        status[0] = t2 > INT32_MAX ? -1 : (int)t2;
+        status[1] = t3 > INT32_MAX ? -1 : (int)t3;
+        status[4] = m2;
+        status[5] = m3;
+    }
+    __syncwarp();
+    if (lane < 6) dst[lane] = status[lane];
+    __threadfence_system();
+}
+
 extern "C" {
 
 int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *positions,
@@ -554,7 +596,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     UF3B_CUDA(nl->img_inv.reserve(n_images));
     UF3B_CUDA(nl->off2.reserve((size_t)n + 1));
     UF3B_CUDA(nl->off3.reserve((size_t)n + 1));
-    UF3B_CUDA(nl->totals.reserve(8));
+    UF3B_CUDA(nl->totals.reserve(8 + NL_REGIONS));      // [0] scan total, [1..4] status (8 ints), [8..] claims
     UF3B_CUDA(cudaMemcpyAsync(nl->img_off.p, image_offsets, sizeof(double) * 3 * n_images, cudaMemcpyDefault, stream));
     UF3B_CUDA(cudaMemcpyAsync(nl->img_inv.p, inv.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, stream));
     if (n == 0) {
@@ -631,8 +673,9 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
                 nl->spec.p, nl->cell_of.p, nl->cell_start.p, nl->cell_cursor.p, nl->slots.p);
 
     // one pass; the index arrays keep their capacity from earlier builds (first guess below)
-    int *status = (int *)(nl->totals.p + 1);        // 4 ints
-    int h_status[4];
+    int *status = (int *)(nl->totals.p + 1);        // 8 ints
+    int *claims = (int *)(nl->totals.p + 8);        // 2 * NL_REGIONS ints
+    int h_status[6];
     UF3B_CUDA(nl->cnt2.reserve((size_t)n + 1));
     UF3B_CUDA(nl->cnt3.reserve((size_t)n + 1));
     if (nl->idx2.cap == 0) UF3B_CUDA(nl->idx2.reserve((size_t)n * 80 + 1024));
@@ -641,27 +684,29 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     for (int attempt = 0; attempt < 2; ++attempt) {
         UF3B_CUDA(nl->scratch2.reserve(nl->idx2.cap));
         UF3B_CUDA(nl->scratch3.reserve(nl->idx3.cap));
-        UF3B_CUDA(cudaMemsetAsync(status, 0, sizeof h_status, stream));
+        UF3B_CUDA(cudaMemsetAsync(status, 0, 8 * sizeof(int), stream));
+        UF3B_CUDA(cudaMemsetAsync(claims, 0, 2 * NL_REGIONS * sizeof(int), stream));
         if (nl->c_count < n) {      // rows of the atoms other ranks own stay empty
             UF3B_CUDA(cudaMemsetAsync(nl->cnt2.p, 0, sizeof(int) * n, stream));
             UF3B_CUDA(cudaMemsetAsync(nl->cnt3.p, 0, sizeof(int) * n, stream));
             UF3B_CUDA(cudaMemsetAsync(nl->off2.p, 0, sizeof(int) * n, stream));
             UF3B_CUDA(cudaMemsetAsync(nl->off3.p, 0, sizeof(int) * n, stream));
         }
-        const int cap2 = (int)std::min<size_t>(nl->idx2.cap, (size_t)INT32_MAX);
-        const int cap3 = (int)std::min<size_t>(nl->idx3.cap, (size_t)INT32_MAX);
+        const int cap2 = (int)(std::min<size_t>(nl->idx2.cap, (size_t)INT32_MAX) / NL_REGIONS);
+        const int cap3 = (int)(std::min<size_t>(nl->idx3.cap, (size_t)INT32_MAX) / NL_REGIONS);
         UF3B_LAUNCH(k_neighbors, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G, nl->slots.p,
                     nl->cell_start.p, nl->c_first, nl->c_count, nl->off2.p, nl->cnt2.p, nl->off3.p, nl->cnt3.p, nl->idx2.p,
-                    nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status);
-        UF3B_LAUNCH(k_post_small, 1, 32, 0, stream, (const double *)status, nl->h_mapped + 8, 2);
+                    nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status, claims);
+        UF3B_LAUNCH(k_post_status, 1, 32, 0, stream, claims, status, (volatile int *)(nl->h_mapped + 8));
         UF3B_CUDA(cudaStreamSynchronize(stream));
         memcpy(h_status, nl->h_mapped + 8, sizeof h_status);
         if (h_status[0] < 0 || h_status[1] < 0)
             return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
         if (!h_status[2]) break;
         if (attempt == 1) return fail(UF3B_ERR_CAPACITY, "neighbour list did not fit after regrowth");
-        UF3B_CUDA(nl->idx2.reserve((size_t)h_status[0] + 1));     // reserve() adds 25 % headroom
-        UF3B_CUDA(nl->idx3.reserve((size_t)h_status[1] + 1));
+        // every region must hold the fullest one; reserve() adds 25 % headroom
+        UF3B_CUDA(nl->idx2.reserve((size_t)(h_status[4] + 1) * NL_REGIONS));
+        UF3B_CUDA(nl->idx3.reserve((size_t)(h_status[5] + 1) * NL_REGIONS));
     }
     nl->total2 = h_status[0];
     nl->total3 = h_status[1];
@@ -681,7 +726,7 @@ int uf3b_neighbors_export(const uf3b_nlist *nl, int which, int64_t *offsets, int
     if (!nl || !offsets || (which != 2 && which != 3)) return fail(UF3B_ERR_INVALID, "bad argument");
     const int64_t total = which == 2 ? nl->total2 : nl->total3;
     const size_t n = (size_t)nl->n;
-    std::vector<int> start(n), count(n), idx((size_t)total);
+    std::vector<int> start(n), count(n), idx;
     UF3B_CUDA(cudaDeviceSynchronize());
     if (n) {
         UF3B_CUDA(cudaMemcpy(start.data(), which == 2 ? nl->off2.p : nl->off3.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
@@ -689,7 +734,10 @@ int uf3b_neighbors_export(const uf3b_nlist *nl, int which, int64_t *offsets, int
     }
     if (total) {
         if (!supercell_index) return fail(UF3B_ERR_INVALID, "null index buffer");
-        UF3B_CUDA(cudaMemcpy(idx.data(), which == 2 ? nl->idx2.p : nl->idx3.p, sizeof(int) * idx.size(), cudaMemcpyDeviceToHost));
+        size_t extent = 0;          // rows are spread over the claim regions of the index array
+        for (size_t a = 0; a < n; ++a) extent = std::max(extent, (size_t)start[a] + (size_t)count[a]);
+        idx.resize(extent);
+        UF3B_CUDA(cudaMemcpy(idx.data(), which == 2 ? nl->idx2.p : nl->idx3.p, sizeof(int) * extent, cudaMemcpyDeviceToHost));
     }
     // rows live in claim order on the device; the export is the standard CSR by atom
     int64_t run = 0;
