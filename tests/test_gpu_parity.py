@@ -196,6 +196,33 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
         assert gu.rel_err(outs[other][0], outs[2][0]) <= 1e-11
 
 
+def test_grid_reuse_between_builds_keeps_the_lists_exact():
+    """Consecutive builds on one handle reuse the cell grid while the atoms stay within its
+    skin (MD steps) and fall back to a fresh grid when they leave it; the lists stay the
+    oracle's either way, also for a different atom count or image table on the same handle."""
+    case = gu.Case("syn_w128_demo")
+    basis = case.basis()
+    packed = orc.PackedBasis(basis)
+    images = geometry.image_table(case.cell, case.pbc, basis.r_cut)
+    eng = Engine(basis)
+    rng = np.random.default_rng(4)
+    pos = case.positions.copy()
+    for shift in (0.0, 0.05, 0.2, 0.6, 3.0, 0.1, -7.5):
+        pos = pos + rng.normal(0, 0.02, pos.shape) + shift
+        eng.build_neighbors(pos, case.numbers, images=images)
+        for which in (2, 3):
+            off, idx = eng.neighbor_list(which)
+            want_off, want_idx = orc.neighbor_lists(packed, pos, case.numbers, images[1], which)
+            assert np.array_equal(off, want_off) and np.array_equal(idx, want_idx), (shift, which)
+    small = gu.Case("syn_w16_demo")
+    images16 = geometry.image_table(small.cell, small.pbc, basis.r_cut)
+    eng.build_neighbors(small.positions, small.numbers, images=images16)
+    off, idx = eng.neighbor_list(3)
+    want_off, want_idx = orc.neighbor_lists(packed, small.positions, small.numbers, images16[1], 3)
+    assert np.array_equal(off, want_off) and np.array_equal(idx, want_idx)
+    eng.close()
+
+
 def test_empty_and_single_atom():
     basis = gu.Case("syn_w16_demo").basis()
     eng = Engine(basis)

@@ -157,6 +157,16 @@ struct uf3b_nlist {
     // they never queue behind a large device->host row copy on the copy engine
     double *h_mapped = nullptr;
     ~uf3b_nlist() { if (h_mapped) cudaFreeHost(h_mapped); }
+    // cell grid of the last build, reusable while the centres stay within `grid_skin` of the
+    // box it was sized for (MD: one host synchronisation per build instead of two)
+    bool grid_valid = false;
+    double grid_par[7] = {0, 0, 0, 0, 0, 0, 0};   // ox oy oz hx hy hz edge
+    int grid_dim[3] = {0, 0, 0};
+    double grid_box[6] = {0, 0, 0, 0, 0, 0};      // bounding box of the centres it was built for
+    long long grid_n = -1;
+    double grid_rsearch = 0.0;
+    int grid_cfirst = 0, grid_ccount = 0;
+    std::vector<double> grid_imgoff;
     uf3b::DevBuf<double> pos, img_off;
     uf3b::DevBuf<int> z, spec, img_inv;
     uf3b::DevBuf<int> off2, off3, cnt2, cnt3, idx2, idx3, scratch2, scratch3;

@@ -12,6 +12,7 @@
 //   list 3:  r3min < d <= r3max                                      (angles.py:340)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -515,8 +516,24 @@ __global__ void k_post_small(const double *__restrict__ src, volatile double *ds
 }
 
 // totals and fullest region of both lists -> status[0], [1], [4], [5]; status -> mapped host memory
-__global__ void k_post_status(const int *__restrict__ claims, int *__restrict__ status, volatile int *dst) {
+// status[6]: the centres left the box (+ skin) the reused grid was sized for; status[7]: element /
+// position error flags of k_prepare (only checked here when the grid was reused)
+struct BoxCheck { int active; double lo[3], hi[3], skin; };
+
+__global__ void k_post_status(const int *__restrict__ claims, int *__restrict__ status, volatile int *dst,
+                              const double *__restrict__ misc, const BoxCheck chk) {
     const int lane = threadIdx.x;
+    if (chk.active && lane == 0) {
+        int stale = 0, bad = ((const int *)(misc + 6))[0] ? 1 : 0;
+        for (int c = 0; c < 3; ++c) {
+            const double lo = misc[c], hi = misc[3 + c];
+            if (!(lo >= chk.lo[c] - chk.skin) || !(hi <= chk.hi[c] + chk.skin)) stale = 1;
+            if (!isfinite(lo) || !isfinite(hi)) bad |= 2;
+        }
+        status[6] = stale;
+        status[7] = bad;
+    }
+    __syncwarp();
     long long t2 = 0, t3 = 0;
     int m2 = 0, m3 = 0;
     for (int r = lane; r < NL_REGIONS; r += 32) {
@@ -535,7 +552,7 @@ __global__ void k_post_status(const int *__restrict__ claims, int *__restrict__ 
         status[5] = m3;
     }
     __syncwarp();
-    if (lane < 6) dst[lane] = status[lane];
+    if (lane < 8) dst[lane] = status[lane];
     __threadfence_system();
 }
 
@@ -618,12 +635,25 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     UF3B_LAUNCH(k_prepare, prep_blocks, 1024, 0, stream, n, nl->c_first, nl->c_count, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
                 nl->spec.p, nl->misc.p, d_err);
     if (!nl->h_mapped) UF3B_CUDA(cudaHostAlloc((void **)&nl->h_mapped, 16 * sizeof(double), cudaHostAllocMapped));
-    double h_misc[7];
-    UF3B_LAUNCH(k_post_small, 1, 32, 0, stream, nl->misc.p, nl->h_mapped, 7);
-    UF3B_CUDA(cudaStreamSynchronize(stream));
-    memcpy(h_misc, nl->h_mapped, sizeof h_misc);
-    int h_err;
-    memcpy(&h_err, &h_misc[6], sizeof h_err);
+    // reuse the previous build's grid (no bounding-box read-back) when the problem is the same
+    // and — checked on the device, read back with the list totals — the centres moved less
+    // than the skin it was padded with
+    const double grid_skin = 1.0;
+    static const bool no_reuse = getenv("UF3B_NO_GRID_REUSE") != nullptr;
+    const bool reuse = !no_reuse && nl->grid_valid && nl->grid_n == n_atoms && nl->c_count > 0
+                       && nl->grid_rsearch == basis->tab.r_search
+                       && nl->grid_cfirst == nl->c_first && nl->grid_ccount == nl->c_count
+                       && nl->grid_imgoff.size() == 3 * (size_t)n_images && !is_device_pointer(image_offsets)
+                       && memcmp(nl->grid_imgoff.data(), image_offsets, sizeof(double) * 3 * n_images) == 0;
+    double h_misc[7] = {0, 0, 0, 0, 0, 0, 0};
+    int h_err = 0;
+    if (!reuse) {
+        UF3B_LAUNCH(k_post_small, 1, 32, 0, stream, nl->misc.p, nl->h_mapped, 7);
+        UF3B_CUDA(cudaStreamSynchronize(stream));
+        memcpy(h_misc, nl->h_mapped, sizeof h_misc);
+        memcpy(&h_err, &h_misc[6], sizeof h_err);
+    }
+    nl->grid_valid = false;
     if (h_err) return fail(UF3B_ERR_ELEMENT, "configuration holds an element outside the basis");
     if (nl->c_count == 0) {         // a rank without centres: empty rows, nothing to bin
         UF3B_CUDA(nl->cnt2.reserve((size_t)n + 1));
@@ -638,25 +668,46 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
         *inout = nl;
         return UF3B_OK;
     }
-    for (int c = 0; c < 6; ++c)
-        if (!std::isfinite(h_misc[c])) return fail(UF3B_ERR_INVALID, "non-finite position");
-
-    // grid over the bounding box of the real atoms padded by the search radius
     GridParams G;
-    const double pad = basis->tab.r_search * (1.0 + 1e-9);
-    G.edge = pad;
-    G.ox = h_misc[0] - pad; G.oy = h_misc[1] - pad; G.oz = h_misc[2] - pad;
-    G.hx = h_misc[3] + pad; G.hy = h_misc[4] + pad; G.hz = h_misc[5] + pad;
     long long n_cell;
-    const long long cell_cap = std::max<long long>(1 << 22, 8 * n_sup);
-    for (;;) {
-        G.nx = (int)std::floor((G.hx - G.ox) / G.edge) + 1;
-        G.ny = (int)std::floor((G.hy - G.oy) / G.edge) + 1;
-        G.nz = (int)std::floor((G.hz - G.oz) / G.edge) + 1;
+    if (reuse) {
+        G.ox = nl->grid_par[0]; G.oy = nl->grid_par[1]; G.oz = nl->grid_par[2];
+        G.hx = nl->grid_par[3]; G.hy = nl->grid_par[4]; G.hz = nl->grid_par[5];
+        G.edge = nl->grid_par[6];
+        G.nx = nl->grid_dim[0]; G.ny = nl->grid_dim[1]; G.nz = nl->grid_dim[2];
         n_cell = (long long)G.nx * G.ny * G.nz;
-        if (n_cell <= cell_cap) break;
-        G.edge *= 1.26;     // very sparse configuration: coarser cells stay correct
+    } else {
+        for (int c = 0; c < 6; ++c)
+            if (!std::isfinite(h_misc[c])) return fail(UF3B_ERR_INVALID, "non-finite position");
+        // grid over the bounding box of the centres padded by the search radius and the skin
+        const double pad = basis->tab.r_search * (1.0 + 1e-9);
+        G.edge = pad;
+        G.ox = h_misc[0] - pad - grid_skin; G.oy = h_misc[1] - pad - grid_skin; G.oz = h_misc[2] - pad - grid_skin;
+        G.hx = h_misc[3] + pad + grid_skin; G.hy = h_misc[4] + pad + grid_skin; G.hz = h_misc[5] + pad + grid_skin;
+        const long long cell_cap = std::max<long long>(1 << 22, 8 * n_sup);
+        for (;;) {
+            G.nx = (int)std::floor((G.hx - G.ox) / G.edge) + 1;
+            G.ny = (int)std::floor((G.hy - G.oy) / G.edge) + 1;
+            G.nz = (int)std::floor((G.hz - G.oz) / G.edge) + 1;
+            n_cell = (long long)G.nx * G.ny * G.nz;
+            if (n_cell <= cell_cap) break;
+            G.edge *= 1.26;     // very sparse configuration: coarser cells stay correct
+        }
+        const double par[7] = {G.ox, G.oy, G.oz, G.hx, G.hy, G.hz, G.edge};
+        memcpy(nl->grid_par, par, sizeof par);
+        nl->grid_dim[0] = G.nx; nl->grid_dim[1] = G.ny; nl->grid_dim[2] = G.nz;
+        memcpy(nl->grid_box, h_misc, sizeof nl->grid_box);
+        nl->grid_n = n_atoms;
+        nl->grid_rsearch = basis->tab.r_search;
+        nl->grid_cfirst = nl->c_first;
+        nl->grid_ccount = nl->c_count;
+        if (!is_device_pointer(image_offsets)) nl->grid_imgoff.assign(image_offsets, image_offsets + 3 * (size_t)n_images);
+        else nl->grid_imgoff.clear();
     }
+    BoxCheck chk = {};
+    chk.active = reuse ? 1 : 0;
+    chk.skin = grid_skin;
+    for (int c = 0; c < 3; ++c) { chk.lo[c] = nl->grid_box[c]; chk.hi[c] = nl->grid_box[3 + c]; }
     UF3B_CUDA(nl->cell_of.reserve((size_t)n_sup));
     UF3B_CUDA(nl->cell_start.reserve((size_t)n_cell + 1));
     UF3B_CUDA(nl->cell_cursor.reserve((size_t)n_cell));
@@ -675,7 +726,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     // one pass; the index arrays keep their capacity from earlier builds (first guess below)
     int *status = (int *)(nl->totals.p + 1);        // 8 ints
     int *claims = (int *)(nl->totals.p + 8);        // 2 * NL_REGIONS ints
-    int h_status[6];
+    int h_status[8];
     UF3B_CUDA(nl->cnt2.reserve((size_t)n + 1));
     UF3B_CUDA(nl->cnt3.reserve((size_t)n + 1));
     if (nl->idx2.cap == 0) UF3B_CUDA(nl->idx2.reserve((size_t)n * 80 + 1024));
@@ -697,9 +748,20 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
         UF3B_LAUNCH(k_neighbors, (unsigned)n_cell, NL_WARPS * 32, 0, stream, basis->tab, G, nl->slots.p,
                     nl->cell_start.p, nl->c_first, nl->c_count, nl->off2.p, nl->cnt2.p, nl->off3.p, nl->cnt3.p, nl->idx2.p,
                     nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status, claims);
-        UF3B_LAUNCH(k_post_status, 1, 32, 0, stream, claims, status, (volatile int *)(nl->h_mapped + 8));
+        UF3B_LAUNCH(k_post_status, 1, 32, 0, stream, claims, status, (volatile int *)(nl->h_mapped + 8), nl->misc.p,
+                    chk);
         UF3B_CUDA(cudaStreamSynchronize(stream));
         memcpy(h_status, nl->h_mapped + 8, sizeof h_status);
+        if (reuse) {
+            if (h_status[7] & 1) return fail(UF3B_ERR_ELEMENT, "configuration holds an element outside the basis");
+            if (h_status[7] & 2) return fail(UF3B_ERR_INVALID, "non-finite position");
+            if (h_status[6]) {      // the centres left the cached box: build again with a fresh grid
+                guard.armed = false;
+                *inout = nl;
+                return uf3b_neighbors_build_range(basis, n_atoms, positions, atomic_numbers, n_images,
+                                                  image_offsets, image_abc, first_centre, n_centres, inout, stream_);
+            }
+        }
         if (h_status[0] < 0 || h_status[1] < 0)
             return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
         if (!h_status[2]) break;
@@ -711,6 +773,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     nl->total2 = h_status[0];
     nl->total3 = h_status[1];
     nl->max3 = h_status[3];
+    nl->grid_valid = true;
     guard.armed = false;
     *inout = nl;
     return UF3B_OK;
