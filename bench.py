@@ -42,18 +42,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons WHILE the timed region runs: an NVML polling thread
+    (5 ms period; ctypes calls release the GIL, so the bench loop is not held up), with
+    `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
+        self.sm, self.smax, self.reasons = [], None, set()
+        self.thread = self.proc = self.tmp = None
+        self.stop_flag = False
+
+    def _poll(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                for name, attr in self.REASONS:
+                    if mask & getattr(nv, attr):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() \
+                else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
                  "--format=csv,noheader,nounits", "-lms", "100"],
@@ -63,6 +98,14 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=statistics.median(self.sm), sm_max_mhz=self.smax, samples=len(self.sm),
+                           source="nvml, 5 ms period")
+            out["reasons"] = sorted(self.reasons)
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -91,6 +134,7 @@ class ClockSampler:
             out["sm_mhz"] = statistics.median(sm)
             out["sm_max_mhz"] = max(smax)
             out["samples"] = len(sm)
+            out["source"] = "nvidia-smi -lms 100"
         out["reasons"] = sorted(reasons)
         return out
 
