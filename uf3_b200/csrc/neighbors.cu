@@ -358,35 +358,40 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
         for (int p = threadIdx.x; p < B.n_pairs; p += NL_WARPS * 32) { s_lo[p] = B.pair_lo[p]; s_hi[p] = B.pair_hi[p]; }
     const double *pair_lo = bounds_staged ? s_lo : B.pair_lo, *pair_hi = bounds_staged ? s_hi : B.pair_hi;
     const int cz = cell % G.nz, cy = (cell / G.nz) % G.ny, cx = cell / (G.nz * G.ny);
-    if (threadIdx.x == 0) {
-        int total = 0, k = 0;
-        for (int dx = -1; dx <= 1; ++dx)
-            for (int dy = -1; dy <= 1; ++dy, ++k) {
-                const int x = cx + dx, y = cy + dy;
-                int lo = 0, cnt = 0;
-                if (x >= 0 && x < G.nx && y >= 0 && y < G.ny) {
-                    const int z0 = cz > 0 ? cz - 1 : 0, z1 = cz + 1 < G.nz ? cz + 1 : G.nz - 1;
-                    const int row = (x * G.ny + y) * G.nz;
-                    lo = cell_start[row + z0];
-                    cnt = cell_start[row + z1 + 1] - lo;
-                }
-                run_lo[k] = lo;
-                run_n[k] = cnt;
-                total += cnt;
+    if (threadIdx.x < 32) {       // warp 0: lane k < 9 owns z-run k = (dx, dy) of the 3 x 3 x 3 block
+        const int k = threadIdx.x;
+        int lo = 0, cnt = 0;
+        if (k < 9) {
+            const int x = cx + k / 3 - 1, y = cy + k % 3 - 1;
+            if (x >= 0 && x < G.nx && y >= 0 && y < G.ny) {
+                const int z0 = cz > 0 ? cz - 1 : 0, z1 = cz + 1 < G.nz ? cz + 1 : G.nz - 1;
+                const int row = (x * G.ny + y) * G.nz;
+                lo = cell_start[row + z0];
+                cnt = cell_start[row + z1 + 1] - lo;
             }
-        n_cand = total;
-        if (total <= NL_TILE) {
-            const unsigned b = smem_addr(&bar);
-            mbar_init(b, 1);
-            mbar_expect_tx(b, (unsigned)total * (unsigned)sizeof(Slot));
-            unsigned dst = smem_addr(tile);
-            for (int r = 0; r < 9; ++r)
-                if (run_n[r] > 0) {
-                    const unsigned bytes = (unsigned)run_n[r] * (unsigned)sizeof(Slot);
-                    bulk_copy_g2s(dst, slots + run_lo[r], bytes, b);
-                    dst += bytes;
-                }
+            run_lo[k] = lo;
+            run_n[k] = cnt;
         }
+        int before = cnt;                 // inclusive prefix of the run lengths over lanes 0..8
+        for (int sft = 1; sft < 16; sft <<= 1) {
+            const int up = __shfl_up_sync(FULL, before, sft);
+            if (k >= sft) before += up;
+        }
+        const int total = __shfl_sync(FULL, before, 8);
+        before -= cnt;
+        const unsigned b = smem_addr(&bar);
+        if (k == 0) {
+            n_cand = total;
+            if (total <= NL_TILE) {
+                mbar_init(b, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                mbar_expect_tx(b, (unsigned)total * (unsigned)sizeof(Slot));
+            }
+        }
+        __syncwarp();
+        if (total <= NL_TILE && k < 9 && cnt > 0)
+            bulk_copy_g2s(smem_addr(tile) + (unsigned)before * (unsigned)sizeof(Slot), slots + lo,
+                          (unsigned)cnt * (unsigned)sizeof(Slot), b);
     }
     __syncthreads();
     const int total = n_cand;
@@ -396,6 +401,7 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
     const unsigned lt = (1u << lane) - 1u;
     const bool has3 = B.n_trios > 0;
     const int region = cell % NL_REGIONS;
+    const double r2_search = B.r_search * B.r_search * (1.0 + 1e-12);     // no cutoff exceeds r_search
     for (int s = s0 + warp; s < s1; s += NL_WARPS) {
         const Slot c = slots[s];
         if ((unsigned)(c.m - c_first) >= (unsigned)c_count) continue;   // ghosts (and real atoms of
@@ -414,11 +420,16 @@ k_neighbors(const BasisTab B, const GridParams G, const Slot *__restrict__ slots
                     int m = 0;
                     if (q < count) {
                         const Slot t = cand[q];
-                        const Vec3 pt = {t.x, t.y, t.z};
-                        const double d = dist_rn(pc, pt);
-                        const int p = pair_index(B.ne, c.spec, t.spec);
-                        k2 = d > pair_lo[p] && d < pair_hi[p];
-                        k3 = has3 && d > B.r3min && d <= B.r3max;
+                        // squared distance first (the same rounded operations dist_rn takes the
+                        // root of): candidates beyond the search radius need no square root
+                        const double dx = __dsub_rn(pc.x, t.x), dy = __dsub_rn(pc.y, t.y), dz = __dsub_rn(pc.z, t.z);
+                        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        if (d2 <= r2_search) {
+                            const double d = __dsqrt_rn(d2);
+                            const int p = pair_index(B.ne, c.spec, t.spec);
+                            k2 = d > pair_lo[p] && d < pair_hi[p];
+                            k3 = has3 && d > B.r3min && d <= B.r3max;
+                        }
                         m = t.m;
                     }
                     const unsigned b2 = __ballot_sync(FULL, k2), b3 = __ballot_sync(FULL, k3);
