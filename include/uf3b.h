@@ -155,6 +155,14 @@ int uf3b_gram_accumulate(uf3b_gram *gram, const double *x, const double *y, int6
                          int64_t ld, int is_force, void *stream);
 int uf3b_gram_export(const uf3b_gram *gram, int is_force, double *gram_out, double *ord_out);
 void uf3b_gram_destroy(uf3b_gram *gram);
+/* -- analysis ----------------------------------------------------------------------- */
+/* Pair-distance histogram per pair interaction over list 2 of `nl` (replaces the counting of
+ * distances.summarize_distances, representation/distances.py:401-423): bin_edges [n_bins+1]
+ * uniform and ascending, counts [n_pairs*n_bins] (pair-major, the basis' pair order); every
+ * (real centre, neighbour) entry is counted, as the reference's masked distance matrix does. */
+int uf3b_pair_histogram(uf3b_basis *basis, const uf3b_nlist *nl, const double *bin_edges,
+                        int32_t n_bins, int64_t *counts, void *stream);
+
 /* Dense solve A x = b on the device (cuSOLVER getrf + getrs), the regularised normal
  * equations of regression/least_squares.py:248-272,763-771.  a [n*n] row-major, b and x
  * [n_rhs][n]; host or device pointers; synchronises the stream. */

@@ -15,7 +15,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def case_names(kind=None):
     names = sorted(os.path.splitext(os.path.basename(p))[0]
                    for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    names = [n for n in names if not n.startswith("fit_")]      # multi-frame fit fixtures have their own tests
+    names = [n for n in names if not n.startswith(("fit_", "rdf_"))]      # multi-frame fixtures have their own tests
     if kind == "featurize":
         names = [n for n in names if not n.startswith("calc_")]
     elif kind == "calculator":

@@ -301,6 +301,28 @@ def test_plumbing_featurize_and_fit_matches_reference():
         assert np.allclose(model.predict(x_f), fix["predict_f"], rtol=1e-5, atol=1e-6)
 
 
+def test_pair_distribution_summary_matches_reference():
+    """summarize_distances on the GPU pair list against the histograms the reference wrote for
+    the same frames (oracle/make_golden_rdf.py: three triclinic periodic Ne/Xe cells and one
+    free cluster, r_cut 7 A, 70 bins)."""
+    import os
+    from uf3_b200 import composition
+    from uf3_b200.distances import summarize_distances
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "rdf_summary.npz"))
+    frames = []
+    for k in range(int(fix["n_frames"])):
+        pbc = fix[f"pbc_{k}"]
+        frames.append(Atoms(numbers=fix[f"numbers_{k}"], positions=fix[f"positions_{k}"],
+                            cell=fix["cell"] if pbc.any() else None, pbc=pbc))
+    chem = composition.ChemicalSystem(["Ne", "Xe"], degree=2)
+    hist, edges, lower = summarize_distances(frames, chem, r_cut=7.0, n_bins=70, print_stats=False, progress=None)
+    assert np.array_equal(edges, fix["edges"])
+    for pair in chem.interactions_map[2]:
+        key = "-".join(pair)
+        assert np.allclose(hist[pair], fix["hist_" + key], rtol=1e-12, atol=0)
+        assert lower[pair] == float(fix["lower_" + key])
+
+
 def test_cusolver_solve_matches_host_lapack():
     rng = np.random.default_rng(3)
     for n in (1, 7, 73, 456):
