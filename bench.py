@@ -209,7 +209,6 @@ def inference_extras(torch, dev, stream, steps=20):
     """BASELINE.json configs[2] and configs[4] at one GPU: energy + forces per step through
     the C ABI (neighbour lists + evaluator), inputs resident / via host buffers.  Reported
     beside the headline; not part of `value`."""
-    import glob
     from uf3_b200 import bspline, composition, geometry, synthetic
     from uf3_b200.engine import Engine
 

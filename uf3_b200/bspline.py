@@ -20,7 +20,7 @@ import itertools
 import os
 import re
 import warnings
-from typing import Any, Collection, Dict, List, Tuple
+from typing import Collection, Dict, List, Tuple
 
 import numpy as np
 

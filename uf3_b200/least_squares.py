@@ -11,7 +11,7 @@ LAPACK, exactly as the reference does it (`np.linalg.solve`, :763-771).
 """
 import ctypes as C
 import warnings
-from typing import Collection, Dict
+from typing import Dict
 
 import numpy as np
 
