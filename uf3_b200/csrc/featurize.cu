@@ -920,10 +920,13 @@ __device__ __forceinline__ void legs_three_body_cached(const BasisTab &B, const 
 // 2-body rows of atom `a` (bspline.py:810-895) added into acc[4 * col + (e, fx, fy, fz)]:
 // lanes evaluate 32 pairs at a time into `prec`, then every lane gathers the records that
 // touch ITS feature column.
+// `chunk0`, `chunk_step`: the passes (of 32 pairs) this caller takes — all of them by default;
+// the cooperative kernel deals even and odd passes to two warps with separate accumulators.
 __device__ __forceinline__ void two_body_rows(const BasisTab &B, const FrameView &f, int a, int sa, const Vec3 &pa,
-                                              double *acc, PairRec *prec, int lane) {
+                                              double *acc, PairRec *prec, int lane, int chunk0 = 0,
+                                              int chunk_step = 1) {
     const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
-    for (int base = r0; base < r1; base += CHUNK) {
+    for (int base = r0 + chunk0 * CHUNK; base < r1; base += chunk_step * CHUNK) {
         const int e = base + lane;
         PairRec rec;
         rec.col0 = -(1 << 20);
@@ -1135,6 +1138,7 @@ struct CoopGeom {
     int nap;                // plane row stride in cells
     int slots;              // leg records per table
     int off_ltab, off_gleg; // block-shared: legs of the atom's own row; W group legs
+    int off_acc2;           // block-shared: second accumulator of the pair columns [col0][4]
     int off_warp, warp_bytes;   // per-warp region: [L records][N records][plane A][plane B][dummy]
     int off_plane;          // of plane A inside the warp region
     int plane_bytes;        // of one plane array
@@ -1216,6 +1220,7 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
     const int F = B.n_feats;
     const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
     double *acc = reinterpret_cast<double *>(smem);                         // [F][e, fx, fy, fz]
+    double *acc2 = reinterpret_cast<double *>(smem + cg.off_acc2);          // pair columns, odd passes
     const unsigned smem_s = pin(smem_addr(smem));
     const unsigned ltab_s = smem_s + (unsigned)cg.off_ltab, gleg_s = smem_s + (unsigned)cg.off_gleg;
     unsigned char *mine = smem + cg.off_warp + warp * cg.warp_bytes;
@@ -1243,6 +1248,7 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
 #pragma unroll
         for (int c = 0; c < 4; ++c) r[l][c] = 0.0;
     for (int k = tid; k < 4 * F; k += blockDim.x) acc[k] = 0.0;
+    for (int k = tid; k < 4 * g.col0; k += blockDim.x) acc2[k] = 0.0;
     {
         double2 *z = reinterpret_cast<double2 *>(mine + cg.off_plane);
         for (int k = lane; k < (2 * cg.plane_bytes + 32) / 16; k += 32) z[k] = make_double2(0.0, 0.0);
@@ -1253,11 +1259,13 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
         const int sa = __ldg(f.spec + a);
         const Vec3 pa = real_position(f, a);
         const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
-        // work slots of the atom, dealt to the warps W at a time: slot 0 = pair rows, then the
-        // neighbour-role groups, then the centre-role groups.  The legs of a's own row are only
-        // read by centre-role groups: the warp of slot 1 evaluates them in round 0 unless a
-        // centre group already falls into round 0 (few neighbours / energy only).
-        const int c0 = 1 + (want_f ? n3a : 0);        // first centre-role slot
+        // work slots of the atom, dealt to the warps W at a time: slots 0 and 1 = pair rows (even /
+        // odd passes, the odd ones into a second small accumulator merged at the fold, so that
+        // round 0 is balanced), then the neighbour-role groups, then the centre-role groups.  The
+        // legs of a's own row are only read by centre-role groups: the warp of the first group
+        // slot loads them in round 0 unless a centre group already falls into round 0.
+        const int s2 = W > 1 ? 2 : 1;                 // pair-row slots (even / odd passes of 32 pairs)
+        const int c0 = s2 + (want_f ? n3a : 0);       // first centre-role slot
         const int n_slots = c0 + (n3a > 1 ? n3a : 0);
         const bool early = c0 < W;
         const unsigned char *mine_c = g.leg_cache + (size_t)a * g.cache_stride * SPL_REC;
@@ -1268,15 +1276,17 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
         }
         for (int g0 = 0; g0 < n_slots; g0 += W) {
             const int slot = g0 + warp;
-            if (!early && slot == (W > 1 ? 1 : 0) && lane < n3a)
+            if (!early && slot == (W > 1 ? s2 : 0) && lane < n3a)
                 copy_leg_record(mine_c + (size_t)lane * SPL_REC, 1.0, smem + cg.off_ltab + lane * SPL_REC);
             if (slot == 0) {
                 if (lane == 0) acc[4 * sa] += 1.0;      // composition column n_el (composition.py:96-111)
                 __syncwarp();
-                two_body_rows(B, f, a, sa, pa, acc, prec, lane);
+                two_body_rows(B, f, a, sa, pa, acc, prec, lane, 0, s2);
+            } else if (slot == 1 && s2 == 2) {
+                two_body_rows(B, f, a, sa, pa, acc2, prec, lane, 1, 2);
             }
             // gs: group index in the old numbering (centre groups 0..n3a-1, neighbour groups n3a..)
-            const int gs = slot == 0 ? -1 : (slot < c0 ? n3a + (slot - 1) : (slot < n_slots ? slot - c0 : -1));
+            const int gs = slot < s2 ? -1 : (slot < c0 ? n3a + (slot - s2) : (slot < n_slots ? slot - c0 : -1));
             const int n_groups = 2 * n3a;
             int role = 0;                         // 0 none, 1 centre, 2 neighbour
             if (gs >= 0 && gs < n3a) {
@@ -1385,6 +1395,8 @@ k_featurize_coop(const BasisTab B, const FrameView f, const CoopGeom cg, double 
             __syncthreads();
         }
 
+        // ---- pair columns of the odd passes (3-body columns start at g.col0)
+        for (int k = tid; k < 4 * g.col0; k += blockDim.x) { acc[k] += acc2[k]; acc2[k] = 0.0; }
         // ---- fold the registers into the column accumulators: bins with l <= m, then l > m
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
@@ -1579,7 +1591,8 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         cg.plane_bytes = tg.ma * cg.nap * 16;
         cg.off_ltab = (int)featurize_acc_bytes(F, false);
         cg.off_gleg = cg.off_ltab + cg.slots * (int)SPL_REC;
-        cg.off_warp = cg.off_gleg + cg.warps * (int)GL_REC;
+        cg.off_acc2 = cg.off_gleg + cg.warps * (int)GL_REC;
+        cg.off_warp = cg.off_acc2 + 32 * tg.col0;
         cg.off_plane = 2 * cg.slots * (int)SPL_REC;
         cg.warp_bytes = cg.off_plane + 2 * cg.plane_bytes + 32;
         const size_t smem_c = (size_t)cg.off_warp + (size_t)cg.warps * cg.warp_bytes;
