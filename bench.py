@@ -459,7 +459,9 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": n_atoms * 28 + images[1].nbytes + images[0].size * 4,
                 "d2h_bytes_per_step": (3 * n_atoms + 1) * F * 8},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_featurize", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm",
+                     "kernel": "k_leg_cache + " + ("k_featurize<0,7>" if args.basis == "demo" else "k_featurize_coop<8>"),
+                     "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES.get(args.basis), "traffic_source": "ncu --set full, profiles/ (v20)",
                      "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
