@@ -93,6 +93,10 @@ int uf3b_basis_create(const uf3b_basis_desc *desc, uf3b_basis **out);
  * construct_trio_potentials (forcefield/calculator.py:490-573).  `coefficients` is the
  * flat model vector of length n_feats (host pointer). */
 int uf3b_basis_set_coefficients(uf3b_basis *basis, const double *coefficients, int32_t n);
+/* Throughput knob for streams of frames (no counterpart in the reference): with k handles
+ * working on k consecutive frames on k streams, let every uf3b_featurize launch occupy only
+ * 1/k of the SM resources, so that the frames in flight share each SM.  Default 1. */
+int uf3b_basis_set_frames_in_flight(uf3b_basis *basis, int32_t k);
 void uf3b_basis_destroy(uf3b_basis *basis);
 
 /* -- neighbour lists -------------------------------------------------------------- */

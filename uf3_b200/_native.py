@@ -50,6 +50,7 @@ SIGNATURES = {
     "uf3b_set_device": (C.c_int, [C.c_int]),
     "uf3b_basis_create": (C.c_int, [C.POINTER(BasisDesc), C.POINTER(C.c_void_p)]),
     "uf3b_basis_set_coefficients": (C.c_int, [C.c_void_p, _f64p, C.c_int32]),
+    "uf3b_basis_set_frames_in_flight": (C.c_int, [C.c_void_p, C.c_int32]),
     "uf3b_basis_destroy": (None, [C.c_void_p]),
     "uf3b_neighbors_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),

@@ -259,6 +259,12 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     return UF3B_OK;
 }
 
+int uf3b_basis_set_frames_in_flight(uf3b_basis *b, int32_t k) {
+    if (!b || k < 1 || k > 8) return fail(UF3B_ERR_INVALID, "frames in flight must be 1..8");
+    b->frames_in_flight = k;
+    return UF3B_OK;
+}
+
 int uf3b_basis_set_coefficients(uf3b_basis *b, const double *coefficients, int32_t n) {
     if (!b || !coefficients) return fail(UF3B_ERR_INVALID, "null argument");
     if (n != b->n_feats) return fail(UF3B_ERR_INVALID, "expected %d coefficients, got %d", b->n_feats, n);

@@ -136,6 +136,7 @@ struct uf3b_basis {
     int device = 0;
     std::vector<int> h_trio_goff, h_bin_col, h_trio_col, h_trio_sym, h_trio_dims;   // dims: [3*t + leg]
     bool no_tile = false;          // force the general scatter path (tests / profiling)
+    int frames_in_flight = 1;      // k_featurize launches take 1/k of the resident blocks
     std::vector<double> h_bin_w;
     std::vector<int> h_numbers;
     // scratch for energy partial sums and force-row staging (grow-only)

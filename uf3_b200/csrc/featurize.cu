@@ -1602,7 +1602,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
             int per_sm = 1;
             UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc, cg.warps * 32, smem_c));
             if (per_sm < 1) per_sm = 1;
-            int grid = std::min(sm_count() * per_sm, n);
+            int grid = std::min(std::max(1, sm_count() * per_sm / std::max(1, basis->frames_in_flight)), n);
             double *d_xf = x_forces;
             long long d_ld = ld;
             if (x_forces && !f_dev) {
@@ -1667,7 +1667,10 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
     // `waves` resident grids: 1 = persistent blocks; more lets blocks retire during the launch,
     // so kernels of another stream (the next frame's list build) can be scheduled in between
     static const int waves = getenv("UF3B_GRID_WAVES") ? std::max(1, atoi(getenv("UF3B_GRID_WAVES"))) : 1;
-    int grid = sm_count() * per_sm * waves;
+    // frames in flight (uf3b_basis_set_frames_in_flight): a launch takes only 1/k of the resident
+    // blocks, so that k frames on different streams share every SM — the tail of one frame's
+    // kernel and the next frame's list build overlap instead of leaving SMs idle
+    int grid = std::max(1, sm_count() * per_sm * waves / std::max(1, basis->frames_in_flight));
     const int need = (n + warps - 1) / warps;
     if (grid > need) grid = need;
     const int n_gw = grid * warps;

@@ -18,7 +18,9 @@ def _ptr(arr):
 
 
 class Engine:
-    def __init__(self, basis, device=None):
+    def __init__(self, basis, device=None, frames_in_flight=1):
+        """`frames_in_flight` = k: this engine is one of k working on consecutive frames on k
+        streams; its feature kernels then take 1/k of the SM resources per launch."""
         self._lib = _native.lib()
         if device is not None:
             _native.check(self._lib.uf3b_set_device(int(device)))
@@ -26,6 +28,8 @@ class Engine:
         self.n_feats = self.tables.n_feats
         self._basis = C.c_void_p()
         _native.check(self._lib.uf3b_basis_create(C.byref(self.tables.desc), C.byref(self._basis)))
+        if frames_in_flight != 1:
+            _native.check(self._lib.uf3b_basis_set_frames_in_flight(self._basis, int(frames_in_flight)))
         self._nlist = C.c_void_p()
         self.n_atoms = 0
         self.has_coefficients = False
