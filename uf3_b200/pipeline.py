@@ -18,10 +18,10 @@ from uf3_b200 import geometry
 
 
 class FramePipeline:
-    def __init__(self, basis, max_atoms, device=None, forces=True, depth=2):
+    def __init__(self, basis, max_atoms, device=None, forces=True, depth=2, frames_in_flight=1):
         from uf3_b200.engine import Engine
         index = torch.cuda.current_device() if device is None else int(device)
-        self.engines = [Engine(basis, device=index) for _ in range(depth)]
+        self.engines = [Engine(basis, device=index, frames_in_flight=frames_in_flight) for _ in range(depth)]
         self.F = self.engines[0].n_feats
         self.max_atoms = int(max_atoms)
         self.forces = forces
