@@ -315,12 +315,16 @@ def run_ours(args, rank, world, local_rank):
                                    stream)
         eng.featurize_device(d_xe.data_ptr(), d_xf.data_ptr(), F, stream)
 
-    # e2e: host (pinned) positions in, rows back in host memory, through the frame pipeline
-    # (device->host copy of frame k overlapped with the kernels of frame k+1)
-    from uf3_b200.pipeline import FramePipeline
+    # e2e: host (pinned) positions in, rows back in host memory, through the library's own
+    # pipeline (uf3b_pipeline_*: one worker thread per slot runs the two C-ABI calls of a frame
+    # with HOST pointers; the row copy of a frame overlaps the kernels of the next ones)
+    from uf3_b200.pipeline import NativePipeline
     h_pos_np = [torch.from_numpy(fr[0]).pin_memory().numpy() for fr in frames]
     h_num_np = torch.from_numpy(frames[0][1]).pin_memory().numpy()
-    pipe = FramePipeline(basis, n_atoms, device=local_rank, depth=3)
+    e2e_depth = 4
+    pipe = NativePipeline(basis, depth=e2e_depth, device=local_rank)
+    h_out = [(torch.empty(F, dtype=torch.float64).pin_memory().numpy(),
+              torch.empty((3 * n_atoms, F), dtype=torch.float64).pin_memory().numpy()) for _ in range(e2e_depth)]
 
     def run_e2e(steps):
         """wall-clock ms for `steps` frames, every frame's rows landed in host memory"""
@@ -331,12 +335,14 @@ def run_ours(args, rank, world, local_rank):
         pending = []
         checksum = 0.0
         for k in range(steps):
-            pending.append(pipe.submit(h_pos_np[k % N_POOL], h_num_np, images))
-            if len(pending) == pipe.depth:         # every frame's rows are read on the host
-                xe, xf = pipe.result(pending.pop(0))
+            xe, xf = h_out[k % e2e_depth]
+            pending.append((pipe.submit(h_pos_np[k % N_POOL], h_num_np, images, xe, xf), xe, xf))
+            if len(pending) == e2e_depth:          # every frame's rows are read on the host
+                ticket, xe, xf = pending.pop(0)
+                pipe.wait(ticket)
                 checksum += float(xe[1]) + float(xf[-1, -1])
-        for slot in pending:
-            xe, xf = pipe.result(slot)
+        for ticket, xe, xf in pending:
+            pipe.wait(ticket)
             checksum += float(xe[1]) + float(xf[-1, -1])
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3
@@ -461,8 +467,9 @@ def run_ours(args, rank, world, local_rank):
                    "streams": f"{n_slots} slots alternate frames (one engine + stream each), "
                               f"each launch on 1/{in_flight} of the SM resources"},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "ms_per_step": e2e_ms / args.steps,
-                "how": "uf3_b200.pipeline.FramePipeline: pinned host positions in, rows read back on the "
-                       "host every step, D2H of frame k overlapped with the kernels of frame k+1; wall clock",
+                "how": "uf3b_pipeline_* (uf3_b200.pipeline.NativePipeline, 4 slots): pinned host positions in, "
+                       "rows read on the host every step, the row copy of a frame overlapped with the kernels "
+                       "of the next ones; wall clock",
                 "h2d_bytes_per_step": n_atoms * 28 + images[1].nbytes + images[0].size * 4,
                 "d2h_bytes_per_step": (3 * n_atoms + 1) * F * 8},
         "gpu_launches": launches,

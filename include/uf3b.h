@@ -159,6 +159,23 @@ int uf3b_gram_accumulate(uf3b_gram *gram, const double *x, const double *y, int6
                          int64_t ld, int is_force, void *stream);
 int uf3b_gram_export(const uf3b_gram *gram, int is_force, double *gram_out, double *ord_out);
 void uf3b_gram_destroy(uf3b_gram *gram);
+/* -- frames in flight through host buffers --------------------------------------------- */
+/* `depth` slots, each with its own handles, stream and worker thread; a submitted frame runs
+ * uf3b_neighbors_build + uf3b_featurize with the HOST pointers given (pinned memory makes the
+ * row copy asynchronous to the other slots' kernels).  The reference processes one
+ * configuration at a time (process.py:121-174).  positions / numbers / x_energy / x_forces must
+ * stay valid until uf3b_pipeline_wait(ticket) returns; a slot is reused every `depth`
+ * submissions (submit blocks while its previous frame is still running).  Submit and wait from
+ * one thread. */
+typedef struct uf3b_pipeline uf3b_pipeline;
+int uf3b_pipeline_create(const uf3b_basis_desc *desc, int32_t depth, uf3b_pipeline **out);
+int uf3b_pipeline_submit(uf3b_pipeline *pipe, int64_t n_atoms, const double *positions,
+                         const int32_t *atomic_numbers, int32_t n_images, const double *image_offsets,
+                         const int32_t *image_abc, double *x_energy, double *x_forces, int64_t ld,
+                         int64_t *ticket);
+int uf3b_pipeline_wait(uf3b_pipeline *pipe, int64_t ticket);
+void uf3b_pipeline_destroy(uf3b_pipeline *pipe);
+
 /* -- analysis ----------------------------------------------------------------------- */
 /* Pair-distance histogram per pair interaction over list 2 of `nl` (replaces the counting of
  * distances.summarize_distances, representation/distances.py:401-423): bin_edges [n_bins+1]

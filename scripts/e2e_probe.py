@@ -36,3 +36,26 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(20): h.copy_(d, non_blocking=True)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 20
 print(f"D2H alone: {dt*1e3:.3f} ms per block, {d.numel()*8/dt/1e9:.1f} GB/s")
+
+# native pipeline (C worker threads, no torch on the path)
+from uf3_b200.pipeline import NativePipeline
+def run_native(depth, steps=60):
+    pipe = NativePipeline(basis, depth=depth, device=0)
+    F = pipe.n_feats
+    outs = [(torch.empty(F, dtype=torch.float64).pin_memory().numpy(),
+             torch.empty((30000, F), dtype=torch.float64).pin_memory().numpy()) for _ in range(depth)]
+    def go(n):
+        tickets = []
+        for k in range(n):
+            xe, xf = outs[k % depth]
+            tickets.append(pipe.submit(h_pos[k % 8], h_num, images, xe, xf))
+            if len(tickets) == depth:
+                pipe.wait(tickets.pop(0))
+        for t in tickets:
+            pipe.wait(t)
+    go(10)
+    t0 = time.perf_counter(); go(steps); ms = (time.perf_counter() - t0) * 1e3 / steps
+    pipe.close()
+    return ms
+for depth in (2, 3, 4, 6):
+    print(f"native pipeline depth {depth}: {run_native(depth):.3f} ms/frame", flush=True)

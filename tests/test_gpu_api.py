@@ -364,6 +364,48 @@ def test_frame_pipeline_matches_single_frame_calls():
         assert np.allclose(xf, case["x_forces"], rtol=1e-5, atol=1e-8)
 
 
+def test_native_pipeline_matches_single_frame_calls():
+    """uf3b_pipeline_*: frames of different sizes in flight on three slots give the rows of the
+    one-frame-at-a-time calls, bit for bit; an unknown element surfaces at wait()."""
+    import torch
+    from uf3_b200 import _native
+    from uf3_b200.engine import Engine
+    from uf3_b200.pipeline import NativePipeline
+    names = ["syn_w54_demo", "syn_w16_demo", "syn_w128_demo", "syn_w36_slab", "syn_w54_demo", "syn_w128_demo", "syn_w16_demo"]
+    cases = [gu.Case(n) for n in names]
+    basis = cases[0].basis()
+    F = basis.n_feats
+    pipe = NativePipeline(basis, depth=3)
+    eng = Engine(basis)
+    pending, outs = [], []
+    for case in cases:
+        n = len(case.numbers)
+        pos = torch.from_numpy(np.ascontiguousarray(case.positions)).pin_memory().numpy()
+        num = np.ascontiguousarray(case.numbers, dtype=np.int32)
+        xe = torch.empty(F, dtype=torch.float64).pin_memory().numpy()
+        xf = torch.empty((3 * n, F), dtype=torch.float64).pin_memory().numpy()
+        images = geometry.image_table(case.cell, case.pbc, basis.r_cut)
+        pending.append(pipe.submit(pos, num, images, xe, xf))
+        outs.append((xe, xf))
+        if len(pending) == 3:                 # a ticket is valid until its slot is reused
+            pipe.wait(pending.pop(0))
+    for t in pending:
+        pipe.wait(t)
+    with pytest.raises(_native.UF3BError):    # ticket 0 went through slot 0, which has been reused since
+        pipe.wait(0)
+    for case, (xe, xf) in zip(cases, outs):
+        eng.build_neighbors(case.positions, case.numbers, images=geometry.image_table(case.cell, case.pbc, basis.r_cut))
+        want_e, want_f = eng.featurize()
+        assert np.array_equal(xe, want_e) and np.array_equal(xf, want_f)
+        assert gu.rel_err(xf, case["x_forces"]) <= 1e-6
+    bad = np.array([74, 26], dtype=np.int32)
+    t = pipe.submit(np.zeros((2, 3)), bad, (np.zeros((1, 3), dtype=np.int64), np.zeros((1, 3))), np.zeros(F), np.zeros((6, F)))
+    with pytest.raises(_native.ElementError):
+        pipe.wait(t)
+    pipe.close()
+    eng.close()
+
+
 def test_accumulate_frames_sharded():
     """uf3_b200.distributed.accumulate_frames on one GPU: the two shards add up to the whole."""
     from uf3_b200 import distributed

@@ -69,6 +69,11 @@ SIGNATURES = {
                                        C.c_int, C.c_void_p]),
     "uf3b_gram_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "uf3b_gram_destroy": (None, [C.c_void_p]),
+    "uf3b_pipeline_create": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "uf3b_pipeline_submit": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]),
+    "uf3b_pipeline_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "uf3b_pipeline_destroy": (None, [C.c_void_p]),
     "uf3b_pair_histogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "uf3b_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "uf3b_host_eval_basis": (C.c_int, [_f64p, C.c_int32, C.c_double, _f64p, _f64p]),

@@ -1482,8 +1482,11 @@ static int finish_featurize(uf3b_basis *basis, double *x_energy, double *x_force
                             cudaEvent_t ev0, cudaEvent_t ev1) {
     bool need_sync = g_timing;
     if (x_forces && !f_dev) {
-        UF3B_CUDA(cudaMemcpy2DAsync(x_forces, sizeof(double) * ld, d_xf, sizeof(double) * F,
-                                    sizeof(double) * F, (size_t)3 * n, cudaMemcpyDeviceToHost, stream));
+        if (ld == F)        // contiguous rows: one linear copy
+            UF3B_CUDA(cudaMemcpyAsync(x_forces, d_xf, sizeof(double) * F * (size_t)3 * n, cudaMemcpyDeviceToHost, stream));
+        else
+            UF3B_CUDA(cudaMemcpy2DAsync(x_forces, sizeof(double) * ld, d_xf, sizeof(double) * F,
+                                        sizeof(double) * F, (size_t)3 * n, cudaMemcpyDeviceToHost, stream));
         need_sync = true;
     }
     if (x_energy && !e_dev) {

@@ -94,6 +94,61 @@ class FramePipeline:
             eng.close()
 
 
+class NativePipeline:
+    """`depth` frames in flight through HOST buffers, driven by the worker threads of the C
+    library (`uf3b_pipeline_*`): submit() hands over pinned input / output arrays and returns a
+    ticket at once, wait(ticket) blocks until that frame's rows are in its output arrays.
+    No torch on this path; the caller owns every buffer and keeps it alive until wait()."""
+
+    def __init__(self, basis, depth=3, device=None):
+        import ctypes as C
+        from uf3_b200 import _native
+        from uf3_b200.tables import BasisTables
+        self._C, self._native = C, _native
+        self._lib = _native.lib()
+        if device is not None:
+            _native.check(self._lib.uf3b_set_device(int(device)))
+        self.tables = BasisTables(basis)
+        self.n_feats = self.tables.n_feats
+        self.depth = int(depth)
+        self._pipe = C.c_void_p()
+        _native.check(self._lib.uf3b_pipeline_create(C.byref(self.tables.desc), self.depth, C.byref(self._pipe)))
+        self._keep = {}
+
+    def submit(self, positions, numbers, images, out_energy, out_forces):
+        """positions (n,3) float64, numbers (n,) int32, images = geometry.image_table(...),
+        out_energy (F,) and out_forces (3n, F) float64 C-contiguous (or None)."""
+        C = self._C
+        abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
+        offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
+        if positions.dtype != np.float64 or numbers.dtype != np.int32 or not positions.flags.c_contiguous:
+            raise ValueError("positions must be C-contiguous float64 and numbers int32")
+        ticket = C.c_int64()
+        self._native.check(self._lib.uf3b_pipeline_submit(
+            self._pipe, len(positions), C.c_void_p(positions.ctypes.data), C.c_void_p(numbers.ctypes.data),
+            len(offsets), C.c_void_p(offsets.ctypes.data), C.c_void_p(abc.ctypes.data),
+            C.c_void_p(out_energy.ctypes.data) if out_energy is not None else None,
+            C.c_void_p(out_forces.ctypes.data) if out_forces is not None else None,
+            self.n_feats, C.byref(ticket)))
+        self._keep[ticket.value % self.depth] = (positions, numbers, out_energy, out_forces)
+        return ticket.value
+
+    def wait(self, ticket):
+        self._native.check(self._lib.uf3b_pipeline_wait(self._pipe, int(ticket)))
+
+    def close(self):
+        if getattr(self, "_pipe", None):
+            self._lib.uf3b_pipeline_destroy(self._pipe)
+            self._pipe = self._C.c_void_p()
+            self._keep = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def featurize_frames(featurizer, frames, max_atoms=None):
     """Generator of (x_energy, x_forces) copies for an iterable of geometries, pipelined."""
     from uf3_b200.atoms import frame_arrays
