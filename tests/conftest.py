@@ -11,6 +11,13 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the product never builds itself (uf3_b200._native.lib() fails loudly without the library);
+    # the TEST session does, so that a fresh checkout can run `pytest` directly
+    lib = os.path.join(ROOT, "uf3_b200", "lib", "libuf3b.so")
+    if not os.path.isfile(lib):
+        import subprocess
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "uf3_b200", "csrc"), "-j", str(os.cpu_count() or 4)],
+                       check=True)
 
 
 def pytest_collection_modifyitems(config, items):
