@@ -54,8 +54,14 @@ def accumulate_frames(featurizer, frames, stats=None, rank=0, world_size=1):
     if stats is None:
         stats = GramAccumulator(F)
     stream = torch.cuda.current_stream().cuda_stream
+    mine = shard(frames, rank, world_size)
+    # energy rows stay on the device until the end (one small copy for the whole shard) and the
+    # force targets go up asynchronously, so a frame costs no host synchronisation beyond the
+    # one inside its list build
+    xe_all = torch.zeros((max(len(mine), 1), F), dtype=torch.float64, device="cuda")
     rows = None
-    for geom, energy, forces in shard(frames, rank, world_size):
+    energy_rows = []
+    for k, (geom, energy, forces) in enumerate(mine):
         positions, numbers, cell, pbc = frame_arrays(geom)
         images = geometry.image_table(cell, pbc, featurizer.r_cut) if np.any(pbc) else None
         eng.build_neighbors(positions, numbers, images=images, stream=stream)
@@ -63,13 +69,18 @@ def accumulate_frames(featurizer, frames, stats=None, rank=0, world_size=1):
         want_f = forces is not None and featurizer.fit_forces and n > 0
         if want_f and (rows is None or rows.shape[0] < 3 * n):
             rows = torch.empty((3 * n, F), dtype=torch.float64, device="cuda")
-        xe = np.empty(F)
-        eng._featurize_mixed(xe, rows.data_ptr() if want_f else None, F, stream)
+        eng.featurize_device(xe_all[k].data_ptr(), rows.data_ptr() if want_f else None, F, stream)
         if energy is not None:
-            stats.add_energy_row(xe, energy, n)
+            energy_rows.append((k, float(energy), n))
         if want_f:
-            stats.add_force_rows_device(rows.data_ptr(), np.asarray(forces, dtype=np.float64).reshape(-1),
-                                        3 * n, F, stream)
+            y = np.ascontiguousarray(forces, dtype=np.float64).reshape(-1)
+            y_dev = torch.from_numpy(y).to("cuda", non_blocking=True)
+            stats.add_force_rows_device(rows.data_ptr(), y_dev.data_ptr(), 3 * n, F, stream,
+                                        y_moments=(float(y.sum()), float(np.dot(y, y))))
+            del y_dev        # freed by torch's caching allocator in stream order
+    xe_host = xe_all.cpu().numpy()
+    for k, energy, n in energy_rows:
+        stats.add_energy_row(xe_host[k], energy, n)
     return stats
 
 
