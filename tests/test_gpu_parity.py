@@ -169,17 +169,20 @@ def test_energy_forces_match_oracle_mid_size():
 @pytest.mark.parametrize("name", ["syn_w54_demo", "syn_w36_slab", "syn_w16_demo", "ref_ar3_default",
                                   "syn_w54_manuscript"])
 def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
-    """Unary bases with a small untrimmed 3-body grid take the leg-grouped tile path of
-    k_featurize (symmetry >= 2, rows <= 32), larger grids of symmetry 2 the plane path
+    """Unary bases of symmetry 2 with a small untrimmed 3-body grid (la <= 4, na <= 10, rows <= 32)
+    take the register-tiled kernel k_featurize_tiled; UF3B_NO_TILED sends them to the leg-grouped
+    tile path of k_featurize (symmetry >= 2, rows <= 32), larger grids of symmetry 2 take the plane path
     as the cooperative block-per-atom kernel (UF3B_PLANES forces it for small grids too,
     UF3B_NO_COOP selects the warp-per-atom plane path), else the per-triangle register-tile
     path; UF3B_NO_LEGS / UF3B_NO_TILE force the next more general path.  The leg-grouped path
     reads its legs from the k_leg_cache records unless UF3B_NO_LEG_CACHE is set."""
     case = gu.Case(name)
     outs = []
-    for env in ({}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"}, {"UF3B_PLANES": "1"},
-                {"UF3B_PLANES": "1", "UF3B_NO_COOP": "1"}, {"UF3B_NO_LEG_CACHE": "1"}):
-        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES", "UF3B_NO_COOP", "UF3B_NO_LEG_CACHE"):
+    for env in ({"UF3B_NO_TILED": "1"}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"},
+                {"UF3B_PLANES": "1"}, {"UF3B_PLANES": "1", "UF3B_NO_COOP": "1"},
+                {"UF3B_NO_TILED": "1", "UF3B_NO_LEG_CACHE": "1"}, {}, {"UF3B_TILED_CG": "3"}):
+        for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES", "UF3B_NO_COOP", "UF3B_NO_LEG_CACHE",
+                    "UF3B_NO_TILED", "UF3B_TILED_CG"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
@@ -191,7 +194,7 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     for xe, xf in outs:
         assert gu.rel_err(xe, case["x_energy"]) <= REL
         assert gu.rel_err(xf, case["x_forces"]) <= REL
-    for other in (0, 1, 3, 4, 5):
+    for other in (0, 1, 3, 4, 5, 6, 7):
         assert gu.rel_err(outs[other][1], outs[2][1]) <= 1e-11
         assert gu.rel_err(outs[other][0], outs[2][0]) <= 1e-11
 

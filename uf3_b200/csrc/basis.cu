@@ -251,6 +251,10 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     b->h_trio_sym = trio_sym;
     b->h_trio_dims.resize(3 * n_trios);
     for (int k = 0; k < 3 * n_trios; ++k) b->h_trio_dims[k] = trio_nk[k] - 4;
+    b->h_trio_koff = trio_koff;
+    b->h_trio_poff = trio_poff;
+    b->h_trio_scale = trio_scale;
+    b->h_knots3 = knots3;
     b->no_tile = getenv("UF3B_NO_TILE") != nullptr;
     b->h_bin_col = bin_col;
     b->h_bin_w = bin_w;

@@ -153,6 +153,7 @@ k_energy_forces(const BasisTab B_, const FrameView f, double *forces,
             // entries, two positions and two image offsets from global memory
             const bool staged = n3a <= 32;
             double4 *nb = s_nbr + warp * 32;
+            __syncwarp();       // the previous centre's triangles may still be reading the table
             if (staged && lane < n3a) {
                 int aj;
                 const Vec3 pj = super_position(f, __ldg(f.idx3 + row0 + lane), aj);
