@@ -170,7 +170,9 @@ def test_energy_forces_match_oracle_mid_size():
                                   "syn_w54_manuscript"])
 def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     """Unary bases of symmetry 2 with a small untrimmed 3-body grid (la <= 4, na <= 10, rows <= 32)
-    take the register-tiled kernel k_featurize_tiled; UF3B_NO_TILED sends them to the leg-grouped
+    take the register-tiled kernels k_rows_nbr / k_rows_ctr (UF3B_TILED_ORPHANS: the centre role
+    recomputes every plane itself, the path of a group whose neighbour does not list the centre);
+    UF3B_NO_TILED sends them to the leg-grouped
     tile path of k_featurize (symmetry >= 2, rows <= 32), larger grids of symmetry 2 take the plane path
     as the cooperative block-per-atom kernel (UF3B_PLANES forces it for small grids too,
     UF3B_NO_COOP selects the warp-per-atom plane path), else the per-triangle register-tile
@@ -180,9 +182,10 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     outs = []
     for env in ({"UF3B_NO_TILED": "1"}, {"UF3B_NO_LEGS": "1"}, {"UF3B_NO_LEGS": "1", "UF3B_NO_TILE": "1"},
                 {"UF3B_PLANES": "1"}, {"UF3B_PLANES": "1", "UF3B_NO_COOP": "1"},
-                {"UF3B_NO_TILED": "1", "UF3B_NO_LEG_CACHE": "1"}, {}, {"UF3B_TILED_CG": "3"}):
+                {"UF3B_NO_TILED": "1", "UF3B_NO_LEG_CACHE": "1"}, {}, {"UF3B_TILED_CG": "3"},
+                {"UF3B_TILED_ORPHANS": "1"}):
         for key in ("UF3B_NO_LEGS", "UF3B_NO_TILE", "UF3B_PLANES", "UF3B_NO_COOP", "UF3B_NO_LEG_CACHE",
-                    "UF3B_NO_TILED", "UF3B_TILED_CG"):
+                    "UF3B_NO_TILED", "UF3B_TILED_CG", "UF3B_TILED_ORPHANS"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
@@ -194,7 +197,7 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
     for xe, xf in outs:
         assert gu.rel_err(xe, case["x_energy"]) <= REL
         assert gu.rel_err(xf, case["x_forces"]) <= REL
-    for other in (0, 1, 3, 4, 5, 6, 7):
+    for other in (0, 1, 3, 4, 5, 6, 7, 8):
         assert gu.rel_err(outs[other][1], outs[2][1]) <= 1e-11
         assert gu.rel_err(outs[other][0], outs[2][0]) <= 1e-11
 

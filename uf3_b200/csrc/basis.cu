@@ -255,6 +255,7 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
     b->h_trio_poff = trio_poff;
     b->h_trio_scale = trio_scale;
     b->h_knots3 = knots3;
+    b->h_pair_nk0 = pair_nk[0];
     b->no_tile = getenv("UF3B_NO_TILE") != nullptr;
     b->h_bin_col = bin_col;
     b->h_bin_w = bin_w;

@@ -138,6 +138,7 @@ struct uf3b_basis {
     std::vector<int> h_trio_koff, h_trio_poff;     // [3*t + leg] offsets (doubles) into knots3 / poly3
     std::vector<double> h_trio_scale;              // [3*t + leg]
     std::vector<double> h_knots3;                  // host copy of the 3-body knot vectors
+    int h_pair_nk0 = 0;                            // knots of pair 0
     bool no_tile = false;          // force the general scatter path (tests / profiling)
     int frames_in_flight = 1;      // k_featurize launches take 1/k of the resident blocks
     std::vector<double> h_bin_w;
@@ -149,6 +150,7 @@ struct uf3b_basis {
     uf3b::DevBuf<double> gacc;     // global-memory accumulators for very wide rows
     uf3b::DevBuf<unsigned char> leg_cache;   // k_leg_cache records of the current frame
     uf3b::DevBuf<double> legv, legd, epos;   // k_centre_legs tables of the current frame (tiled path)
+    uf3b::DevBuf<double> planes;             // plane table of the current frame (tiled path)
 };
 
 struct uf3b_nlist {

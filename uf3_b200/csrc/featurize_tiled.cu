@@ -1,28 +1,34 @@
-// featurize_tiled.cu — fit path, register-tiled leg-grouped kernel for small 3-body grids.
+// featurize_tiled.cu — fit path, register-tiled leg-grouped kernels for small 3-body grids.
 //
 // Same mathematics as the leg-grouped path of featurize.cu (the 3-body rows of
 // angles.featurize_force_3b / featurize_energy_3b, representation/angles.py:17-286, factored
-// per LEG GROUP instead of per triangle; unary trio of symmetry 2):
-//   centre role     x_a += sum_j  u_aj dB_l(r_aj) (x) P_j,      P_j[m,n] = sum_{k != j} B_m(r_ak) B_n(r_jk)
-//   energy          e   += sum_j  1/2 B_l(r_aj)  (x) P_j        (both orders of a pair fold onto one column)
-//   neighbour role  x_a += -u_ia dB_l(r_ia) (x) P + B_l(r_ia) (x) Q,
-//                   P[m,n] = sum_k B_m(r_ik) B_n(r_ak),   Q_c[m,n] = sum_k w_ak,c B_m(r_ik) dB_n(r_ak)
-// but organised as small dense contractions with REGISTER tiles.  The previous kernel gave
-// every lane one (m, n) cell and read both factors of every product from shared memory (one
-// shared load per FMA: the L1/LSU pipe was 88 % busy, the FP64 pipe 10 %).  Here
-//   * lane = (group g, n): a contraction round works on G = 32 / NA leg groups at once and a lane
-//     keeps the [m] x {P, Qx, Qy, Qz} tile of its (group, n) in registers: one partner step is
-//     NQ + 1 shared loads (the partner's A[m] and w, broadcast within the group; the lane's
-//     (B_n, dB_n)) for 5 LM floating-point instructions;
-//   * the [c][l][m] force accumulators of the lane's n stay in registers for the whole atom and
-//     are folded into the compressed columns once per atom (lanes of different g are summed with
-//     shuffles first);
-//   * the legs (centre, neighbour) — needed 14 times each, by the centre and by every neighbour —
-//     are evaluated once per frame by k_centre_legs into two small dense tables (96 B per list
-//     entry, L2 resident), together with the position of every atom in its neighbour's row;
-//   * the legs between two neighbours are evaluated in place by the lanes (two groups per pass)
-//     from positions, dense by (basis index - first untrimmed index): no leg cache, no global
-//     traffic beyond positions and list entries.
+// per LEG GROUP instead of per triangle; unary trio of symmetry 2).  With the PLANE of a group
+//   P_(i,j)[m,n] = sum_{k != j} B_m(r_ik) B_n(r_jk)            (centre i, its neighbour j, partners k)
+// the rows of atom a are
+//   neighbour role  x_a += sum_{i in row(a)}  -u_ia dB_l(r_ia) (x) P_(i,a') + B_l(r_ia) (x) Q,
+//                   Q_c[m,n] = sum_k w_a'k,c B_m(r_ik) dB_n(r_a'k)
+//   centre role     x_a += sum_{j in row(a)}   u_aj dB_l(r_aj) (x) P_(a,j)
+//   energy          e   += sum_{j in row(a)}   1/2 B_l(r_aj)  (x) P_(a,j)   (both orders of a pair fold onto one column)
+// The plane P_(i,j) is needed twice: by atom j in its neighbour role and by atom i in its centre
+// role.  It is computed ONCE — by j, whose neighbour role needs the legs (j, k) anyway — and left in
+// an L2-resident table (216 B per list entry); the centre role of every atom is then 14 plane reads
+// and outer products instead of a second round of leg evaluations and contractions.
+//
+//   k_centre_legs   one thread per 3-body list entry: the leg (centre, entry) dense by basis index,
+//                   the entry's ghost position, the row of its parent atom and the position of the
+//                   centre's image in that row — so the consumers reach everything about a
+//                   neighbour's row with ONE level of coalesced loads.
+//   k_rows_nbr      warp = atom, neighbour role.  Lanes evaluate the legs (a', k) of two groups per
+//                   pass into sparse records in shared memory; then lane = (group g, n) contracts
+//                   G = 32 / NA groups per round with the [m] x {P, Qx, Qy, Qz} tile of its (g, n) in
+//                   registers (one partner step = NQ + 2 shared loads for 5 LM FP64 instructions —
+//                   the previous kernel read both factors of EVERY product from shared memory and
+//                   sat at 88 % of the L1/LSU pipe with the FP64 pipe at 10 %), stores P to the
+//                   plane table and adds the outer products to the folded [c][{l, m}] force tile of
+//                   its n, which lives in registers for the whole atom and is stored straight into
+//                   the rows.
+//   k_rows_ctr      warp = atom, centre role from the plane table + pair rows + composition columns;
+//                   completes the rows k_rows_nbr started and produces the energy-row partials.
 #include <algorithm>
 #include <cstdlib>
 
@@ -36,13 +42,14 @@ struct TiledGeom {
     int nk_l, koff_l, poff_l;       // spline table of the l/m legs (doubles into knots3 / poly3)
     int nk_n, koff_n, poff_n;       // ... of the n leg
     double scale_l, scale_n;
-    int n_knots3, n_poly3;          // table sizes (doubles), staged in shared memory per block
     int ps, cg, sl_shift;           // partner slots per group; groups per chunk; log2(lanes per group
                                     // in an evaluation pass)
-    int off_warps, warp_bytes;      // per-warp regions behind the block's tables
-    int off_own, off_grp, off_pos, off_zero, off_aw, off_vn;   // inside a warp's region: legs a -> e, legs centre(e) -> a',
-                                            // ghost positions of the row, (A, w) records, dense n-leg records
+    int off_warps, warp_bytes;      // k_rows_nbr: per-warp regions behind the block's spline table
+    int off_zero, off_aw, off_vn;   // inside a warp's region: [legs centre(e) -> a'] zero word, (A, w) records,
+                                    // n-leg records
+    int all_orphans;                // test hook: k_rows_ctr recomputes every plane itself
     const double *legv, *legd, *epos;   // k_centre_legs tables
+    double *planes;                 // [entry][LM][NA] plane table
 };
 
 template <int LM, int NA>
@@ -53,9 +60,11 @@ struct TiledShape {
     static constexpr unsigned AWB = 16u * NQ;         // bytes of an (A, w) record
     static constexpr unsigned VNB = 80;               // bytes of an n-leg record: the four non-zero (B_n, dB_n),
                                                       // then {first basis index - n0, pad}
+    static constexpr int NS = LM * (LM + 1) / 2;      // unordered pairs {l, m}
+    static constexpr int PL = LM * NA;                // doubles per plane
 };
-constexpr unsigned OWN_REC = 96, POS_REC = 32;        // v[4] dv[4] u[3] pad; x y z pad
-constexpr int TL_MAX_ROW = 32;                        // longest 3-body row the kernel takes
+constexpr unsigned OWN_REC = 96;                      // v[4] dv[4] u[3] pad
+constexpr int TL_MAX_ROW = 32;                        // longest 3-body row the kernels take
 constexpr int TL_DEAD = -(1 << 20);                   // first basis index of a leg that contributes nothing
 
 template <int I>
@@ -247,25 +256,35 @@ __host__ __device__ constexpr int sym_idx(int l, int m, int LM) {
     return l <= m ? l * LM - l * (l - 1) / 2 + (m - l) : m * LM - m * (m - 1) / 2 + (l - m);
 }
 
-// ---------------------------------------------------------------- the kernel
-// Block = W independent warps (W chosen by the host from the shared-memory budget), warp = one
-// atom at a time.  Per-warp shared memory: accumulators [col0][e, fx, fy, fz] of the composition
-// and pair columns (layout of featurize.cu, shared with two_body_rows), three small tables of the
-// atom's own row (legs a -> e, legs centre(e) -> a', ghost positions), and the chunk buffers of
-// cg groups x ps partner slots (slot = position in the centre's row; the slot of the group's own
-// atom stays zero).  The 3-body columns never pass through shared memory: the folded
-// [c][{l, m}] tile of the lane's n lives in registers and is stored straight into the rows.
+// compressed column of the cell ({l, m}, n) of the untrimmed window, or -1
+__device__ __forceinline__ int cell_col(const BasisTab &B, const TiledGeom &tg, int l, int m, int n) {
+    return __ldg(B.bin_col + tg.goff + ((tg.l0 + l) * tg.dim_m + tg.l0 + m) * tg.dim_n + tg.n0 + n);
+}
+
+// Sum of the lanes (g, n), g = 0..G-1, delivered to lane n (the other lanes get garbage).
+template <int G, int NA>
+__device__ __forceinline__ double fold_groups(double v) {
+    double t = v;
+#pragma unroll
+    for (int g = 1; g < G; ++g) t += __shfl_down_sync(FULL, v, g * NA);
+    return t;
+}
+
+// ---------------------------------------------------------------- k_rows_nbr
+// Block = W independent warps, warp = one atom at a time.  Per-warp shared memory: the legs
+// centre(e) -> a' of the atom's row, a zero word, and the chunk buffers of cg groups x ps partner
+// slots (slot = position in the centre's row; the slot of the group's own atom is a dead record).
+// want_f = 0 (energy row only): the planes are still needed by k_rows_ctr; they are built with the
+// values-only contraction and nothing is written to the rows.
 template <int LM, int NA>
 __global__ void __launch_bounds__(128, 4)
-k_featurize_tiled(const BasisTab B, const FrameView f, const TiledGeom tg, double *__restrict__ xf, long long ld,
-                  double *__restrict__ partials, int want_e_, int want_f_) {
+k_rows_nbr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__restrict__ xf, long long ld, int want_f_) {
     using S = TiledShape<LM, NA>;
-    constexpr int NS = LM * (LM + 1) / 2;
+    constexpr int NS = S::NS;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int gw = blockIdx.x * nw + warp, n_gw = gridDim.x * nw;
-    const int F = B.n_feats;
-    const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
+    const bool want_f = want_f_ != 0;
 
     // ---- block: n-leg spline table (knots, then pieces PIECE_B apart)
     const int n_kn = (tg.nk_n + 1) & ~1;
@@ -285,42 +304,22 @@ k_featurize_tiled(const BasisTab B, const FrameView f, const TiledGeom tg, doubl
     nt.nk = tg.nk_n;
     nt.scale = tg.scale_n;
 
-    // ---- warp regions
+    // ---- warp region
     unsigned char *mine = smem + tg.off_warps + (size_t)warp * (size_t)tg.warp_bytes;
-    const unsigned mine_s = pin(smem_s + (unsigned)tg.off_warps + (unsigned)warp * (unsigned)tg.warp_bytes);
-    double *acc = reinterpret_cast<double *>(mine);              // [col0][e, fx, fy, fz]
-    PairRec *prec = reinterpret_cast<PairRec *>(mine + tg.off_aw);      // pair pass scratch (aliases the chunk buffers)
-    const int c_g = lane / NA;                                           // contraction role of the lane: group,
-    const int c_n = (lane - c_g * NA < tg.na) ? lane - c_g * NA : -(1 << 24);   // n (lanes outside the window pick nothing)
-    const bool c_on = c_g < S::G;
-    const double half_e = want_e ? 0.5 : 0.0;
-    const int n_acc = 4 * tg.col0;
-
-    for (int k = lane; k < n_acc; k += 32) acc[k] = 0.0;
+    const unsigned grp_s = pin(smem_s + (unsigned)tg.off_warps + (unsigned)warp * (unsigned)tg.warp_bytes);
+    const unsigned zero_s = grp_s + (unsigned)tg.off_zero;
+    const unsigned aw_s = grp_s + (unsigned)tg.off_aw, vn_s = grp_s + (unsigned)tg.off_vn;
     if (lane == 0) *reinterpret_cast<double2 *>(mine + tg.off_zero) = make_double2(0.0, 0.0);
-    double er[NS];              // energy tile {l, m} of the lane's (g, n), kept over all atoms of the warp
-#pragma unroll
-    for (int s = 0; s < NS; ++s) er[s] = 0.0;
+    const int ps = tg.ps, cg = tg.cg;
+    const int gpp = 32 >> tg.sl_shift;                                   // groups per evaluation pass
+    const int e_gg = lane >> tg.sl_shift, e_k = lane & ((1 << tg.sl_shift) - 1);
+    const int c_g = lane / NA;                                           // contraction role of the lane: group,
+    const int c_n = lane - c_g * NA;                                     // n
+    const int c_pick = c_n < tg.na ? c_n : -(1 << 24);                   // lanes outside the window pick nothing
+    const bool c_on = c_g < S::G;
     __syncwarp();
 
     for (int a = gw; a < f.n; a += n_gw) {
-        {
-            const int sa = __ldg(f.spec + a);
-            const Vec3 pa = real_position(f, a);
-            if (lane == 0) acc[4 * sa] += 1.0;      // composition column n_el (composition.py:96-111)
-            __syncwarp();
-            // -------------------------------------------- 2-body (bspline.py:810-895)
-            two_body_rows(B, f, a, sa, pa, acc, prec, lane);
-        }
-
-        // ------------------------------------------------ 3-body
-        const unsigned own_s = mine_s + (unsigned)tg.off_own, grp_s = mine_s + (unsigned)tg.off_grp;
-        const unsigned pos_s = mine_s + (unsigned)tg.off_pos;
-        const unsigned aw_s = mine_s + (unsigned)tg.off_aw, vn_s = mine_s + (unsigned)tg.off_vn;
-        const unsigned zero_s = mine_s + (unsigned)tg.off_zero;
-        const int ps = tg.ps, cg = tg.cg;
-        const int gpp = 32 >> tg.sl_shift;                               // groups per evaluation pass
-        const int e_gg = lane >> tg.sl_shift, e_k = lane & ((1 << tg.sl_shift) - 1);
         const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
         double fr[3][NS];           // force tile [c][{l, m}] of the lane's (g, n)
 #pragma unroll
@@ -328,26 +327,17 @@ k_featurize_tiled(const BasisTab B, const FrameView f, const TiledGeom tg, doubl
 #pragma unroll
             for (int s = 0; s < NS; ++s) fr[c][s] = 0.0;
 
-        // the atom's own row from the k_centre_legs tables: legs (a, e), ghost positions, and for
-        // the neighbour role the row of every neighbour's parent atom and that centre's leg to a'
+        // entry e of the atom's row: the row of its parent atom (the centre i), the position of a's
+        // image a' in it, and that centre's leg to a'
         int my_rowi = 0, my_ni = 0, my_qa = -1;
         if (lane < n3a) {
             const size_t p = (size_t)(row0 + lane);
-            const double2 *gv = reinterpret_cast<const double2 *>(tg.legv + 4 * p);
-            const double2 *gd = reinterpret_cast<const double2 *>(tg.legd + 8 * p);
-            const double2 *gp = reinterpret_cast<const double2 *>(tg.epos + 4 * p);
-            const double2 v01 = __ldg(gv), v23 = __ldg(gv + 1), d01 = __ldg(gd), d23 = __ldg(gd + 1);
-            const double2 u01 = __ldg(gd + 2), u2t = __ldg(gd + 3), pxy = __ldg(gp), pzt = __ldg(gp + 1);
-            my_qa = (int)(__double_as_longlong(u2t.y) >> 32);
+            const double2 tag = __ldg(reinterpret_cast<const double2 *>(tg.legd + 8 * p) + 3);
+            const double2 pzt = __ldg(reinterpret_cast<const double2 *>(tg.epos + 4 * p) + 1);
+            my_qa = (int)(__double_as_longlong(tag.y) >> 32);
             const long long rt = __double_as_longlong(pzt.y);
             my_rowi = (int)(rt & 0xffffffffll);
             my_ni = (int)(rt >> 32);
-            const unsigned o = own_s + OWN_REC * (unsigned)lane;
-            sts128(o, v01); sts128(o + 16, v23); sts128(o + 32, d01); sts128(o + 48, d23);
-            sts128(o + 64, u01); sts64(o + 80, u2t.x);
-            const unsigned po = pos_s + POS_REC * (unsigned)lane;
-            sts128(po, pxy);
-            sts64(po + 16, pzt.x);
             if (want_f && my_qa >= 0) {
                 const size_t p2 = (size_t)(my_rowi + my_qa);
                 const double2 *hv = reinterpret_cast<const double2 *>(tg.legv + 4 * p2);
@@ -361,167 +351,444 @@ k_featurize_tiled(const BasisTab B, const FrameView f, const TiledGeom tg, doubl
         }
         __syncwarp();
 
-        // ---- (ii) `a` as a neighbour of the centre i named by entry e of its row
-        if (want_f) {
-            for (int c0 = 0; c0 < n3a; c0 += cg) {
-                const int ng = min(cg, n3a - c0);
-                for (int gb = 0; gb < ng; gb += gpp) {          // evaluation passes: legs (a', k) and A = B_m(r_ik)
-                    const int gi = gb + e_gg;
-                    const int e = min(c0 + gi, TL_MAX_ROW - 1);
-                    const int rowi = __shfl_sync(FULL, my_rowi, e), ni = __shfl_sync(FULL, my_ni, e);
-                    const int qa = __shfl_sync(FULL, my_qa, e);
-                    if (gi < ng && qa >= 0 && e_k < ni) {
-                        const double2 *ga = reinterpret_cast<const double2 *>(tg.epos + 4 * (size_t)(rowi + qa));
-                        const double2 *gk = reinterpret_cast<const double2 *>(tg.epos + 4 * (size_t)(rowi + e_k));
-                        const double2 *gv = reinterpret_cast<const double2 *>(tg.legv + 4 * (size_t)(rowi + e_k));
-                        const double2 axy = __ldg(ga), azt = __ldg(ga + 1), kxy = __ldg(gk), kzt = __ldg(gk + 1);
-                        double2 q[S::NQ];
+        for (int c0 = 0; c0 < n3a; c0 += cg) {
+            const int ng = min(cg, n3a - c0);
+            for (int gb = 0; gb < ng; gb += gpp) {          // evaluation passes: legs (a', k) and A = B_m(r_ik)
+                const int gi = gb + e_gg;
+                const int e = min(c0 + gi, TL_MAX_ROW - 1);
+                const int rowi = __shfl_sync(FULL, my_rowi, e), ni = __shfl_sync(FULL, my_ni, e);
+                const int qa = __shfl_sync(FULL, my_qa, e);
+                if (gi < ng && qa >= 0 && e_k < ni) {
+                    const double2 *ga = reinterpret_cast<const double2 *>(tg.epos + 4 * (size_t)(rowi + qa));
+                    const double2 *gk = reinterpret_cast<const double2 *>(tg.epos + 4 * (size_t)(rowi + e_k));
+                    const double2 *gv = reinterpret_cast<const double2 *>(tg.legv + 4 * (size_t)(rowi + e_k));
+                    const double2 axy = __ldg(ga), azt = __ldg(ga + 1), kxy = __ldg(gk), kzt = __ldg(gk + 1);
+                    double2 q[S::NQ];
 #pragma unroll
-                        for (int i = 0; i < S::NQA; ++i) q[i] = __ldg(gv + i);
-                        const Vec3 pap = {axy.x, axy.y, azt.x}, pk = {kxy.x, kxy.y, kzt.x};
-                        const double d = dist_rn(pap, pk);
-                        double v[4], dv[4];
-                        const int idx = eval_n_leg<true>(nt, d, v, dv);
-                        const unsigned slot = (unsigned)(gi * ps + e_k);
-                        store_sparse_n(vn_s + S::VNB * slot, idx < 0 ? TL_DEAD : idx - tg.n0, v, dv);
-                        const double inv = idx < 0 ? 0.0 : fast_rcp(d);
-                        const double w[3] = {(pk.x - pap.x) * inv, (pk.y - pap.y) * inv, (pk.z - pap.z) * inv};
-                        // (A[LM], w[3]) packed behind each other
-                        double rec[2 * S::NQ];
+                    for (int i = 0; i < S::NQA; ++i) q[i] = __ldg(gv + i);
+                    const Vec3 pap = {axy.x, axy.y, azt.x}, pk = {kxy.x, kxy.y, kzt.x};
+                    const double d = dist_rn(pap, pk);
+                    double v[4], dv[4];
+                    const int idx = eval_n_leg<true>(nt, d, v, dv);
+                    const unsigned slot = (unsigned)(gi * ps + e_k);
+                    store_sparse_n(vn_s + S::VNB * slot, idx < 0 ? TL_DEAD : idx - tg.n0, v, dv);
+                    const double inv = idx < 0 ? 0.0 : fast_rcp(d);
+                    const double w[3] = {(pk.x - pap.x) * inv, (pk.y - pap.y) * inv, (pk.z - pap.z) * inv};
+                    // (A[LM], w[3]) packed behind each other
+                    double rec[2 * S::NQ];
 #pragma unroll
-                        for (int i = 0; i < S::NQA; ++i) { rec[2 * i] = q[i].x; rec[2 * i + 1] = q[i].y; }
-                        rec[LM] = w[0]; rec[LM + 1] = w[1]; rec[LM + 2] = w[2];
-                        if (LM + 3 < 2 * S::NQ) rec[2 * S::NQ - 1] = 0.0;
-                        const unsigned ar = aw_s + S::AWB * slot;
+                    for (int i = 0; i < S::NQA; ++i) { rec[2 * i] = q[i].x; rec[2 * i + 1] = q[i].y; }
+                    rec[LM] = w[0]; rec[LM + 1] = w[1]; rec[LM + 2] = w[2];
+                    if (LM + 3 < 2 * S::NQ) rec[2 * S::NQ - 1] = 0.0;
+                    const unsigned ar = aw_s + S::AWB * slot;
 #pragma unroll
-                        for (int i = 0; i < S::NQ; ++i) sts128(ar + 16u * i, make_double2(rec[2 * i], rec[2 * i + 1]));
-                    }
+                    for (int i = 0; i < S::NQ; ++i) sts128(ar + 16u * i, make_double2(rec[2 * i], rec[2 * i + 1]));
                 }
-                __syncwarp();
-                for (int r0 = 0; r0 < ng; r0 += S::G) {         // contraction rounds
-                    const int gi = r0 + c_g;
-                    const int e = min(c0 + gi, TL_MAX_ROW - 1);
-                    const int ni = __shfl_sync(FULL, my_ni, e), qa = __shfl_sync(FULL, my_qa, e);
-                    const bool on = c_on && gi < ng && qa >= 0;
-                    double P[LM], Q[3][LM];
+            }
+            __syncwarp();
+            for (int r0 = 0; r0 < ng; r0 += S::G) {         // contraction rounds
+                const int gi = r0 + c_g;
+                const int e = min(c0 + gi, TL_MAX_ROW - 1);
+                const int rowi = __shfl_sync(FULL, my_rowi, e), ni = __shfl_sync(FULL, my_ni, e);
+                const int qa = __shfl_sync(FULL, my_qa, e);
+                const bool on = c_on && gi < ng && qa >= 0;
+                double P[LM], Q[3][LM];
+                if (want_f)
                     contract_group<LM, NA, true>(aw_s + S::AWB * (unsigned)(gi * ps), vn_s + S::VNB * (unsigned)(gi * ps),
-                                                 on ? ni : 0, c_n, zero_s, P, Q);
-                    if (on) {       // the centre's leg to a': x_a += -u dB_l (x) P + B_l (x) Q
-                        const unsigned ge = grp_s + OWN_REC * (unsigned)e;
-                        double2 q[6];
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) q[i] = lds128(ge + 16u * i);
-                        q[5].x = lds64(ge + 80);
-                        const double vl[4] = {q[0].x, q[0].y, q[1].x, q[1].y}, dl[4] = {q[2].x, q[2].y, q[3].x, q[3].y};
-                        const double u[3] = {q[4].x, q[4].y, q[5].x};
-#pragma unroll
-                        for (int l = 0; l < LM; ++l) {
-                            const double n0_ = -u[0] * dl[l], n1_ = -u[1] * dl[l], n2_ = -u[2] * dl[l];
-#pragma unroll
-                            for (int m = 0; m < LM; ++m) {
-                                constexpr int dummy_ = 0; (void)dummy_;
-                                const int s = sym_idx(l, m, LM);
-                                fr[0][s] = fma(n0_, P[m], fma(vl[l], Q[0][m], fr[0][s]));
-                                fr[1][s] = fma(n1_, P[m], fma(vl[l], Q[1][m], fr[1][s]));
-                                fr[2][s] = fma(n2_, P[m], fma(vl[l], Q[2][m], fr[2][s]));
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-
-        // ---- (i) `a` as the centre: group j = its leg to neighbour j, partners k != j
-        if (n3a > 1) {
-            for (int c0 = 0; c0 < n3a; c0 += cg) {
-                const int ng = min(cg, n3a - c0);
-                for (int gb = 0; gb < ng; gb += gpp) {          // evaluation passes: legs (j, k), values only
-                    const int gi = gb + e_gg, j = c0 + gi;
-                    if (gi < ng && e_k < n3a) {
-                        const unsigned pj_ = pos_s + POS_REC * (unsigned)j, pk_ = pos_s + POS_REC * (unsigned)e_k;
-                        const double2 jxy = lds128(pj_), kxy = lds128(pk_);
-                        const Vec3 pj = {jxy.x, jxy.y, lds64(pj_ + 16)}, pk = {kxy.x, kxy.y, lds64(pk_ + 16)};
-                        double v[4], dv[4] = {0.0, 0.0, 0.0, 0.0};
-                        const int idx = eval_n_leg<false>(nt, dist_rn(pj, pk), v, dv);
-                        const unsigned slot = (unsigned)(gi * ps + e_k);
-                        store_sparse_n(vn_s + S::VNB * slot, idx < 0 ? TL_DEAD : idx - tg.n0, v, dv);
-                        const unsigned ok = own_s + OWN_REC * (unsigned)e_k, ar = aw_s + S::AWB * slot;
-#pragma unroll
-                        for (int i = 0; i < S::NQA; ++i) sts128(ar + 16u * i, lds128(ok + 16u * i));
-                    }
-                }
-                __syncwarp();
-                for (int r0 = 0; r0 < ng; r0 += S::G) {         // contraction rounds
-                    const int gi = r0 + c_g, j = c0 + gi;
-                    const bool on = c_on && gi < ng;
-                    double P[LM], Q[3][LM];
+                                                 on ? ni : 0, c_pick, zero_s, P, Q);
+                else
                     contract_group<LM, NA, false>(aw_s + S::AWB * (unsigned)(gi * ps), vn_s + S::VNB * (unsigned)(gi * ps),
-                                                  on ? n3a : 0, c_n, zero_s, P, Q);
-                    if (on) {       // x_a += u_aj dB_l (x) P_j,  e += 1/2 B_l (x) P_j
-                        const unsigned oj = own_s + OWN_REC * (unsigned)j;
-                        double2 q[6];
+                                                  on ? ni : 0, c_pick, zero_s, P, Q);
+                if (on) {
+                    // the plane of (centre i, neighbour a') for the centre role of atom i
+                    double *pl = tg.planes + (size_t)(rowi + qa) * S::PL + c_n;
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) q[i] = lds128(oj + 16u * i);
-                        q[5].x = lds64(oj + 80);
-                        const double vl[4] = {q[0].x, q[0].y, q[1].x, q[1].y}, dl[4] = {q[2].x, q[2].y, q[3].x, q[3].y};
-                        const double u[3] = {q[4].x, q[4].y, q[5].x};
+                    for (int m = 0; m < LM; ++m) pl[m * NA] = P[m];
+                }
+                if (on && want_f) {     // the centre's leg to a': x_a += -u dB_l (x) P + B_l (x) Q
+                    const unsigned ge = grp_s + OWN_REC * (unsigned)e;
+                    double2 q[6];
 #pragma unroll
-                        for (int l = 0; l < LM; ++l) {
-                            const double hv = half_e * vl[l];
+                    for (int i = 0; i < 5; ++i) q[i] = lds128(ge + 16u * i);
+                    q[5].x = lds64(ge + 80);
+                    const double vl[4] = {q[0].x, q[0].y, q[1].x, q[1].y}, dl[4] = {q[2].x, q[2].y, q[3].x, q[3].y};
+                    const double u[3] = {q[4].x, q[4].y, q[5].x};
 #pragma unroll
-                            for (int m = 0; m < LM; ++m) {
-                                const int s = sym_idx(l, m, LM);
-                                er[s] = fma(hv, P[m], er[s]);
-                                const double dP = dl[l] * P[m];
-                                fr[0][s] = fma(u[0], dP, fr[0][s]);
-                                fr[1][s] = fma(u[1], dP, fr[1][s]);
-                                fr[2][s] = fma(u[2], dP, fr[2][s]);
-                            }
+                    for (int l = 0; l < LM; ++l) {
+                        const double n0_ = -u[0] * dl[l], n1_ = -u[1] * dl[l], n2_ = -u[2] * dl[l];
+#pragma unroll
+                        for (int m = 0; m < LM; ++m) {
+                            const int s = sym_idx(l, m, LM);
+                            fr[0][s] = fma(n0_, P[m], fma(vl[l], Q[0][m], fr[0][s]));
+                            fr[1][s] = fma(n1_, P[m], fma(vl[l], Q[1][m], fr[1][s]));
+                            fr[2][s] = fma(n2_, P[m], fma(vl[l], Q[2][m], fr[2][s]));
                         }
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
         }
 
-        // ------------------------------------------------ rows fx_a, fy_a, fz_a
+        // ---- 3-body columns of rows fx_a, fy_a, fz_a (k_rows_ctr adds the centre role): lanes of
+        // different g are summed, lane n < na then owns every bin of its n — (l, m, n) and (m, l, n)
+        // share a column — and stores it straight into the rows
         if (want_f) {
-            // 3-body columns: lanes of different g are summed, lane n < na then owns every bin of
-            // its n — (l, m, n) and (m, l, n) share a column — and stores it straight into the rows
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    double t = fr[c][s];
-#pragma unroll
-                    for (int g = 1; g < S::G; ++g) t += __shfl_down_sync(FULL, fr[c][s], g * NA);
-                    fr[c][s] = t;
-                }
+                for (int s = 0; s < NS; ++s) fr[c][s] = fold_groups<S::G, NA>(fr[c][s]);
             if (lane < tg.na) {
 #pragma unroll
                 for (int l = 0; l < LM; ++l)
 #pragma unroll
                     for (int m = l; m < LM; ++m) {
                         if (m < tg.la) {
-                            const int col = __ldg(B.bin_col + tg.goff + ((tg.l0 + l) * tg.dim_m + tg.l0 + m) * tg.dim_n + tg.n0 + lane);
+                            const int col = cell_col(B, tg, l, m, lane);
                             if (col >= 0) {
                                 double *dst = xf + (long long)a * ld + tg.col0 + col;
                                 const int s = sym_idx(l, m, LM);
-                                __stcs(dst, fr[0][s]);
-                                __stcs(dst + (long long)f.n * ld, fr[1][s]);
-                                __stcs(dst + 2 * (long long)f.n * ld, fr[2][s]);
+                                dst[0] = fr[0][s];
+                                dst[(long long)f.n * ld] = fr[1][s];
+                                dst[2 * (long long)f.n * ld] = fr[2][s];
                             }
                         }
                     }
             }
-            // composition and pair columns
-            for (int col = lane; col < tg.col0; col += 32) {
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- k_rows_ctr
+// The plane of an ORPHAN group (centre a, neighbour j whose own row does not hold a — the list
+// criterion r3min < d <= r3max can differ by one ulp between the two ends of a bond, so k_rows_nbr
+// never saw the group): P[m] for the lane's n, every lane evaluating the legs (j, k) itself from the
+// global tables.  Rare; also the test hook tg.all_orphans.
+template <int LM>
+struct PlaneCol { double p[LM]; };
+
+// (arguments by value: a reference to the kernel's parameter structs would move them to local memory)
+template <int LM, int NA>
+__device__ __noinline__ PlaneCol<LM> orphan_plane(const double *knots, const double *poly, int nk, double scale,
+                                                  int lead, int trail, int n0, const double *epos, const double *legv,
+                                                  int row0, int n3a, int j, int n) {
+    PlaneCol<LM> out;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    __stcs(xf + ((long long)c * f.n + a) * ld + col, acc[4 * col + 1 + c]);   // written once: streaming
-                    acc[4 * col + 1 + c] = 0.0;
+    for (int m = 0; m < LM; ++m) out.p[m] = 0.0;
+    const double2 *gj = reinterpret_cast<const double2 *>(epos + 4 * (size_t)(row0 + j));
+    const double2 jxy = __ldg(gj), jzt = __ldg(gj + 1);
+    const Vec3 pj = {jxy.x, jxy.y, jzt.x};
+    for (int k = 0; k < n3a; ++k) {
+        if (k == j) continue;
+        const double2 *gk = reinterpret_cast<const double2 *>(epos + 4 * (size_t)(row0 + k));
+        const double2 kxy = __ldg(gk), kzt = __ldg(gk + 1);
+        const Vec3 pk = {kxy.x, kxy.y, kzt.x};
+        const double d = dist_rn(pj, pk);
+        if (!(d >= __ldg(knots) && d <= __ldg(knots + nk - 1))) continue;        // angles.py:502-508
+        double v[4], dv[4];
+        const int idx = eval_leg(knots, nk, scale, poly, d, lead, trail, v, dv);
+        if (idx < 0) continue;
+        const int q = n - (idx - n0);
+        const double vn = q == 0 ? v[0] : (q == 1 ? v[1] : (q == 2 ? v[2] : (q == 3 ? v[3] : 0.0)));
+        const double *av = legv + 4 * (size_t)(row0 + k);
+#pragma unroll
+        for (int m = 0; m < LM; ++m) out.p[m] = fma(__ldg(av + m), vn, out.p[m]);
+    }
+    return out;
+}
+
+// Pair rows (bspline.evaluate_basis_functions / featurize_force_2B, bspline.py:810-895) of one atom:
+// lanes evaluate 32 pairs at a time into records [q][e, fx, fy, fz] (the four non-zero basis
+// functions, force parts already multiplied by 2 u: every bond is seen from both ends,
+// distances.py:118-120); then lane = (slot s, q) adds entry q of the pairs s, s + 8, ... into the
+// PRIVATE column accumulators of slot s — the four lanes of a pair hit four distinct columns and
+// no two slots share an array, so the read-modify-writes need no ordering.  (The gather used by
+// featurize.cu walks all 32 records once per column: 14 instructions per record and column block.)
+constexpr int PR_SLOTS = 8;
+constexpr unsigned PR_REC = 144;        // 128 bytes of entries + {first column, pad}: 16-byte words, odd multiple
+
+struct PairTab {
+    unsigned knots_s, poly_s;           // shared-window addresses of the pair's knots / pieces
+    int nk, col, lead, trail;
+    double scale;
+};
+
+// One pass: lane evaluates its pair (neighbour position pj, `valid`) into its record, then the
+// records of the pass are added to the slots.
+__device__ __forceinline__ void pair_pass(const PairTab &T, const Vec3 &pa, const Vec3 &pj, bool valid, int count,
+                                          unsigned rec_s, unsigned my_slot, int lane) {
+    const int s = lane >> 2, q = lane & 3;
+    int col0 = -1;
+    if (valid) {
+        const double d = dist_rn(pa, pj);
+        const double t_first = lds64(T.knots_s + 24u), t_last = lds64(T.knots_s + 8u * (unsigned)(T.nk - 4));
+        if (d > t_first && d <= t_last) {       // find_interval (spline.cuh) on the staged table
+            int i = 3 + (int)((d - t_first) * T.scale);
+            if (i > T.nk - 5) i = T.nk - 5;
+            double ti = lds64(T.knots_s + 8u * (unsigned)i);
+            if (!(ti < d && d <= lds64(T.knots_s + 8u * (unsigned)i + 8u))) {
+                int lo = 3, hi = T.nk - 4;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (lds64(T.knots_s + 8u * (unsigned)mid) < d) lo = mid; else hi = mid;
                 }
+                i = lo;
+                ti = lds64(T.knots_s + 8u * (unsigned)i);
+            }
+            const double u = d - ti, inv2 = 2.0 / d;
+            const double ux = (pj.x - pa.x) * inv2, uy = (pj.y - pa.y) * inv2, uz = (pj.z - pa.z) * inv2;
+            const unsigned piece = T.poly_s + PIECE_B * (unsigned)(i - 3);
+            const unsigned rec = rec_s + PR_REC * (unsigned)lane;
+            const int nb = T.nk - 4;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const double2 c01 = lds128(piece + 32u * p), c23 = lds128(piece + 32u * p + 16u);
+                double v = ((c23.y * u + c23.x) * u + c01.y) * u + c01.x;
+                double dv = (3.0 * c23.y * u + 2.0 * c23.x) * u + c01.y;
+                const int bi = i - 3 + p;
+                if (bi < T.lead || bi >= nb - T.trail) { v = 0.0; dv = 0.0; }     // bspline.py:840
+                sts128(rec + 32u * p, make_double2(v, dv * ux));
+                sts128(rec + 32u * p + 16u, make_double2(dv * uy, dv * uz));
+            }
+            col0 = T.col + i - 3;
+        }
+    }
+    asm volatile("st.shared.s32 [%0], %1;" :: "r"(rec_s + PR_REC * (unsigned)lane + 128u), "r"(col0) : "memory");
+    __syncwarp();
+    for (int t = s; t < count; t += PR_SLOTS) {
+        const unsigned rec = rec_s + PR_REC * (unsigned)t;
+        const int c = lds32(rec + 128u);
+        if (c >= 0) {
+            const unsigned ad = my_slot + 32u * (unsigned)(c + q);
+            const double2 r01 = lds128(rec + 32u * q), r23 = lds128(rec + 32u * q + 16u);
+            double2 a01 = lds128(ad), a23 = lds128(ad + 16u);
+            a01.x += r01.x; a01.y += r01.y; a23.x += r23.x; a23.y += r23.y;
+            sts128(ad, a01);
+            sts128(ad + 16u, a23);
+        }
+    }
+    __syncwarp();
+}
+
+// Block = W independent warps, warp = one atom at a time.  Per-block shared memory: the pair spline
+// table; per warp: PR_SLOTS private accumulator arrays [col0][e, fx, fy, fz] of the composition and
+// pair columns and the records of a pair pass.
+template <int LM, int NA>
+__global__ void __launch_bounds__(128, 4)
+k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__restrict__ xf, long long ld,
+           double *__restrict__ partials, int want_e_, int want_f_) {
+    using S = TiledShape<LM, NA>;
+    constexpr int NS = S::NS;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int gw = blockIdx.x * nw + warp, n_gw = gridDim.x * nw;
+    const int F = B.n_feats;
+    const bool want_e = want_e_ != 0, want_f = want_f_ != 0;
+
+    // ---- block: pair spline table (unary basis: one pair)
+    const int nk2 = __ldg(B.pair_nk), n_kn = (nk2 + 1) & ~1;
+    {
+        double *tab = reinterpret_cast<double *>(smem);
+        const int n_po = 16 * (nk2 - 7);
+        for (int k = threadIdx.x; k < nk2; k += blockDim.x) tab[k] = __ldg(B.knots2 + k);
+        for (int k = threadIdx.x; k < n_po; k += blockDim.x)
+            tab[n_kn + (k >> 4) * (int)(PIECE_B / 8) + (k & 15)] = __ldg(B.poly2 + k);
+    }
+    __syncthreads();
+    const unsigned smem_s = pin(smem_addr(smem));
+    PairTab pt;
+    pt.knots_s = smem_s;
+    pt.poly_s = smem_s + 8u * (unsigned)n_kn;
+    pt.nk = nk2;
+    pt.col = __ldg(B.pair_col);
+    pt.lead = B.lead2;
+    pt.trail = B.trail2;
+    pt.scale = __ldg(B.pair_scale);
+
+    const unsigned slot_stride = 32u * (unsigned)tg.col0;
+    const unsigned slot_s = smem_s + (unsigned)tg.off_warps + (unsigned)warp * (unsigned)tg.warp_bytes;
+    const unsigned rec_s = slot_s + PR_SLOTS * slot_stride;       // pair records of a pass, or (before them) the row tables:
+    const unsigned own_s = rec_s, pl_s = rec_s + OWN_REC * (unsigned)tg.ps;     // legs a -> e, planes of the row
+    const int c_g = lane / NA, c_n = lane - c_g * NA;
+    const bool c_on = c_g < S::G && c_n < tg.na;
+    const double half_e = want_e ? 0.5 : 0.0;
+
+    for (unsigned o = 16u * lane; o < PR_SLOTS * slot_stride; o += 512u) sts128(slot_s + o, make_double2(0.0, 0.0));
+    double er[NS];              // energy tile {l, m} of the lane's (g, n), kept over all atoms of the warp
+#pragma unroll
+    for (int s = 0; s < NS; ++s) er[s] = 0.0;
+    __syncwarp();
+
+    for (int a = gw; a < f.n; a += n_gw) {
+        // Every global load of the atom is issued in three batches before the arithmetic — the kernel
+        // is a chain of dependent gathers otherwise (58 % of the stall samples were long-scoreboard
+        // waits): (1) row bounds, (2) the lane's own 3-body entry and its pair-list entries of the
+        // first two passes, (3) the planes and the pair partners' positions.
+        const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
+        const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
+        const int sa = __ldg(f.spec + a);
+        const Vec3 pa = real_position(f, a);
+        if (want_f && lane < tg.na) {       // the 3-body columns k_rows_nbr stored are updated at the end: touch them
+#pragma unroll                              // now (loads to nowhere), so that the update finds them in L1
+            for (int l = 0; l < LM; ++l)
+#pragma unroll
+                for (int m = l; m < LM; ++m)
+                    if (m < tg.la) {
+                        const int col = cell_col(B, tg, l, m, lane);
+                        if (col >= 0) {
+                            const double *src = xf + (long long)a * ld + tg.col0 + col;
+                            const long long cs = (long long)f.n * ld;
+                            double sink;
+                            asm volatile("ld.global.f64 %0, [%1];" : "=d"(sink) : "l"(src));
+                            asm volatile("ld.global.f64 %0, [%1];" : "=d"(sink) : "l"(src + cs));
+                            asm volatile("ld.global.f64 %0, [%1];" : "=d"(sink) : "l"(src + 2 * cs));
+                        }
+                    }
+        }
+        const bool pv0 = r0 + lane < r1, pv1 = r0 + 32 + lane < r1;
+        const int m0 = pv0 ? __ldg(f.idx2 + r0 + lane) : 0, m1 = pv1 ? __ldg(f.idx2 + r0 + 32 + lane) : 0;
+        // own entry (leg a -> e and the validity of its plane) and the planes of the row — n3a x PL
+        // doubles, contiguous in the table; loads first, stores behind the position gathers
+        double2 ow[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ow[i] = make_double2(0.0, 0.0);
+        if (lane < n3a) {
+            const size_t p = (size_t)(row0 + lane);
+            const double2 *gv = reinterpret_cast<const double2 *>(tg.legv + 4 * p);
+            const double2 *gd = reinterpret_cast<const double2 *>(tg.legd + 8 * p);
+            ow[0] = __ldg(gv); ow[1] = __ldg(gv + 1); ow[2] = __ldg(gd); ow[3] = __ldg(gd + 1);
+            ow[4] = __ldg(gd + 2); ow[5] = __ldg(gd + 3);
+        }
+        constexpr int PB = 12;              // plane doubles per lane and batch (14 x 27 = 378 <= 384)
+        const double *pl = tg.planes + (size_t)row0 * S::PL;
+        const int n_pl = n3a * S::PL;
+        double pb[PB];
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+            const int i = 32 * k + lane;
+            pb[k] = i < n_pl ? __ldg(pl + i) : 0.0;
+        }
+        int dummy;
+        Vec3 pj0 = pa, pj1 = pa;
+        if (pv0) pj0 = super_position(f, m0, dummy);
+        if (pv1) pj1 = super_position(f, m1, dummy);
+        if (lane < n3a) {
+            const unsigned o = own_s + OWN_REC * (unsigned)lane;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) sts128(o + 16u * i, ow[i]);
+        }
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+            const int i = 32 * k + lane;
+            if (i < n_pl) sts64(pl_s + 8u * (unsigned)i, pb[k]);
+        }
+        for (int i0 = 32 * PB; i0 < n_pl; i0 += 32 * PB) {      // long rows
+#pragma unroll
+            for (int k = 0; k < PB; ++k) {
+                const int i = i0 + 32 * k + lane;
+                pb[k] = i < n_pl ? __ldg(pl + i) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PB; ++k) {
+                const int i = i0 + 32 * k + lane;
+                if (i < n_pl) sts64(pl_s + 8u * (unsigned)i, pb[k]);
+            }
+        }
+        __syncwarp();
+
+        // ------------------------------------------------ 3-body, centre role: x_a += u_aj dB_l (x) P_j,
+        // e += 1/2 B_l (x) P_j with the planes k_rows_nbr left in the table
+        double fr[3][NS];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) fr[c][s] = 0.0;
+        if (c_on && n3a > 1) {
+            for (int j = c_g; j < n3a; j += S::G) {
+                const unsigned oj = own_s + OWN_REC * (unsigned)j;
+                double2 q[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) q[i] = lds128(oj + 16u * i);
+                const int qa = (int)(__double_as_longlong(q[5].y) >> 32);
+                double P[LM];
+                if (qa >= 0 && !tg.all_orphans) {
+                    const unsigned pj_ = pl_s + 8u * (unsigned)(j * S::PL + c_n);
+#pragma unroll
+                    for (int m = 0; m < LM; ++m) P[m] = lds64(pj_ + 8u * (unsigned)(m * NA));
+                } else {
+                    const PlaneCol<LM> o = orphan_plane<LM, NA>(B.knots3 + tg.koff_n, B.poly3 + tg.poff_n, tg.nk_n, tg.scale_n,
+                                                                B.lead3, B.trail3, tg.n0, tg.epos, tg.legv, row0, n3a, j, c_n);
+#pragma unroll
+                    for (int m = 0; m < LM; ++m) P[m] = o.p[m];
+                }
+                const double vl[4] = {q[0].x, q[0].y, q[1].x, q[1].y}, dl[4] = {q[2].x, q[2].y, q[3].x, q[3].y};
+                const double u[3] = {q[4].x, q[4].y, q[5].x};
+#pragma unroll
+                for (int l = 0; l < LM; ++l) {
+                    const double hv = half_e * vl[l];
+#pragma unroll
+                    for (int m = 0; m < LM; ++m) {
+                        const int s = sym_idx(l, m, LM);
+                        er[s] = fma(hv, P[m], er[s]);
+                        const double dP = dl[l] * P[m];
+                        fr[0][s] = fma(u[0], dP, fr[0][s]);
+                        fr[1][s] = fma(u[1], dP, fr[1][s]);
+                        fr[2][s] = fma(u[2], dP, fr[2][s]);
+                    }
+                }
+            }
+        }
+        __syncwarp();       // the pair records reuse the memory of the row tables
+        // ------------------------------------------------ 2-body and composition columns
+        {
+            if (lane == 0) sts64(slot_s + 32u * (unsigned)sa, lds64(slot_s + 32u * (unsigned)sa) + 1.0);   // n_el (composition.py:96-111)
+            __syncwarp();
+            const unsigned my_slot = slot_s + (unsigned)(lane >> 2) * slot_stride;
+            if (r0 < r1) pair_pass(pt, pa, pj0, pv0, min(32, r1 - r0), rec_s, my_slot, lane);
+            if (r0 + 32 < r1) pair_pass(pt, pa, pj1, pv1, min(32, r1 - r0 - 32), rec_s, my_slot, lane);
+            for (int base = r0 + 64; base < r1; base += 32) {
+                const bool pv = base + lane < r1;
+                Vec3 pj = pa;
+                if (pv) pj = super_position(f, __ldg(f.idx2 + base + lane), dummy);
+                pair_pass(pt, pa, pj, pv, min(32, r1 - base), rec_s, my_slot, lane);
+            }
+        }
+        // ------------------------------------------------ rows fx_a, fy_a, fz_a
+        if (want_f) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int s = 0; s < NS; ++s) fr[c][s] = fold_groups<S::G, NA>(fr[c][s]);
+            if (lane < tg.na) {         // 3-body columns: add the centre role to what k_rows_nbr stored
+#pragma unroll
+                for (int l = 0; l < LM; ++l)
+#pragma unroll
+                    for (int m = l; m < LM; ++m) {
+                        if (m < tg.la) {
+                            const int col = cell_col(B, tg, l, m, lane);
+                            if (col >= 0) {
+                                double *dst = xf + (long long)a * ld + tg.col0 + col;
+                                const long long cs = (long long)f.n * ld;
+                                const int s = sym_idx(l, m, LM);
+                                const double x0 = dst[0], x1 = dst[cs], x2 = dst[2 * cs];
+                                __stcs(dst, x0 + fr[0][s]);
+                                __stcs(dst + cs, x1 + fr[1][s]);
+                                __stcs(dst + 2 * cs, x2 + fr[2][s]);
+                            }
+                        }
+                    }
+            }
+            // composition and pair columns: the slots' force parts are summed, stored and cleared
+            for (int it = lane; it < 3 * tg.col0; it += 32) {
+                const int col = it / 3, c = it - 3 * col;
+                const unsigned ad = slot_s + 32u * (unsigned)col + 8u * (unsigned)(1 + c);
+                double t = 0.0;
+#pragma unroll
+                for (int sl = 0; sl < PR_SLOTS; ++sl) {
+                    t += lds64(ad + (unsigned)sl * slot_stride);
+                    sts64(ad + (unsigned)sl * slot_stride, 0.0);
+                }
+                __stcs(xf + ((long long)c * f.n + a) * ld + col, t);     // written once: streaming
             }
         }
         __syncwarp();
@@ -533,15 +800,18 @@ k_featurize_tiled(const BasisTab B, const FrameView f, const TiledGeom tg, doubl
 #pragma unroll
             for (int m = l; m < LM; ++m) {
                 const int s = sym_idx(l, m, LM);
-                double t = er[s];
-#pragma unroll
-                for (int g = 1; g < S::G; ++g) t += __shfl_down_sync(FULL, er[s], g * NA);
+                const double t = fold_groups<S::G, NA>(er[s]);
                 if (lane < tg.na && m < tg.la) {
-                    const int col = __ldg(B.bin_col + tg.goff + ((tg.l0 + l) * tg.dim_m + tg.l0 + m) * tg.dim_n + tg.n0 + lane);
+                    const int col = cell_col(B, tg, l, m, lane);
                     if (col >= 0) mine_p[tg.col0 + col] = t;
                 }
             }
-        for (int col = lane; col < tg.col0; col += 32) mine_p[col] = acc[4 * col];
+        for (int col = lane; col < tg.col0; col += 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < PR_SLOTS; ++sl) t += lds64(slot_s + (unsigned)sl * slot_stride + 32u * (unsigned)col);
+            mine_p[col] = t;
+        }
     }
 }
 
@@ -561,6 +831,7 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     const int max3 = std::max(nl->max3, 2);
     tg.ps = max3;                   // one slot per position of the longest row
     tg.sl_shift = tg.ps <= 16 ? 4 : 5;
+    tg.all_orphans = getenv("UF3B_TILED_ORPHANS") ? 1 : 0;
     // a chunk of cg groups holds whole contraction rounds (G groups); the larger candidate also holds
     // whole evaluation passes (32 >> sl_shift groups) and is taken when it does not cost resident warps
     const int cg_env = getenv("UF3B_TILED_CG") ? atoi(getenv("UF3B_TILED_CG")) : 0;
@@ -569,18 +840,14 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     const int rows = (max3 + 1) & ~1;
     const size_t tab_bytes = 8 * (size_t)((tg.nk_n + 1) & ~1) + (size_t)PIECE_B * (tg.nk_n - 7);
     tg.off_warps = (int)((tab_bytes + 15) & ~size_t(15));
-    tg.off_own = (int)((4 * (size_t)tg.col0 * sizeof(double) + 15) & ~size_t(15));
-    tg.off_grp = tg.off_own + rows * (int)OWN_REC;
-    tg.off_pos = tg.off_grp + rows * (int)OWN_REC;
-    tg.off_zero = tg.off_pos + rows * (int)POS_REC;
+    tg.off_zero = rows * (int)OWN_REC;
     tg.off_aw = tg.off_zero + 16;
     auto layout = [&](int cg, int &warps, int &blocks) {
         tg.cg = cg;
         // two records of readable padding behind each array (the contraction loads ahead)
         const size_t aw_bytes = ((size_t)cg * tg.ps + 2) * S::AWB;
         tg.off_vn = tg.off_aw + (int)aw_bytes;
-        size_t chunk_bytes = aw_bytes + ((size_t)cg * tg.ps + 2) * S::VNB;
-        chunk_bytes = std::max(chunk_bytes, 32 * sizeof(PairRec));     // the pair pass borrows the chunk buffers
+        const size_t chunk_bytes = aw_bytes + ((size_t)cg * tg.ps + 2) * S::VNB;
         tg.warp_bytes = (int)((tg.off_aw + chunk_bytes + 15) & ~size_t(15));
         // warps per block x blocks per SM: most resident warps within the register budget (16 warps
         // at 128 registers) and the shared memory of an SM (1 KB reserved per block)
@@ -611,24 +878,42 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     }
     if (warps < 1) return 1;            // does not fit: the caller takes another path
     if (w_env > 0 && w_env <= 4 && (size_t)tg.off_warps + (size_t)w_env * tg.warp_bytes <= (size_t)smem_max) warps = w_env;
-    auto kernel = k_featurize_tiled<LM, NA>;
-    const size_t smem = (size_t)tg.off_warps + (size_t)warps * tg.warp_bytes;
-    UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
-    int grid = std::max(1, sm_count() * per_sm / std::max(1, basis->frames_in_flight));
-    grid = std::min(grid, (n + warps - 1) / warps);
-    const int n_gw = grid * warps;
+    auto k_nbr = k_rows_nbr<LM, NA>;
+    auto k_ctr = k_rows_ctr<LM, NA>;
+    const size_t smem_n = (size_t)tg.off_warps + (size_t)warps * tg.warp_bytes;
+    // k_rows_ctr: [pair spline table][per warp: PR_SLOTS x col0 accumulator quads, 32 pair records]
+    const int warps_c = 4;
+    const int nk2 = basis->h_pair_nk0;
+    const size_t tab_c = ((8 * (size_t)((nk2 + 1) & ~1) + (size_t)PIECE_B * (nk2 - 7)) + 15) & ~size_t(15);
+    const size_t rows_c = (size_t)OWN_REC * tg.ps + 8 * (size_t)S::PL * tg.ps;
+    const size_t warp_c = ((size_t)PR_SLOTS * 32 * tg.col0 + std::max<size_t>(32 * PR_REC, rows_c) + 15) & ~size_t(15);
+    const size_t smem_c = tab_c + (size_t)warps_c * warp_c;
+    if (smem_c > (size_t)smem_max) return 1;
+    TiledGeom tgc = tg;
+    tgc.off_warps = (int)tab_c;
+    tgc.warp_bytes = (int)warp_c;
+    UF3B_CUDA(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n));
+    UF3B_CUDA(cudaFuncSetAttribute(k_ctr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    int per_sm_n = 1, per_sm_c = 1;
+    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_n, k_nbr, warps * 32, smem_n));
+    UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_ctr, warps_c * 32, smem_c));
+    const int share = std::max(1, basis->frames_in_flight);
+    int grid_n = std::max(1, sm_count() * std::max(per_sm_n, 1) / share);
+    grid_n = std::min(grid_n, (n + warps - 1) / warps);
+    int grid_c = std::max(1, sm_count() * std::max(per_sm_c, 1) / share);
+    grid_c = std::min(grid_c, (n + warps_c - 1) / warps_c);
+    const int n_gw = grid_c * warps_c;
 
-    // tables of k_centre_legs: one slot per list entry (rows live in claim regions of idx3)
+    // tables of k_centre_legs and the planes: one slot per list entry (rows live in claim regions of idx3)
     const size_t entries = nl->idx3.cap;
     UF3B_CUDA(basis->legv.reserve(4 * entries));
     UF3B_CUDA(basis->legd.reserve(8 * entries));
     UF3B_CUDA(basis->epos.reserve(4 * entries));
+    UF3B_CUDA(basis->planes.reserve((size_t)S::PL * entries));
     tg.legv = basis->legv.p;
     tg.legd = basis->legd.p;
     tg.epos = basis->epos.p;
+    tg.planes = basis->planes.p;
 
     double *d_xf = x_forces;
     long long d_ld = ld;
@@ -656,7 +941,9 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     const long long threads = (long long)n << sub_shift;
     UF3B_LAUNCH(k_centre_legs, (unsigned)((threads + 255) / 256), 256, 0, stream, basis->tab, view, tg, sub_shift,
                 basis->legv.p, basis->legd.p, basis->epos.p);
-    UF3B_LAUNCH(kernel, grid, warps * 32, smem, stream, basis->tab, view, tg, d_xf, d_ld, basis->partials.p,
+    UF3B_LAUNCH(k_nbr, grid_n, warps * 32, smem_n, stream, basis->tab, view, tg, d_xf, d_ld, x_forces ? 1 : 0);
+    tgc.legv = tg.legv; tgc.legd = tg.legd; tgc.epos = tg.epos; tgc.planes = tg.planes;
+    UF3B_LAUNCH(k_ctr, grid_c, warps_c * 32, smem_c, stream, basis->tab, view, tgc, d_xf, d_ld, basis->partials.p,
                 x_energy ? 1 : 0, x_forces ? 1 : 0);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (x_energy)
@@ -664,13 +951,13 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     return finish_featurize(basis, x_energy, x_forces, ld, d_xe, d_xf, F, n, e_dev, f_dev, stream, ev0, ev1);
 }
 
-// Takes the frame if the basis fits the tiled kernel: unary trio of symmetry 2 with unit folding
+// Takes the frame if the basis fits the tiled kernels: unary trio of symmetry 2 with unit folding
 // weights, untrimmed grid la x la x na with la <= 4, na <= 10, rows of at most 32 entries.
 // Returns 1 when it does not apply (the caller goes on to the other paths); error codes are <= 0.
 int featurize_tiled(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, double *x_forces, int64_t ld,
                     cudaStream_t stream) {
     const BasisTab &T = basis->tab;
-    if (T.n_trios != 1 || !T.unit_weights || basis->no_tile || getenv("UF3B_NO_TILED") || getenv("UF3B_NO_LEGS")
+    if (T.n_trios != 1 || T.ne != 1 || !T.unit_weights || basis->no_tile || getenv("UF3B_NO_TILED") || getenv("UF3B_NO_LEGS")
         || getenv("UF3B_PLANES"))
         return 1;
     if (basis->h_trio_sym[0] != 2 || nl->max3 > TL_MAX_ROW) return 1;
@@ -695,8 +982,6 @@ int featurize_tiled(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, d
     tg.nk_n = N + 4; tg.koff_n = basis->h_trio_koff[2]; tg.poff_n = basis->h_trio_poff[2];
     tg.scale_l = basis->h_trio_scale[0];
     tg.scale_n = basis->h_trio_scale[2];
-    tg.n_knots3 = basis->n_knots3;
-    tg.n_poly3 = basis->n_poly3;
     // the kernel stores the 3-body columns from the folded {l, m} tile: they must be the last
     // columns of the row, (l, m, n) and (m, l, n) must share a column, and the cells with l <= m
     // must reach every column exactly once
