@@ -6,9 +6,13 @@
 
 One step = one 10 000-atom frame taken through the whole hot path: neighbour lists
 (Kernel A) + energy row + 3N force rows (Kernel B).  `value` has the frame resident in HBM
-and leaves the rows in HBM; `e2e` goes through the same C-ABI calls with HOST buffers
-(pinned), host->device and device->host copies inside the timed region.  Under torchrun
-every rank featurizes its own frames (frames are independent: weak scaling, no collective
+and leaves the rows in HBM.  `e2e` is the path north_star describes, through the library's own
+frame pipeline with HOST buffers (uf3b_pipeline_submit_fit): pinned positions and force targets
+go up every step, the rows stay in HBM and are folded into the normal equations
+(uf3b_gram_accumulate), the frame's energy row comes back, and the timed region ends with the ONE
+all-reduce of the normal equations and the regularised solve (coefficients on the host).
+`e2e_rows_to_host` is the same frames with every row copied to the host instead (the copy, not the
+kernels, bounds it).  Under torchrun every rank takes its own frames (weak scaling, no collective
 on the data path); time = max over ranks.
 """
 import argparse
@@ -30,7 +34,23 @@ N_POOL = 8          # distinct frames (inputs AND output row buffers) per rank, 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the
 # `ncu --set full` captures summarised under profiles/ (r01_k_featurize_v20_legcache_details.txt,
 # r01_k_featurize_coop_manuscript_v20_details.txt); the leg-cache reads are in it
-NCU_TRAFFIC_BYTES = {"demo": 113.1e6 + 9.5e6, "manuscript": 116.7e6 + 79.1e6}
+NCU_TRAFFIC_BYTES = {"demo": None, "manuscript": 116.7e6 + 79.1e6}
+# executed FP64 flops per launch of the dominant kernels from the same captures (2 per fused, 1 per
+# non-fused thread instruction, predicated-off lanes excluded)
+NCU_FP64_FLOP = {"demo": None, "manuscript": None}
+try:
+    with open(os.path.join(ROOT, "profiles", "ncu_constants.json")) as _fh:
+        _c = json.load(_fh)
+    NCU_TRAFFIC_BYTES.update(_c.get("dram_bytes_per_launch", {}))
+    NCU_FP64_FLOP.update(_c.get("fp64_flop_per_launch", {}))
+except (OSError, ValueError):
+    pass
+
+
+def bench_config(basis_name, n_feats):
+    """`config` of the JSON line: the same dictionary in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "basis": basis_name, "n_feats": int(n_feats),
+            "step": "one 10000-atom frame per rank: neighbour lists + energy row + 3N force rows"}
 
 
 def load_peaks():
@@ -192,8 +212,8 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "basis": args.basis, "n_feats": int(basis.n_feats),
-                   "step": f"{cores} frames of 10000 atoms, one per host thread"},
+        "config": bench_config(args.basis, basis.n_feats),
+        "notes": {"step": f"{cores} frames of 10000 atoms per step, one per host thread"},
         "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{cores} full 10k-atom frames per step (energy row + 3N force "
                                    "rows), oracle/uf3_oracle.c, one frame per thread"},
@@ -205,27 +225,29 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------- inference configs
+def w_model23():
+    """The shipped W 2+3-body model (examples/tungsten_extxyz/model_2and3.json), carried as a test
+    fixture because /root/reference does not exist on the GPU box."""
+    from uf3_b200 import bspline, composition
+    data = np.load(os.path.join(ROOT, "tests", "golden", "calc_syn_w54_model23.npz"))
+    cfg = json.loads(str(data["config"]))
+    knots = {}
+    for key, val in cfg["kwargs"]["knots_map"].items():
+        parts = tuple(key.split("-"))
+        knots[parts] = np.array(val) if len(parts) == 2 else [np.array(v) for v in val]
+    chem = composition.ChemicalSystem(cfg["element_list"], degree=cfg["degree"])
+    lead = {int(k): v for k, v in cfg["kwargs"]["leading_trim"].items()}
+    trail = {int(k): v for k, v in cfg["kwargs"]["trailing_trim"].items()}
+    basis = bspline.BSplineBasis(chem, knots_map=knots, leading_trim=lead, trailing_trim=trail)
+    return basis, np.array(data["coefficients"])
+
+
 def inference_extras(torch, dev, stream, steps=20):
     """BASELINE.json configs[2] and configs[4] at one GPU: energy + forces per step through
     the C ABI (neighbour lists + evaluator), inputs resident / via host buffers.  Reported
     beside the headline; not part of `value`."""
-    from uf3_b200 import bspline, composition, geometry, synthetic
+    from uf3_b200 import geometry, synthetic
     from uf3_b200.engine import Engine
-
-    def model23():
-        # the shipped W 2+3-body model (examples/tungsten_extxyz/model_2and3.json), carried
-        # as a test fixture because /root/reference does not exist on the GPU box
-        data = np.load(os.path.join(ROOT, "tests", "golden", "calc_syn_w54_model23.npz"))
-        cfg = json.loads(str(data["config"]))
-        knots = {}
-        for key, val in cfg["kwargs"]["knots_map"].items():
-            parts = tuple(key.split("-"))
-            knots[parts] = np.array(val) if len(parts) == 2 else [np.array(v) for v in val]
-        chem = composition.ChemicalSystem(cfg["element_list"], degree=cfg["degree"])
-        lead = {int(k): v for k, v in cfg["kwargs"]["leading_trim"].items()}
-        trail = {int(k): v for k, v in cfg["kwargs"]["trailing_trim"].items()}
-        basis = bspline.BSplineBasis(chem, knots_map=knots, leading_trim=lead, trailing_trim=trail)
-        return basis, np.array(data["coefficients"])
 
     def nexe_model():
         data = np.load(os.path.join(ROOT, "tests", "golden", "calc_syn_nexe64_pair.npz"))
@@ -234,7 +256,7 @@ def inference_extras(torch, dev, stream, steps=20):
     out = {}
     for tag, (basis, coeff), fr in (
             ("nexe_50k_energy_forces", nexe_model(), synthetic.nexe((25, 25, 10), seed=0)),
-            ("w_100k_md_step_energy_forces", model23(), synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0))):
+            ("w_100k_md_step_energy_forces", w_model23(), synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0))):
         eng = Engine(basis, device=dev.index)
         eng.set_coefficients(coeff)
         pos, numbers, cell, pbc = fr
@@ -283,11 +305,61 @@ def inference_extras(torch, dev, stream, steps=20):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def md_extra(torch, dist, dev, rank, world, steps=20, warmup=3, dt=0.2):
+    """BASELINE.json configs[4] beside the headline when several GPUs run: the 100 000-atom W MD
+    step (neighbour lists + energy + forces, atom ranges over the ranks), strong scaling."""
+    from uf3_b200 import geometry, synthetic
+    from uf3_b200.distributed import ShardedEvaluator
+    basis, coeff = w_model23()
+    pos, numbers, cell, pbc = synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0)
+    n = len(pos)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    ev = ShardedEvaluator(basis, coeff, device=dev.index)
+    x = torch.from_numpy(pos).to(dev)
+    z = torch.from_numpy(numbers).to(dev)
+    v = torch.zeros_like(x)
+    inv_m = 9.648533e-3 / 183.84
+
+    def step(f):
+        v.add_(f, alpha=0.5 * dt * inv_m)
+        x.add_(v, alpha=dt)
+        e, f_new = ev.energy_forces(x, z, images)
+        v.add_(f_new, alpha=0.5 * dt * inv_m)
+        return e, f_new
+
+    e0, f = ev.energy_forces(x, z, images)
+    e0, f = float(e0), f.clone()
+    for _ in range(warmup):
+        e, f = step(f)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        e, f = step(f)
+    stop.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ke = 0.5 * 183.84 / 9.648533e-3 * float((v * v).sum())
+    drift = float(e) + ke - e0
+    ev.close()
+    return {"workload": "bulk bcc W 25x40x50 cells (100000 atoms), velocity Verlet, model_2and3 (2+3-body)",
+            "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "atom_steps_per_s": n / (ms * 1e-3),
+            "dt_fs": dt, "energy0_eV": e0, "energy_drift_eV": drift, "energy_drift_rel": abs(drift) / abs(e0),
+            "energy_conserved": bool(abs(drift) / abs(e0) < 1e-6)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from uf3_b200 import geometry
+    from uf3_b200 import _native, distributed, geometry, least_squares as ls
     from uf3_b200.engine import Engine
+    from uf3_b200.pipeline import NativePipeline
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -295,6 +367,9 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # many ranks x pipeline workers on one host: sleeping waits instead of spinning ones
+    if world >= 4:
+        _native.check(_native.lib().uf3b_set_blocking_sync(1))
 
     basis = make_basis(args.basis)
     eng = Engine(basis, device=local_rank)
@@ -315,29 +390,87 @@ def run_ours(args, rank, world, local_rank):
                                    stream)
         eng.featurize_device(d_xe.data_ptr(), d_xf.data_ptr(), F, stream)
 
-    # e2e: host (pinned) positions in, rows back in host memory, through the library's own
-    # pipeline (uf3b_pipeline_*: one worker thread per slot runs the two C-ABI calls of a frame
-    # with HOST pointers; the row copy of a frame overlaps the kernels of the next ones)
-    from uf3_b200.pipeline import NativePipeline
-    h_pos_np = [torch.from_numpy(fr[0]).pin_memory().numpy() for fr in frames]
-    h_num_np = torch.from_numpy(frames[0][1]).pin_memory().numpy()
-    e2e_depth = 4
-    pipe = NativePipeline(basis, depth=e2e_depth, device=local_rank)
-    h_out = [(torch.empty(F, dtype=torch.float64).pin_memory().numpy(),
-              torch.empty((3 * n_atoms, F), dtype=torch.float64).pin_memory().numpy()) for _ in range(e2e_depth)]
-
-    def run_e2e(steps):
-        """wall-clock ms for `steps` frames, every frame's rows landed in host memory"""
+    def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---------------------------------------------------------------- host-buffer arms
+    h_pos_np = [torch.from_numpy(fr[0]).pin_memory().numpy() for fr in frames]
+    h_num_np = torch.from_numpy(frames[0][1]).pin_memory().numpy()
+    e2e_depth = 4 if world < 4 else 3
+    # synthetic targets of the fit (outside the timed region): y = rows @ c_true, E = x_e @ c_true
+    model = ls.WeightedLinearModel(basis, solver="cusolver", ridge_1b=1e-10, ridge_2b=1e-10, ridge_3b=1e-10)
+    free = np.zeros(F)
+    free[np.asarray(model.mask)] = 1.0
+    c_true = np.random.default_rng(11).normal(size=F) * 0.1 * free        # frozen columns carry no signal
+    c_dev = torch.from_numpy(c_true).to(dev)
+    h_y, e_target = [], []
+    for i in range(N_POOL):
+        step_resident(i)
+        h_y.append((d_xf @ c_dev).cpu().pin_memory().numpy())
+        e_target.append(float(d_xe @ c_dev))
+    h_xf_check = d_xf.cpu().numpy()         # rows of the last pool frame, for the sanity check of the fit
+    pipe = NativePipeline(basis, depth=e2e_depth, device=local_rank)
+    h_xe = [torch.empty(F, dtype=torch.float64).pin_memory().numpy() for _ in range(e2e_depth)]
+    fit_info = {}
+
+    def run_e2e_fit(steps):
+        """wall-clock ms for `steps` frames per rank from host buffers to fitted coefficients on the
+        host: uf3b_pipeline_submit_fit per frame, then ONE all-reduce and the cuSOLVER solve"""
+        stats = ls.GramStats(F)
+        barrier()
+        t0 = time.perf_counter()
+        pending = []
+        for k in range(steps):
+            xe = h_xe[k % e2e_depth]
+            pending.append((pipe.submit_fit(h_pos_np[k % N_POOL], h_num_np, images, h_y[k % N_POOL], xe), xe, k))
+            if len(pending) == e2e_depth:          # every frame's energy row is read on the host
+                ticket, xe_done, kk = pending.pop(0)
+                pipe.wait(ticket)
+                stats.add_energy_row(xe_done, e_target[kk % N_POOL], n_atoms)
+        for ticket, xe_done, kk in pending:
+            pipe.wait(ticket)
+            stats.add_energy_row(xe_done, e_target[kk % N_POOL], n_atoms)
+        gram_f, ord_f, moments = pipe.export_gram()
+        t1 = time.perf_counter()
+        stats.gram_f += gram_f
+        stats.ord_f += ord_f
+        stats.moments[3:6] += moments
+        distributed.all_reduce_stats(stats)
+        t2 = time.perf_counter()
+        model.fit_from_accumulator(stats, weight=0.5)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        # sanity of the fit: the targets were generated from c_true, so the fitted model must reproduce
+        # the force targets of a frame (columns without signal — trimmed, frozen — are free to differ)
+        y_fit = h_xf_check @ model.coefficients
+        fit_info.update(frames_ms=(t1 - t0) * 1e3, all_reduce_ms=(t2 - t1) * 1e3, solve_ms=(t3 - t2) * 1e3,
+                        frames_only_value=world * n_atoms * steps / ((t1 - t0) * 1e-3),
+                        force_prediction_error_rel=float(np.linalg.norm(y_fit - h_y[N_POOL - 1])
+                                                         / np.linalg.norm(h_y[N_POOL - 1])))
+        return max_over_ranks((t3 - t0) * 1e3)
+
+    # rows-to-host: the same frames with every row copied out (secondary figure)
+    h_out = [(torch.empty(F, dtype=torch.float64).pin_memory().numpy(),
+              torch.empty((3 * n_atoms, F), dtype=torch.float64).pin_memory().numpy()) for _ in range(e2e_depth)]
+
+    def run_e2e_rows(steps):
+        barrier()
         t0 = time.perf_counter()
         pending = []
         checksum = 0.0
         for k in range(steps):
             xe, xf = h_out[k % e2e_depth]
             pending.append((pipe.submit(h_pos_np[k % N_POOL], h_num_np, images, xe, xf), xe, xf))
-            if len(pending) == e2e_depth:          # every frame's rows are read on the host
+            if len(pending) == e2e_depth:
                 ticket, xe, xf = pending.pop(0)
                 pipe.wait(ticket)
                 checksum += float(xe[1]) + float(xf[-1, -1])
@@ -345,27 +478,28 @@ def run_ours(args, rank, world, local_rank):
             pipe.wait(ticket)
             checksum += float(xe[1]) + float(xf[-1, -1])
         torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, checksum
+        return max_over_ranks((time.perf_counter() - t0) * 1e3)
 
-    def barrier():
+    def d2h_ceiling():
+        """GB/s of a plain pinned device->host copy of one frame's rows (per rank, all ranks at once)"""
+        src = d_xf
+        dst = torch.from_numpy(h_out[0][1])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        return 10 * src.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
-    # resident arm: two slots (engine + stream each) alternate frames, so the GPU can run one
-    # frame's kernels while the host reads back the two sizing scalars of the other frame's
-    # list build.  L2: every step reads its own frame and writes its own row buffer out of a
-    # pool of N_POOL; the pool (positions + rows) is larger than the 126 MB L2, so no step
-    # finds its data in cache and no explicit flush is needed.
-    # three slots, each launch taking half of an SM's resources (frames_in_flight=2): two frames'
-    # feature kernels share every SM, so one frame's tail round and the next frame's list build
-    # fill each other's gaps (measured +6 % over two full-width slots)
-    # (the block-per-atom kernel of the manuscript basis measured slower that way: two full-width slots)
+    # ---------------------------------------------------------------- resident arm
+    # L2: every step reads its own frame and writes its own row buffer out of a pool; the pool
+    # (positions + rows) is larger than the 126 MB L2, so no step finds its data in cache and no
+    # explicit flush is needed.  Three slots (engine + stream each) alternate frames, each launch
+    # taking half of an SM's resources (frames_in_flight=2): two frames' kernels share every SM, so
+    # one frame's tail and the next frame's list build (which ends in a host wait) fill each other's
+    # gaps.  (The block-per-atom kernel of the manuscript basis measured slower that way.)
     n_slots = int(os.environ.get("UF3B_BENCH_SLOTS", "3" if args.basis == "demo" else "2"))
     in_flight = int(os.environ.get("UF3B_BENCH_IN_FLIGHT", "2" if args.basis == "demo" else "1"))
     slots = [(Engine(basis, device=local_rank, frames_in_flight=in_flight), torch.cuda.Stream(dev))
@@ -403,22 +537,20 @@ def run_ours(args, rank, world, local_rank):
         stop.record(main)
         barrier()
         launches = eng.launch_count() - launches0
-        total_ms = start.elapsed_time(stop)
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms, launches
+        return max_over_ranks(start.elapsed_time(stop)), launches
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     total_ms, launches = timed(args.steps, args.warmup)
-    run_e2e(args.warmup)
-    e2e_ms, _ = run_e2e(args.steps)
+    run_e2e_fit(max(args.warmup, e2e_depth))        # warm-up: buffers, NCCL connections, cuSOLVER handle
+    e2e_ms = run_e2e_fit(args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    run_e2e_rows(args.warmup)
+    rows_ms = run_e2e_rows(args.steps)
+    copy_gbs = d2h_ceiling()
 
-    # dominant kernel (k_featurize), timed alone with CUDA events on its own stream
+    # dominant kernels (the row kernels of Kernel B), timed alone with CUDA events on their stream
     eng.set_timing(True)
     kernel_ms = []
     for i in range(5):
@@ -428,23 +560,31 @@ def run_ours(args, rank, world, local_rank):
     eng.set_timing(False)
     k_ms = statistics.mean(kernel_ms[1:])
     e2, e3 = eng.neighbor_count(2), eng.neighbor_count(3)
-    # algorithmic bytes of one k_featurize launch (DESIGN.md "Kernel B"): positions + species,
-    # both CSR lists, and the 3N x F force rows + energy row written once.
+    # algorithmic bytes of one launch (DESIGN.md "Kernel B"): positions + species, both lists
+    # (start, count, entries), and the 3N x F force rows + energy row written once
     alg_bytes = n_atoms * 28 + 4 * (e2 + e3) + 8 * (n_atoms + 1) + 24 * n_atoms * F + 8 * F
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
 
     value = world * n_atoms * args.steps / (total_ms * 1e-3)
     e2e_value = world * n_atoms * args.steps / (e2e_ms * 1e-3)
+    rows_value = world * n_atoms * args.steps / (rows_ms * 1e-3)
+
+    extra = None
+    if args.extra:
+        if world == 1:
+            extra = inference_extras(torch, dev, stream)
+        else:
+            extra = {"md": md_extra(torch, dist, dev, rank, world)}
     if rank != 0:
+        pipe.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
     fp64_peak = eng.probe_fp64_tflops()
-    extra = None
-    if world == 1 and args.extra:
-        extra = inference_extras(torch, dev, stream)
+    fp64_flop = NCU_FP64_FLOP.get(args.basis)
+    fp64_achieved = fp64_flop / (k_ms * 1e-3) / 1e12 if fp64_flop else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_cpu_frames = 4
@@ -453,40 +593,60 @@ def run_ours(args, rank, world, local_rank):
                "kind": "port",
                "sample": f"{n_cpu_frames} full 10k-atom frames (energy row + 3N force rows), "
                          "oracle/uf3_oracle.c, single thread"}
+    tiled = args.basis == "demo"
+    reduce_doubles = 2 * F * F + 2 * F + 6
     line = {
         "metric": "atom-steps/s featurized (2+3-body) on 10k-atom W",
         "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "basis": args.basis, "n_feats": F,
-                   "frames_per_rank_pool": N_POOL, "pairs_per_atom": e2 / n_atoms,
-                   "list3_per_atom": e3 / n_atoms,
-                   "step": "neighbour lists + energy row + 3N force rows of one frame per rank",
-                   "l2": "inputs larger than L2: every step uses its own frame and row buffer out of a pool of "
-                         f"{len(out_pool)} ({pool_bytes / 1e6:.0f} MB > 126 MB L2); no explicit flush",
-                   "streams": f"{n_slots} slots alternate frames (one engine + stream each), "
-                              f"each launch on 1/{in_flight} of the SM resources"},
+        "config": bench_config(args.basis, F),
+        "notes": {"frames_per_rank_pool": N_POOL, "pairs_per_atom": e2 / n_atoms, "list3_per_atom": e3 / n_atoms,
+                  "l2": "inputs larger than L2: every step uses its own frame and row buffer out of a pool of "
+                        f"{len(out_pool)} ({pool_bytes / 1e6:.0f} MB > 126 MB L2); no explicit flush",
+                  "streams": f"{n_slots} slots alternate frames (one engine + stream each), "
+                             f"each launch on 1/{in_flight} of the SM resources"},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "ms_per_step": e2e_ms / args.steps,
-                "how": "uf3b_pipeline_* (uf3_b200.pipeline.NativePipeline, 4 slots): pinned host positions in, "
-                       "rows read on the host every step, the row copy of a frame overlapped with the kernels "
-                       "of the next ones; wall clock",
-                "h2d_bytes_per_step": n_atoms * 28 + images[1].nbytes + images[0].size * 4,
-                "d2h_bytes_per_step": (3 * n_atoms + 1) * F * 8},
+                "how": f"uf3b_pipeline_submit_fit ({e2e_depth} slots): pinned host positions and force targets in "
+                       "every step, rows folded into the normal equations on the device, the frame's energy row "
+                       "read on the host every step; the timed region ends with ONE all-reduce of the normal "
+                       "equations and the cuSOLVER solve (coefficients on the host); wall clock, max over ranks",
+                "h2d_bytes_per_step": n_atoms * 28 + 24 * n_atoms + images[1].nbytes + images[0].size * 4,
+                "d2h_bytes_per_step": 8 * F,
+                "d2h_bytes_at_end": 8 * (2 * F * F + F + 3), "all_reduce_doubles": reduce_doubles,
+                "all_reduce_bytes": 8 * reduce_doubles, **fit_info},
+        "e2e_rows_to_host": {"value": rows_value, "unit": "atom-steps/s", "ms_per_step": rows_ms / args.steps,
+                             "how": f"uf3b_pipeline_submit ({e2e_depth} slots): pinned host positions in, energy row + "
+                                    "3N force rows copied to pinned host memory every step",
+                             "d2h_bytes_per_step": (3 * n_atoms + 1) * F * 8,
+                             "d2h_GBps_per_rank": (3 * n_atoms + 1) * F * 8 / (rows_ms / args.steps * 1e-3) / 1e9,
+                             "plain_pinned_copy_GBps_per_rank": copy_gbs},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm",
-                     "kernel": "k_leg_cache + " + ("k_featurize<0,7>" if args.basis == "demo" else "k_featurize_coop<8>"),
+                     "kernel": ("k_centre_legs + k_rows_nbr<3,9> + k_rows_ctr<3,9>" if tiled
+                                else "k_leg_cache + k_featurize_coop<8>"),
                      "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES.get(args.basis), "traffic_source": "ncu --set full, profiles/ (v20)",
+                     "traffic": NCU_TRAFFIC_BYTES.get(args.basis),
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the "
+                                       "kernels named, profiles/ncu_constants.json",
                      "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
-                     "kernel_note": "k_leg_cache + the featurize kernel, timed together"},
-        "roofline_fp64": {"peak_tflops": fp64_peak, "peak_source": "uf3b_probe_fp64_tflops (DFMA chains)",
-                          "note": "3-body rows are FP64-bound, see DESIGN.md"},
+                     "kernel_note": "the kernels named are timed together; the path is bound by the shared-memory "
+                                    "/ FP64 pipes, not by HBM (roofline_fp64, DESIGN.md)"},
+        "roofline_fp64": {"bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": fp64_achieved / fp64_peak if fp64_achieved else None,
+                          "flop_per_launch": fp64_flop,
+                          "flop_source": "ncu: 2 x fused + non-fused FP64 thread instructions of the kernels named "
+                                         "(profiles/ncu_constants.json)",
+                          "peak_source": "uf3b_probe_fp64_tflops (DFMA chains)",
+                          "binding_roof": "fp64: min(HBM time, FP64 time) of the algorithm is the FP64 one "
+                                          "(SURVEY.md 8d)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
         "extra": extra,
     }
     print(json.dumps(line), flush=True)
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -533,6 +693,8 @@ def run_md(args, rank, world, local_rank):
         return e, f_new
 
     e0, f = ev.energy_forces(x, z, images)
+    e0 = float(e0)              # the evaluator reuses its output buffer: keep the VALUE, not a view
+    f = f.clone()
     for _ in range(args.warmup):
         e, f = step(f)
     torch.cuda.synchronize()
@@ -565,7 +727,8 @@ def run_md(args, rank, world, local_rank):
                                    f"velocity Verlet dt={args.dt} fs, model_2and3 (2+3-body)",
                        "partition": "atom ranges, replicated positions, one all-reduce of 3N+1 doubles per step"},
             "gpu_launches": launches,
-            "energy_drift_eV": float(e) + ke - float(e0), "energy0_eV": float(e0)}), flush=True)
+            "energy_drift_eV": float(e) + ke - e0, "energy0_eV": e0,
+            "energy_drift_rel": abs(float(e) + ke - e0) / abs(e0)}), flush=True)
     ev.close()
     if world > 1:
         dist.destroy_process_group()
@@ -684,7 +847,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--basis", default="demo", choices=["demo", "manuscript"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
-    ap.add_argument("--extra", action="store_true", help="also time the inference configs (Ne/Xe 50k, W 100k)")
+    ap.add_argument("--extra", dest="extra", action="store_true", default=True,
+                    help="also time the inference configs: Ne/Xe 50k and W 100k at one GPU, the 100k-atom MD "
+                         "step over all ranks under torchrun (default)")
+    ap.add_argument("--no-extra", dest="extra", action="store_false")
     ap.add_argument("--dt", type=float, default=1.0, help="MD time step in fs (--workload md)")
     ap.add_argument("--workload", default="featurize", choices=["featurize", "md", "fit"],
                     help="featurize = BASELINE.json headline (default); md = configs[4] MD loop, strong scaling; "

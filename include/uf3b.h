@@ -83,6 +83,9 @@ int uf3b_abi_version(void);
 
 /* Device used by subsequent create calls (default: current device). */
 int uf3b_set_device(int device);
+/* Host waits inside the library sleep on a blocking event instead of spinning in
+ * cudaStreamSynchronize (process-wide; for hosts where ranks x pipeline workers outnumber cores). */
+int uf3b_set_blocking_sync(int enabled);
 
 /* -- basis ------------------------------------------------------------------------ */
 /* replaces: BSplineBasis.update_basis_functions / generate_basis_functions
@@ -174,6 +177,19 @@ int uf3b_pipeline_submit(uf3b_pipeline *pipe, int64_t n_atoms, const double *pos
                          const int32_t *image_abc, double *x_energy, double *x_forces, int64_t ld,
                          int64_t *ticket);
 int uf3b_pipeline_wait(uf3b_pipeline *pipe, int64_t ticket);
+/* Fit job: the same frame through uf3b_neighbors_build + uf3b_featurize with the 3N x F force rows
+ * LEFT IN HBM, then uf3b_gram_accumulate into the slot's own normal-equation accumulator — what
+ * BasisFeaturizer.batched_to_hdf + WeightedLinearModel.fit_from_file do through an HDF5 file
+ * (process.py:256-291, least_squares.py:355-433).  y_forces: host targets [3N] in row order
+ * (fx_0.., fy_0.., fz_0..) or NULL for an energy-only frame; x_energy: host array [F] that receives
+ * the frame's energy row (or NULL).  Only positions and targets go up; F doubles come back. */
+int uf3b_pipeline_submit_fit(uf3b_pipeline *pipe, int64_t n_atoms, const double *positions,
+                             const int32_t *atomic_numbers, int32_t n_images, const double *image_offsets,
+                             const int32_t *image_abc, const double *y_forces, double *x_energy,
+                             int64_t *ticket);
+/* Waits for every slot, then sums the slots' force accumulators: gram_out [F*F] row-major, ord_out [F],
+ * moments_out [3] = number of force targets, their sum and sum of squares (any may be NULL). */
+int uf3b_pipeline_export_gram(uf3b_pipeline *pipe, double *gram_out, double *ord_out, double *moments_out);
 void uf3b_pipeline_destroy(uf3b_pipeline *pipe);
 
 /* -- analysis ----------------------------------------------------------------------- */

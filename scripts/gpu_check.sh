@@ -14,7 +14,7 @@ for what in "$@"; do
       tail -2 gpurun_out/${tag}_bench_man.err; cat gpurun_out/${tag}_bench_manuscript.json ;;
     ncu)
       ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-        python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 ;;
+        python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1 ;;
     ncufull)
       ncu --set full --clock-control none --import-source on -k regex:k_featurize -s 3 -c 1 -f -o gpurun_out/${tag}_featurize \
         python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncufull.log 2>&1

@@ -422,3 +422,55 @@ def test_accumulate_frames_sharded():
         host.add_force_rows(c["x_forces"], f.reshape(-1))
     ref = host.to_vector()
     assert np.abs(whole - ref).max() <= 1e-8 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_fit_pipeline_matches_host_gram_and_keeps_errors():
+    """uf3b_pipeline_submit_fit (distributed.accumulate_frames_pipelined): the rows stay in HBM, the
+    normal equations summed over the slots equal the ones built on the host from the reference
+    rows; the shards of two ranks add up to the whole; a failing frame nobody waited for is
+    reported by a later call instead of being lost."""
+    from uf3_b200 import _native, distributed
+    from uf3_b200.pipeline import NativePipeline
+    names = ("syn_w16_demo", "syn_w54_demo", "syn_w36_slab", "syn_w128_demo", "syn_w54_demo")
+    cases = [gu.Case(n) for n in names]
+    basis = cases[0].basis()
+    F = basis.n_feats
+    rng = np.random.default_rng(5)
+    frames = [(c.atoms(), float(rng.normal()), rng.normal(size=(3, len(c.numbers)))) for c in cases]
+    frames[2] = (frames[2][0], frames[2][1], None)          # an energy-only frame
+    whole = distributed.accumulate_frames_pipelined(basis, frames, depth=3).to_vector()
+    parts = sum(distributed.accumulate_frames_pipelined(basis, frames, rank=r, world_size=2, depth=2).to_vector()
+                for r in range(2))
+    assert np.allclose(parts, whole, rtol=1e-10, atol=1e-10)
+    host = ls.GramStats(F)
+    for c, (_, e, f) in zip(cases, frames):
+        host.add_energy_row(c["x_energy"], e, len(c.numbers))
+        if f is not None:
+            host.add_force_rows(c["x_forces"], f.reshape(-1))
+    ref = host.to_vector()
+    assert np.abs(whole - ref).max() <= 1e-8 * np.abs(ref).max()
+    # sticky error: the bad frame's slot is reused before anybody waits for it
+    pipe = NativePipeline(basis, depth=1)
+    none = (np.zeros((1, 3), dtype=np.int64), np.zeros((1, 3)))
+    pipe.submit_fit(np.zeros((2, 3)), np.array([74, 26], dtype=np.int32), none, None, np.zeros(F))
+    with pytest.raises(_native.UF3BError):
+        pipe.submit_fit(np.zeros((1, 3)), np.array([74], dtype=np.int32), none, None, np.zeros(F))
+    with pytest.raises(_native.UF3BError):
+        pipe.export_gram()
+    pipe.close()
+    # argument validation happens at submit()
+    pipe = NativePipeline(basis, depth=2)
+    with pytest.raises(_native.UF3BError):
+        pipe._native.check(pipe._lib.uf3b_pipeline_submit(pipe._pipe, -1, None, None, 1, None, None, None, None, F, None))
+    pipe.close()
+
+
+@pytest.mark.gpu
+def test_singular_normal_equations_are_an_error():
+    """uf3b_solve reports a zero pivot of the factorisation instead of returning inf / NaN."""
+    from uf3_b200 import _native
+    a = np.zeros((4, 4))
+    a[0, 0] = a[1, 1] = 1.0
+    with pytest.raises(_native.UF3BError):
+        ls.device_solve(a, np.ones(4))

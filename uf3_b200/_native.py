@@ -48,6 +48,7 @@ SIGNATURES = {
     "uf3b_last_error": (C.c_char_p, []),
     "uf3b_abi_version": (C.c_int, []),
     "uf3b_set_device": (C.c_int, [C.c_int]),
+    "uf3b_set_blocking_sync": (C.c_int, [C.c_int]),
     "uf3b_basis_create": (C.c_int, [C.POINTER(BasisDesc), C.POINTER(C.c_void_p)]),
     "uf3b_basis_set_coefficients": (C.c_int, [C.c_void_p, _f64p, C.c_int32]),
     "uf3b_basis_set_frames_in_flight": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -73,6 +74,9 @@ SIGNATURES = {
     "uf3b_pipeline_submit": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]),
     "uf3b_pipeline_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "uf3b_pipeline_submit_fit": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, _i64p]),
+    "uf3b_pipeline_export_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uf3b_pipeline_destroy": (None, [C.c_void_p]),
     "uf3b_pair_histogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "uf3b_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

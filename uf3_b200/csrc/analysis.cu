@@ -60,6 +60,6 @@ extern "C" int uf3b_pair_histogram(uf3b_basis *basis, const uf3b_nlist *nl, cons
         UF3B_LAUNCH(k_pair_histogram, blocks, 256, 0, stream, basis->tab, nl->view(), d_edges.p, n_bins, d_hist.p);
     }
     UF3B_CUDA(cudaMemcpyAsync(counts, d_hist.p, sizeof(long long) * n_out, cudaMemcpyDefault, stream));
-    UF3B_CUDA(cudaStreamSynchronize(stream));
+    UF3B_CUDA(stream_sync(stream));
     return UF3B_OK;
 }

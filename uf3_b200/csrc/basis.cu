@@ -30,6 +30,19 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+static std::atomic<bool> g_blocking_sync{false};
+
+cudaError_t stream_sync(cudaStream_t stream) {
+    if (!g_blocking_sync.load(std::memory_order_relaxed)) return cudaStreamSynchronize(stream);
+    thread_local cudaEvent_t ev = nullptr;
+    if (!ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) { ev = nullptr; return e; }
+    }
+    cudaError_t e = cudaEventRecord(ev, stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ev);
+}
+
 int sm_count() {
     static int cached = 0;
     if (!cached) {
@@ -71,6 +84,11 @@ int uf3b_set_timing(int enabled) {
     return UF3B_OK;
 }
 double uf3b_last_kernel_ms(void) { return g_last_kernel_ms; }
+
+int uf3b_set_blocking_sync(int enabled) {
+    g_blocking_sync.store(enabled != 0);
+    return UF3B_OK;
+}
 
 int uf3b_set_device(int device) {
     UF3B_CUDA(cudaSetDevice(device));

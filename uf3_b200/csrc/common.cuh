@@ -73,6 +73,11 @@ inline bool is_device_pointer(const void *ptr) {
 
 int sm_count();
 
+// Host wait for `stream`.  Default: cudaStreamSynchronize (spins: lowest latency).  With
+// uf3b_set_blocking_sync(1) the thread sleeps on an event created with cudaEventBlockingSync
+// instead — for hosts where ranks x pipeline workers outnumber the cores.
+cudaError_t stream_sync(cudaStream_t stream);
+
 // ------------------------------------------------------------------ device tables
 // Flattened BSplineBasis on the device.  Pair p = (a<=b) -> a*ne - a*(a-1)/2 + (b-a);
 // trio t = centre*n_pairs + pair(j,k).  Every knot vector owns (n_knots - 7) cubic

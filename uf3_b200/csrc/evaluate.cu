@@ -362,7 +362,7 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
         UF3B_CUDA(cudaMemcpyAsync(energy, d_e, sizeof(double), cudaMemcpyDeviceToHost, stream));
         need_sync = true;
     }
-    if (need_sync) UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (need_sync) UF3B_CUDA(stream_sync(stream));
     if (virial) {
         const double full[9] = {h_sums[1], h_sums[6], h_sums[5], h_sums[6], h_sums[2], h_sums[4],
                                 h_sums[5], h_sums[4], h_sums[3]};

@@ -1422,7 +1422,7 @@ int uf3b::finish_featurize(uf3b_basis *basis, double *x_energy, double *x_forces
         UF3B_CUDA(cudaMemcpyAsync(x_energy, d_xe, sizeof(double) * F, cudaMemcpyDeviceToHost, stream));
         need_sync = true;
     }
-    if (need_sync) UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (need_sync) UF3B_CUDA(stream_sync(stream));
     if (g_timing) {
         float ms = 0.f;
         UF3B_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));

@@ -192,7 +192,7 @@ int uf3b_gram_accumulate(uf3b_gram *gm, const double *x, const double *y, int64_
                              gm->b[which], 1);
         if (st != CUBLAS_STATUS_SUCCESS) return fail(UF3B_ERR_CUDA, "cuBLAS dsyrk/dgemv status %d", (int)st);
         g_launches.fetch_add(2, std::memory_order_relaxed);
-        if (dx != x || dy != y) UF3B_CUDA(cudaStreamSynchronize(stream));
+        if (dx != x || dy != y) UF3B_CUDA(stream_sync(stream));
         return UF3B_OK;
     }
     const int nb = (gm->n_cols + GT - 1) / GT;
@@ -208,7 +208,7 @@ int uf3b_gram_accumulate(uf3b_gram *gm, const double *x, const double *y, int64_
     if (ny > 65535) return fail(UF3B_ERR_CAPACITY, "too many rows in one call (max %d)", 65535 * OROWS);
     UF3B_LAUNCH(k_ordinate, dim3((gm->n_cols + 31) / 32, ny), 256, 0, stream, dx, dld, dy, (long long)rows,
                 gm->n_cols, gm->b[which]);
-    if (dx != x || dy != y) UF3B_CUDA(cudaStreamSynchronize(stream));
+    if (dx != x || dy != y) UF3B_CUDA(stream_sync(stream));
     return UF3B_OK;
 }
 

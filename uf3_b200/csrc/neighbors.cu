@@ -628,7 +628,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     UF3B_CUDA(cudaMemcpyAsync(nl->img_off.p, image_offsets, sizeof(double) * 3 * n_images, cudaMemcpyDefault, stream));
     UF3B_CUDA(cudaMemcpyAsync(nl->img_inv.p, inv.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, stream));
     if (n == 0) {
-        UF3B_CUDA(cudaStreamSynchronize(stream));
+        UF3B_CUDA(stream_sync(stream));
         guard.armed = false;
         *inout = nl;
         return UF3B_OK;
@@ -660,7 +660,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     int h_err = 0;
     if (!reuse) {
         UF3B_LAUNCH(k_post_small, 1, 32, 0, stream, nl->misc.p, nl->h_mapped, 7);
-        UF3B_CUDA(cudaStreamSynchronize(stream));
+        UF3B_CUDA(stream_sync(stream));
         memcpy(h_misc, nl->h_mapped, sizeof h_misc);
         memcpy(&h_err, &h_misc[6], sizeof h_err);
     }
@@ -761,7 +761,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
                     nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status, claims);
         UF3B_LAUNCH(k_post_status, 1, 32, 0, stream, claims, status, (volatile int *)(nl->h_mapped + 8), nl->misc.p,
                     chk);
-        UF3B_CUDA(cudaStreamSynchronize(stream));
+        UF3B_CUDA(stream_sync(stream));
         memcpy(h_status, nl->h_mapped + 8, sizeof h_status);
         if (reuse) {
             if (h_status[7] & 1) return fail(UF3B_ERR_ELEMENT, "configuration holds an element outside the basis");

@@ -32,7 +32,13 @@ extern "C" int uf3b_solve(const double *a, const double *b, int32_t n, int32_t n
     if (!a || !b || !x || n < 1 || n_rhs < 1) return fail(UF3B_ERR_INVALID, "bad argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = UF3B_OK;
-    cusolverDnHandle_t handle = nullptr;
+    // one cuSOLVER handle per host thread and device, kept for the life of the process: creating
+    // it costs tens of milliseconds, more than a p = 73 solve itself
+    static thread_local cusolverDnHandle_t t_handle[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cusolverDnHandle_t local = nullptr;
+    cusolverDnHandle_t &handle = (dev >= 0 && dev < 16) ? t_handle[dev] : local;
     double *d_a = nullptr, *d_b = nullptr, *d_work = nullptr;
     int *d_piv = nullptr, *d_info = nullptr;
     int lwork = 0, h_info = 0;
@@ -44,18 +50,26 @@ extern "C" int uf3b_solve(const double *a, const double *b, int32_t n, int32_t n
     // `a` is row-major: LAPACK sees its transpose, so the solve below uses op = T
     UF3B_CUDA_GOTO(cudaMemcpyAsync(d_a, a, a_bytes, cudaMemcpyDefault, stream));
     UF3B_CUDA_GOTO(cudaMemcpyAsync(d_b, b, b_bytes, cudaMemcpyDefault, stream));   // [n_rhs][n]: column-major n x n_rhs
-    UF3B_SOLVER(cusolverDnCreate(&handle));
+    if (!handle) UF3B_SOLVER(cusolverDnCreate(&handle));
     UF3B_SOLVER(cusolverDnSetStream(handle, stream));
     UF3B_SOLVER(cusolverDnDgetrf_bufferSize(handle, n, n, d_a, n, &lwork));
     UF3B_CUDA_GOTO(cudaMalloc((void **)&d_work, sizeof(double) * (size_t)std::max(lwork, 1)));
     UF3B_SOLVER(cusolverDnDgetrf(handle, n, n, d_a, n, d_work, d_piv, d_info));
+    // the factorisation's status is read before getrs overwrites devInfo with its own: a zero pivot
+    // (all-zero regulariser with uncovered columns) must not come back as inf / NaN coefficients
+    UF3B_CUDA_GOTO(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    UF3B_CUDA_GOTO(uf3b::stream_sync(stream));
+    if (h_info != 0) {
+        rc = fail(UF3B_ERR_STATE, "singular normal equations (getrf info %d)", h_info);
+        goto done;
+    }
     UF3B_SOLVER(cusolverDnDgetrs(handle, CUBLAS_OP_T, n, n_rhs, d_a, n, d_piv, d_b, n, d_info));
     UF3B_CUDA_GOTO(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, stream));
     UF3B_CUDA_GOTO(cudaMemcpyAsync(x, d_b, b_bytes, cudaMemcpyDefault, stream));
-    UF3B_CUDA_GOTO(cudaStreamSynchronize(stream));
-    if (h_info != 0) rc = fail(UF3B_ERR_STATE, "singular normal equations (getrf info %d)", h_info);
+    UF3B_CUDA_GOTO(uf3b::stream_sync(stream));
+    if (h_info != 0) rc = fail(UF3B_ERR_INVALID, "getrs rejected its arguments (info %d)", h_info);
 done:
-    if (handle) cusolverDnDestroy(handle);
+    if (local) cusolverDnDestroy(local);
     cudaFree(d_a);
     cudaFree(d_b);
     cudaFree(d_work);

@@ -84,6 +84,61 @@ def accumulate_frames(featurizer, frames, stats=None, rank=0, world_size=1):
     return stats
 
 
+def accumulate_frames_pipelined(basis, frames, stats=None, rank=0, world_size=1, device=None, depth=4,
+                                fit_forces=True):
+    """This rank's share of `frames` through the library's own frame pipeline in FIT mode
+    (`uf3b_pipeline_submit_fit`): host positions / targets in, force rows left in HBM and folded
+    into the slots' normal-equation accumulators, one energy row (F doubles) back per frame.
+    Nothing else crosses PCIe, so the throughput does not depend on the host's ingest bandwidth
+    (the rows-to-host path is bound by it: 17.5 MB per 10 000-atom frame at 73 columns).
+
+    frames: sequence of (geom, energy, forces) with forces shaped (3, N) or None; `geom` anything
+    `uf3_b200.atoms.frame_arrays` understands.  Returns `GramStats` (host) holding this rank's
+    sums; `all_reduce_stats` then makes them global with ONE collective — the replacement of
+    `batched_to_hdf` + `fit_from_file` (process.py:256-291, least_squares.py:355-433)."""
+    from uf3_b200 import geometry
+    from uf3_b200.atoms import frame_arrays
+    from uf3_b200.least_squares import GramStats
+    from uf3_b200.pipeline import NativePipeline
+
+    pipe = NativePipeline(basis, depth=depth, device=device)
+    F = pipe.n_feats
+    if stats is None:
+        stats = GramStats(F)
+    r_cut = basis.r_cut
+    pending = []
+
+    def finish(item):
+        ticket, xe, energy, n = item
+        pipe.wait(ticket)
+        if energy is not None and n > 0:
+            stats.add_energy_row(xe, energy, n)
+
+    try:
+        for geom, energy, forces in shard(frames, rank, world_size):
+            positions, numbers, cell, pbc = frame_arrays(geom)
+            images = geometry.image_table(cell, pbc, r_cut) if np.any(pbc) else \
+                (np.zeros((1, 3), dtype=np.int64), np.zeros((1, 3)))
+            y = None
+            if forces is not None and fit_forces and len(positions) > 0:
+                y = np.ascontiguousarray(forces, dtype=np.float64).reshape(-1)
+            xe = np.zeros(F)
+            pending.append((pipe.submit_fit(np.ascontiguousarray(positions, dtype=np.float64),
+                                            np.ascontiguousarray(numbers, dtype=np.int32), images, y, xe),
+                            xe, energy, len(positions)))
+            if len(pending) == depth:
+                finish(pending.pop(0))
+        while pending:
+            finish(pending.pop(0))
+        gram_f, ord_f, moments = pipe.export_gram()
+    finally:
+        pipe.close()
+    stats.gram_f += gram_f
+    stats.ord_f += ord_f
+    stats.moments[3:6] += moments
+    return stats
+
+
 def atom_range(n_atoms, rank, world_size):
     """Contiguous, balanced atom range (first, count) of `rank`."""
     base, rem = divmod(int(n_atoms), int(world_size))

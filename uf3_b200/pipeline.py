@@ -136,6 +136,37 @@ class NativePipeline:
     def wait(self, ticket):
         self._native.check(self._lib.uf3b_pipeline_wait(self._pipe, int(ticket)))
 
+    def submit_fit(self, positions, numbers, images, y_forces, out_energy):
+        """Fit job: the frame's force rows stay in HBM and go straight into the slot's normal-equation
+        accumulator (`uf3b_pipeline_submit_fit`).  y_forces: (3n,) float64 targets in row order
+        (fx_0.., fy_0.., fz_0..) or None; out_energy: (F,) float64 array receiving the energy row."""
+        C = self._C
+        abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
+        offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
+        if positions.dtype != np.float64 or numbers.dtype != np.int32 or not positions.flags.c_contiguous:
+            raise ValueError("positions must be C-contiguous float64 and numbers int32")
+        if y_forces is not None and (y_forces.dtype != np.float64 or y_forces.size != 3 * len(positions)
+                                     or not y_forces.flags.c_contiguous):
+            raise ValueError("y_forces must be C-contiguous float64 with one target per force row")
+        ticket = C.c_int64()
+        self._native.check(self._lib.uf3b_pipeline_submit_fit(
+            self._pipe, len(positions), C.c_void_p(positions.ctypes.data), C.c_void_p(numbers.ctypes.data),
+            len(offsets), C.c_void_p(offsets.ctypes.data), C.c_void_p(abc.ctypes.data),
+            C.c_void_p(y_forces.ctypes.data) if y_forces is not None else None,
+            C.c_void_p(out_energy.ctypes.data) if out_energy is not None else None, C.byref(ticket)))
+        self._keep[ticket.value % self.depth] = (positions, numbers, y_forces, out_energy)
+        return ticket.value
+
+    def export_gram(self):
+        """(gram_f [F, F], ord_f [F], (n, sum y, sum y^2)) summed over the slots; waits for every frame."""
+        C = self._C
+        F = self.n_feats
+        gram, ordinate, moments = np.zeros((F, F)), np.zeros(F), np.zeros(3)
+        self._native.check(self._lib.uf3b_pipeline_export_gram(
+            self._pipe, C.c_void_p(gram.ctypes.data), C.c_void_p(ordinate.ctypes.data),
+            C.c_void_p(moments.ctypes.data)))
+        return gram, ordinate, moments
+
     def close(self):
         if getattr(self, "_pipe", None):
             self._lib.uf3b_pipeline_destroy(self._pipe)
