@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "common.cuh"
 #include "spline.cuh"
@@ -17,8 +19,8 @@ namespace uf3b {
 
 static thread_local std::string t_error;
 std::atomic<long long> g_launches{0};
-bool g_timing = false;
-double g_last_kernel_ms = 0.0;
+std::atomic<bool> g_timing{false};
+std::atomic<double> g_last_kernel_ms{0.0};
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -44,15 +46,29 @@ cudaError_t stream_sync(cudaStream_t stream) {
 }
 
 int sm_count() {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess
-            || cached <= 0)
-            cached = 148;
+    static std::atomic<int> cached[64];        // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    int n = cached[slot].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[slot].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
+}
+
+cudaError_t ensure_dynamic_smem(const void *kernel, size_t bytes) {
+    static std::mutex m;
+    static std::map<std::pair<int, const void *>, size_t> limit;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(m);
+    size_t &cur = limit[std::make_pair(dev, kernel)];
+    if (bytes <= cur || bytes <= 48 * 1024) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
 }
 
 namespace {
@@ -80,10 +96,10 @@ const char *uf3b_last_error(void) { return t_error.c_str(); }
 int uf3b_abi_version(void) { return UF3B_ABI_VERSION; }
 int64_t uf3b_launch_count(void) { return (int64_t)g_launches.load(); }
 int uf3b_set_timing(int enabled) {
-    g_timing = enabled != 0;
+    g_timing.store(enabled != 0);
     return UF3B_OK;
 }
-double uf3b_last_kernel_ms(void) { return g_last_kernel_ms; }
+double uf3b_last_kernel_ms(void) { return g_last_kernel_ms.load(); }
 
 int uf3b_set_blocking_sync(int enabled) {
     g_blocking_sync.store(enabled != 0);
@@ -291,6 +307,7 @@ int uf3b_basis_set_frames_in_flight(uf3b_basis *b, int32_t k) {
 int uf3b_basis_set_coefficients(uf3b_basis *b, const double *coefficients, int32_t n) {
     if (!b || !coefficients) return fail(UF3B_ERR_INVALID, "null argument");
     if (n != b->n_feats) return fail(UF3B_ERR_INVALID, "expected %d coefficients, got %d", b->n_feats, n);
+    DeviceGuard on_device(b->device);
     // decompress_3B as a gather (bspline.py:693-719): grid[bin] = c[col(bin)] * w(bin)
     std::vector<double> grid(b->n_bins > 0 ? b->n_bins : 1, 0.0);
     const int n_trios = b->tab.n_trios;

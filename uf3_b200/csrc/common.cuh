@@ -15,8 +15,8 @@ namespace uf3b {
 // ------------------------------------------------------------------ host utilities
 int fail(int code, const char *fmt, ...);
 extern std::atomic<long long> g_launches;
-extern bool g_timing;
-extern double g_last_kernel_ms;
+extern std::atomic<bool> g_timing;            // read and written by the pipeline's worker threads
+extern std::atomic<double> g_last_kernel_ms;
 
 #define UF3B_CUDA(expr)                                                                   \
     do {                                                                                  \
@@ -71,7 +71,24 @@ inline bool is_device_pointer(const void *ptr) {
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
-int sm_count();
+int sm_count();      // of the current device
+
+// Raises a kernel's dynamic shared-memory limit to at least `bytes` and never lowers it: handles
+// with different bases (and the pipeline's worker threads) share the kernels, so a per-call exact
+// value could shrink the limit between another thread's call and its launch.
+cudaError_t ensure_dynamic_smem(const void *kernel, size_t bytes);
+
+// Makes the handle's device current for the duration of a C-ABI call and restores the caller's.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 // Host wait for `stream`.  Default: cudaStreamSynchronize (spins: lowest latency).  With
 // uf3b_set_blocking_sync(1) the thread sleeps on an event created with cudaEventBlockingSync

@@ -278,6 +278,7 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     if (!basis || !nl) return fail(UF3B_ERR_INVALID, "null handle");
     if (!basis->has_coeff) return fail(UF3B_ERR_STATE, "coefficients not set");
     if (!energy && !forces && !virial) return UF3B_OK;
+    DeviceGuard on_device(basis->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n = (int)nl->n;
     const bool e_dev = energy && is_device_pointer(energy);
@@ -312,7 +313,7 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
             st.knots3 = basis->n_knots3; st.poly3 = basis->n_poly3; smem += trio_b;
         }
     }
-    if (smem > 48 * 1024) UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UF3B_CUDA(ensure_dynamic_smem((const void *)kernel, smem));
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EV_WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;

@@ -1436,6 +1436,7 @@ int uf3b::finish_featurize(uf3b_basis *basis, double *x_energy, double *x_forces
 extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy,
                               double *x_forces, int64_t ld, void *stream_) {
     if (!basis || !nl) return fail(UF3B_ERR_INVALID, "null handle");
+    DeviceGuard on_device(basis->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int F = basis->n_feats;
     const int n = (int)nl->n;
@@ -1535,7 +1536,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         const size_t smem_c = (size_t)cg.off_warp + (size_t)cg.warps * cg.warp_bytes;
         auto kc = tg.la <= 4 ? k_featurize_coop<4> : k_featurize_coop<8>;
         if (smem_c <= (size_t)smem_max) {
-            UF3B_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+            UF3B_CUDA(ensure_dynamic_smem((const void *)kc, smem_c));
             int per_sm = 1;
             UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc, cg.warps * 32, smem_c));
             if (per_sm < 1) per_sm = 1;
@@ -1597,7 +1598,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         case 7: kernel = k_featurize<false, 7>; break;
         default: break;
     }
-    UF3B_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UF3B_CUDA(ensure_dynamic_smem((const void *)kernel, smem));
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;

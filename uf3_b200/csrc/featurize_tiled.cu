@@ -892,8 +892,8 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     TiledGeom tgc = tg;
     tgc.off_warps = (int)tab_c;
     tgc.warp_bytes = (int)warp_c;
-    UF3B_CUDA(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n));
-    UF3B_CUDA(cudaFuncSetAttribute(k_ctr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    UF3B_CUDA(ensure_dynamic_smem((const void *)k_nbr, smem_n));
+    UF3B_CUDA(ensure_dynamic_smem((const void *)k_ctr, smem_c));
     int per_sm_n = 1, per_sm_c = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_n, k_nbr, warps * 32, smem_n));
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_ctr, warps_c * 32, smem_c));

@@ -590,6 +590,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     if (!image_offsets || !image_abc) return fail(UF3B_ERR_INVALID, "null image table");
     const long long n_sup = (long long)n_atoms * n_images;
     if (n_sup >= (1LL << 31) - 64) return fail(UF3B_ERR_CAPACITY, "supercell exceeds int32 indices");
+    DeviceGuard on_device(basis->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool created = (*inout == nullptr);
     uf3b_nlist *nl = created ? new uf3b_nlist() : *inout;

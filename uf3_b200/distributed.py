@@ -53,12 +53,14 @@ def accumulate_frames(featurizer, frames, stats=None, rank=0, world_size=1):
     F = eng.n_feats
     if stats is None:
         stats = GramAccumulator(F)
-    stream = torch.cuda.current_stream().cuda_stream
+    # every tensor lives on the ENGINE's device, and the kernels run on that device's current stream
+    dev = torch.device("cuda", eng.device if getattr(eng, "device", None) is not None else torch.cuda.current_device())
+    stream = torch.cuda.current_stream(dev).cuda_stream
     mine = shard(frames, rank, world_size)
     # energy rows stay on the device until the end (one small copy for the whole shard) and the
     # force targets go up asynchronously, so a frame costs no host synchronisation beyond the
     # one inside its list build
-    xe_all = torch.zeros((max(len(mine), 1), F), dtype=torch.float64, device="cuda")
+    xe_all = torch.zeros((max(len(mine), 1), F), dtype=torch.float64, device=dev)
     rows = None
     energy_rows = []
     for k, (geom, energy, forces) in enumerate(mine):
@@ -68,13 +70,13 @@ def accumulate_frames(featurizer, frames, stats=None, rank=0, world_size=1):
         n = len(positions)
         want_f = forces is not None and featurizer.fit_forces and n > 0
         if want_f and (rows is None or rows.shape[0] < 3 * n):
-            rows = torch.empty((3 * n, F), dtype=torch.float64, device="cuda")
+            rows = torch.empty((3 * n, F), dtype=torch.float64, device=dev)
         eng.featurize_device(xe_all[k].data_ptr(), rows.data_ptr() if want_f else None, F, stream)
         if energy is not None:
             energy_rows.append((k, float(energy), n))
         if want_f:
             y = np.ascontiguousarray(forces, dtype=np.float64).reshape(-1)
-            y_dev = torch.from_numpy(y).to("cuda", non_blocking=True)
+            y_dev = torch.from_numpy(y).to(dev, non_blocking=True)
             stats.add_force_rows_device(rows.data_ptr(), y_dev.data_ptr(), 3 * n, F, stream,
                                         y_moments=(float(y.sum()), float(np.dot(y, y))))
             del y_dev        # freed by torch's caching allocator in stream order

@@ -22,6 +22,10 @@ class Engine:
         """`frames_in_flight` = k: this engine is one of k working on consecutive frames on k
         streams; its feature kernels then take 1/k of the SM resources per launch."""
         self._lib = _native.lib()
+        # the basis handle remembers the device it was created on and every C-ABI call that takes
+        # it makes that device current for its duration (DeviceGuard), so engines on different
+        # GPUs can be driven from one thread
+        self.device = None if device is None else int(device)
         if device is not None:
             _native.check(self._lib.uf3b_set_device(int(device)))
         self.tables = BasisTables(basis)
