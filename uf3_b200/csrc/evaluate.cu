@@ -17,6 +17,7 @@
 // its list and adds only its own share — no atomics, bit-reproducible, 3x the triangles.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -68,13 +69,28 @@ constexpr int EV_WARPS = 4;
 // Table sizes (doubles) for staging the spline tables in shared memory; 0 = leave in global.
 struct EvalStage { int knots2, poly2, knots3, poly3; };
 
-template <bool NEWTON, bool VIRIAL>
+// One neighbour of the centre in the per-warp table (leg table path, see k_energy_forces).
+// x y z {atom | species} | (B, dB) x 4 of the leg (centre, neighbour) | r {first index, lo | cnt << 8} | pad:
+// 144 bytes, an odd multiple of 16, so that lanes reading the same field of different records spread over
+// the banks (with 128 the table reads cost 4-5 wavefronts too many each)
+constexpr unsigned NB_REC = 144;
+constexpr int PS_SMEM = 18;         // doubles between polynomial pieces staged in shared memory (spline.cuh)
+
+// PADDED: the spline tables are staged in shared memory, pieces PS_SMEM doubles apart.
+// leg_table (unary basis whose two centre legs share their knots, NEWTON scheme): every leg
+// (centre, neighbour) is evaluated ONCE per centre into the warp's neighbour table — the per-triangle
+// form evaluated it once per triangle, 13 times in bulk W — with the trims applied, and the 4 x 4 x 4
+// contraction only walks the basis functions the trims keep (their coefficients are the only
+// non-zero ones: decompress_3B scatters into the untrimmed bins, bspline.py:693-719), 2 x 2 x 4 of
+// the 64 terms on average for the W model.
+template <bool NEWTON, bool VIRIAL, bool PADDED>
 __global__ void __launch_bounds__(EV_WARPS * 32, 4)
 k_energy_forces(const BasisTab B_, const FrameView f, double *forces,
                 double *__restrict__ e_partials, int want_e_, int want_f_, int n_grid, int grid_in_smem,
-                const EvalStage st) {
+                const EvalStage st, int leg_table) {
+    constexpr int PS = PADDED ? PS_SMEM : 16;
     __shared__ RoleViews s_views[EV_WARPS];
-    __shared__ double4 s_nbr[EV_WARPS * 32];
+    __shared__ __align__(16) unsigned char s_nbr_raw[EV_WARPS * 32 * NB_REC];
     extern __shared__ __align__(16) double s_grid[];
     // knots and polynomial pieces are read ~14 times per leg: staged in shared memory next to
     // the coefficient grids (the capture of the global-table version showed long-scoreboard
@@ -85,14 +101,14 @@ k_energy_forces(const BasisTab B_, const FrameView f, double *forces,
         if (st.knots2 > 0) {
             for (int k = threadIdx.x; k < st.knots2; k += blockDim.x) dst[k] = B_.knots2[k];
             B.knots2 = dst; dst += (st.knots2 + 1) & ~1;
-            for (int k = threadIdx.x; k < st.poly2; k += blockDim.x) dst[k] = B_.poly2[k];
-            B.poly2 = dst; dst += (st.poly2 + 1) & ~1;
+            for (int k = threadIdx.x; k < st.poly2; k += blockDim.x) dst[(k >> 4) * PS + (k & 15)] = B_.poly2[k];
+            B.poly2 = dst; dst += (st.poly2 / 16) * PS;
         }
         if (st.knots3 > 0) {
             for (int k = threadIdx.x; k < st.knots3; k += blockDim.x) dst[k] = B_.knots3[k];
             B.knots3 = dst; dst += (st.knots3 + 1) & ~1;
-            for (int k = threadIdx.x; k < st.poly3; k += blockDim.x) dst[k] = B_.poly3[k];
-            B.poly3 = dst; dst += (st.poly3 + 1) & ~1;
+            for (int k = threadIdx.x; k < st.poly3; k += blockDim.x) dst[(k >> 4) * PS + (k & 15)] = B_.poly3[k];
+            B.poly3 = dst; dst += (st.poly3 / 16) * PS;
         }
     }
     if (grid_in_smem)
@@ -125,8 +141,8 @@ k_energy_forces(const BasisTab B_, const FrameView f, double *forces,
             const double d = dist_rn(pa, pj);
             const int pr = pair_index(B.ne, sa, __ldg(f.spec + aj));
             double v[4], dv[4];
-            const int idx = eval_leg<false>(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
-                                     B.poly2 + __ldg(B.pair_poff + pr), d, 0, 0, v, dv);
+            const int idx = eval_leg<false, PS>(B.knots2 + __ldg(B.pair_koff + pr), __ldg(B.pair_nk + pr), __ldg(B.pair_scale + pr),
+                                                B.poly2 + __ldg(B.pair_poff + pr) / 16 * PS, d, 0, 0, v, dv);
             if (idx < 0) continue;
             const double *c = B.coeff + __ldg(B.pair_col + pr) + idx;
             double s = 0.0, ds = 0.0;
@@ -152,28 +168,126 @@ k_energy_forces(const BasisTab B_, const FrameView f, double *forces,
             // per-warp table: a triangle then reads two entries instead of gathering two list
             // entries, two positions and two image offsets from global memory
             const bool staged = n3a <= 32;
-            double4 *nb = s_nbr + warp * 32;
+            const bool tab = staged && leg_table != 0 && NEWTON;
+            unsigned char *nb = s_nbr_raw + warp * 32 * NB_REC;
+            const unsigned nb_s = smem_addr(nb);
             __syncwarp();       // the previous centre's triangles may still be reading the table
             if (staged && lane < n3a) {
                 int aj;
                 const Vec3 pj = super_position(f, __ldg(f.idx3 + row0 + lane), aj);
-                nb[lane] = make_double4(pj.x, pj.y, pj.z,
-                                        __longlong_as_double(((long long)__ldg(f.spec + aj) << 32) | (unsigned)aj));
+                const unsigned rec = nb_s + NB_REC * (unsigned)lane;
+                sts128(rec, make_double2(pj.x, pj.y));
+                sts128(rec + 16, make_double2(pj.z, __longlong_as_double(((long long)__ldg(f.spec + aj) << 32) | (unsigned)aj)));
+                if (tab) {      // the leg (centre, neighbour), trims applied
+                    const double d = dist_rn(pa, pj);
+                    const int nkl = __ldg(B_.trio_nk);
+                    const double *tl = B.knots3 + __ldg(B_.trio_koff);
+                    double v[4] = {0.0, 0.0, 0.0, 0.0}, dv[4] = {0.0, 0.0, 0.0, 0.0};
+                    int idx = -1, lo = 0, cnt = 0;
+                    if (d >= tl[0] && d <= tl[nkl - 1]) {          // angles.py:502-508
+                        idx = eval_leg<false, PS>(tl, nkl, __ldg(B_.trio_scale), B.poly3 + __ldg(B_.trio_poff) / 16 * PS, d,
+                                                  B.lead3, B.trail3, v, dv);
+                        if (idx >= 0) {
+                            lo = max(0, B.lead3 - idx);
+                            cnt = max(0, min(4, nkl - 4 - B.trail3 - idx) - lo);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sts128(rec + 32 + 16 * q, make_double2(v[q], dv[q]));
+                    const long long tag = ((long long)(lo | (cnt << 8)) << 32) | (unsigned)idx;
+                    sts128(rec + 96, make_double2(d, __longlong_as_double(tag)));
+                }
             }
             __syncwarp();
+            if (tab) {
+                const int nkn = __ldg(B_.trio_nk + 2);
+                const double *tn = B.knots3 + __ldg(B_.trio_koff + 2);
+                const double *pn = B.poly3 + __ldg(B_.trio_poff + 2) / 16 * PS;
+                const double scale_n = __ldg(B_.trio_scale + 2);
+                const int dim_m = __ldg(B_.trio_nk + 1) - 4, dim_n = nkn - 4, mn = dim_m * dim_n;
+                for (int t = lane; t < n_tri; t += 32) {
+                    int qj, qk;
+                    unrank_pair(t, qj, qk);
+                    const unsigned rj = nb_s + NB_REC * (unsigned)qj, rk = nb_s + NB_REC * (unsigned)qk;
+                    const double2 hj = lds128(rj + 96), hk = lds128(rk + 96);
+                    const long long tj = __double_as_longlong(hj.y), tk = __double_as_longlong(hk.y);
+                    const int il = (int)(tj & 0xffffffffll), im = (int)(tk & 0xffffffffll);
+                    const int lo_l = (int)(tj >> 32) & 0xff, cnt_l = (int)(tj >> 40) & 0xff;
+                    const int lo_m = (int)(tk >> 32) & 0xff, cnt_m = (int)(tk >> 40) & 0xff;
+                    if (il < 0 || im < 0 || cnt_l == 0 || cnt_m == 0) continue;
+                    const double2 jxy = lds128(rj), jzt = lds128(rj + 16), kxy = lds128(rk), kzt = lds128(rk + 16);
+                    const Vec3 pj = {jxy.x, jxy.y, jzt.x}, pk = {kxy.x, kxy.y, kzt.x};
+                    const double djk = dist_rn(pj, pk);
+                    if (!(djk >= tn[0] && djk <= tn[nkn - 1])) continue;
+                    double vn[4], dvn[4];
+                    const int in = eval_leg<false, PS>(tn, nkn, scale_n, pn, djk, B.lead3, B.trail3, vn, dvn);
+                    if (in < 0 || in + 4 <= B.lead3 || in >= dim_n - B.trail3) continue;
+                    // sum_pqr C[il+p, im+q, in+r] Bl_p Bm_q Bn_r and its three leg-partials over the kept
+                    // p, q (trimmed r have zero values)
+                    double val = 0.0, gl = 0.0, gm = 0.0, gn = 0.0;
+                    const double *base = c_grid + (il * dim_m + im) * dim_n + in;
+                    for (int p = lo_l; p < lo_l + cnt_l; ++p) {
+                        double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+                        for (int q = lo_m; q < lo_m + cnt_m; ++q) {
+                            const double *row = base + p * mn + q * dim_n;
+                            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const double c = row[r];
+                                t0 += c * vn[r];
+                                t1 += c * dvn[r];
+                            }
+                            const double2 m_ = lds128(rk + 32 + 16 * (unsigned)q);     // (B_m, dB_m)
+                            u0 += t0 * m_.x;
+                            u1 += t0 * m_.y;
+                            u2 += t1 * m_.x;
+                        }
+                        const double2 l_ = lds128(rj + 32 + 16 * (unsigned)p);         // (B_l, dB_l)
+                        val += u0 * l_.x;
+                        gl += u0 * l_.y;
+                        gm += u1 * l_.x;
+                        gn += u2 * l_.x;
+                    }
+                    e_acc += val;
+                    const double il_ = fast_rcp(hj.x), im_ = fast_rcp(hk.x), in_ = fast_rcp(djk);
+                    const double uij[3] = {(pj.x - pa.x) * il_, (pj.y - pa.y) * il_, (pj.z - pa.z) * il_};
+                    const double uik[3] = {(pk.x - pa.x) * im_, (pk.y - pa.y) * im_, (pk.z - pa.z) * im_};
+                    const double ujk[3] = {(pk.x - pj.x) * in_, (pk.y - pj.y) * in_, (pk.z - pj.z) * in_};
+                    fx += gl * uij[0] + gm * uik[0];
+                    fy += gl * uij[1] + gm * uik[1];
+                    fz += gl * uij[2] + gm * uik[2];
+                    if (VIRIAL) {
+                        add_virial(gl * hj.x, uij[0], uij[1], uij[2]);
+                        add_virial(gm * hk.x, uik[0], uik[1], uik[2]);
+                        add_virial(gn * djk, ujk[0], ujk[1], ujk[2]);
+                    }
+                    if (want_f) {       // reactions on the parent atoms of j and k
+                        const int atom_j = (int)(__double_as_longlong(jzt.y) & 0xffffffffll);
+                        const int atom_k = (int)(__double_as_longlong(kzt.y) & 0xffffffffll);
+                        double *fj = forces + 3 * (size_t)atom_j, *fk = forces + 3 * (size_t)atom_k;
+                        atomicAdd(fj + 0, -gl * uij[0] + gn * ujk[0]);
+                        atomicAdd(fj + 1, -gl * uij[1] + gn * ujk[1]);
+                        atomicAdd(fj + 2, -gl * uij[2] + gn * ujk[2]);
+                        atomicAdd(fk + 0, -gm * uik[0] - gn * ujk[0]);
+                        atomicAdd(fk + 1, -gm * uik[1] - gn * ujk[1]);
+                        atomicAdd(fk + 2, -gm * uik[2] - gn * ujk[2]);
+                    }
+                }
+            } else
             for (int t = lane; t < n_tri; t += 32) {
                 int qj, qk;
                 unrank_pair(t, qj, qk);
                 Triangle T;
                 if (staged) {
-                    const double4 ej = nb[qj], ek = nb[qk];
-                    const long long tj = __double_as_longlong(ej.w), tk = __double_as_longlong(ek.w);
-                    const Vec3 pj = {ej.x, ej.y, ej.z}, pk = {ek.x, ek.y, ek.z};
-                    if (!eval_triangle_at<false>(B, pa, sa, pj, (int)(tj & 0xffffffff), (int)(tj >> 32), pk,
-                                                 (int)(tk & 0xffffffff), (int)(tk >> 32), 0, 0, 0, T))
+                    const unsigned rj = nb_s + NB_REC * (unsigned)qj, rk = nb_s + NB_REC * (unsigned)qk;
+                    const double2 jxy = lds128(rj), jzt = lds128(rj + 16), kxy = lds128(rk), kzt = lds128(rk + 16);
+                    const long long tj = __double_as_longlong(jzt.y), tk = __double_as_longlong(kzt.y);
+                    const Vec3 pj = {jxy.x, jxy.y, jzt.x}, pk = {kxy.x, kxy.y, kzt.x};
+                    if (!eval_triangle_at<false, PS>(B, pa, sa, pj, (int)(tj & 0xffffffff), (int)(tj >> 32), pk,
+                                                     (int)(tk & 0xffffffff), (int)(tk >> 32), 0, 0, 0, T))
                         continue;
-                } else if (!eval_triangle<false>(B, f, pa, sa, __ldg(f.idx3 + row0 + qj), __ldg(f.idx3 + row0 + qk), 0,
-                                                 0, 0, T))
+                } else if (!eval_triangle<false, PS>(B, f, pa, sa, __ldg(f.idx3 + row0 + qj), __ldg(f.idx3 + row0 + qk), 0,
+                                                     0, 0, T))
                     continue;
                 double val, gl, gm, gn;
                 contract(c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
@@ -209,8 +323,8 @@ k_energy_forces(const BasisTab B_, const FrameView f, double *forces,
                         if (mk == apr) continue;
                         const bool first = apr < mk;
                         Triangle T;
-                        if (!eval_triangle<false>(B, f, real_position(f, ci), __ldg(f.spec + ci), first ? apr : mk,
-                                           first ? mk : apr, first ? 1 : 2, 0, 0, T))
+                        if (!eval_triangle<false, PS>(B, f, real_position(f, ci), __ldg(f.spec + ci), first ? apr : mk,
+                                                      first ? mk : apr, first ? 1 : 2, 0, 0, T))
                             continue;
                         double val, gl, gm, gn;
                         contract(c_grid + __ldg(B.trio_goff + T.trio), T, val, gl, gm, gn);
@@ -298,21 +412,39 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     const bool partial = nl->c_count < n;       // this rank owns a range of centres only
     const bool deterministic = getenv("UF3B_DETERMINISTIC_FORCES") != nullptr && !partial;
     const bool newton = (!deterministic && basis->tab.n_trios > 0) || partial;
-    auto kernel = virial ? (newton ? k_energy_forces<true, true> : k_energy_forces<false, true>)
-                         : (newton ? k_energy_forces<true, false> : k_energy_forces<false, false>);
     const int n_grid = basis->n_bins;
     const size_t grid_bytes = sizeof(double) * (size_t)n_grid;
     const int grid_in_smem = (n_grid > 0 && grid_bytes <= 48 * 1024) ? 1 : 0;
     size_t smem = grid_in_smem ? sizeof(double) * (size_t)((n_grid + 1) & ~1) : 0;
     EvalStage st = {0, 0, 0, 0};
-    {   // spline tables next to the coefficient grids while the block stays under 56 KB
-        const size_t pair_b = sizeof(double) * (size_t)(((basis->n_knots2 + 1) & ~1) + ((basis->n_poly2 + 1) & ~1));
-        const size_t trio_b = sizeof(double) * (size_t)(((basis->n_knots3 + 1) & ~1) + ((basis->n_poly3 + 1) & ~1));
-        if (smem + pair_b <= 56 * 1024) { st.knots2 = basis->n_knots2; st.poly2 = basis->n_poly2; smem += pair_b; }
-        if (basis->tab.n_trios > 0 && smem + trio_b <= 56 * 1024) {
-            st.knots3 = basis->n_knots3; st.poly3 = basis->n_poly3; smem += trio_b;
+    bool padded = false;
+    {   // spline tables next to the coefficient grids (pieces PS_SMEM doubles apart) while the block
+        // stays under 56 KB; both or neither, so that one piece stride serves the whole kernel
+        const size_t pair_b = sizeof(double) * (size_t)(((basis->n_knots2 + 1) & ~1) + basis->n_poly2 / 16 * PS_SMEM);
+        const size_t trio_b = basis->tab.n_trios > 0
+            ? sizeof(double) * (size_t)(((basis->n_knots3 + 1) & ~1) + basis->n_poly3 / 16 * PS_SMEM) : 0;
+        if (smem + pair_b + trio_b <= 56 * 1024) {
+            st.knots2 = basis->n_knots2; st.poly2 = basis->n_poly2;
+            if (basis->tab.n_trios > 0) { st.knots3 = basis->n_knots3; st.poly3 = basis->n_poly3; }
+            smem += pair_b + trio_b;
+            padded = true;
         }
     }
+    // leg table path: unary basis whose two centre legs share their knots (featurize_tiled.cu checks the same)
+    int leg_table = 0;
+    if (newton && basis->tab.n_trios == 1 && basis->tab.ne == 1 && !getenv("UF3B_NO_LEG_TABLE")
+        && basis->h_trio_dims[0] == basis->h_trio_dims[1]) {
+        leg_table = 1;
+        const double *k0 = basis->h_knots3.data() + basis->h_trio_koff[0], *k1 = basis->h_knots3.data() + basis->h_trio_koff[1];
+        for (int k = 0; k < basis->h_trio_dims[0] + 4; ++k)
+            if (k0[k] != k1[k]) leg_table = 0;
+    }
+    auto pick = [&](auto pad) {
+        constexpr bool P = decltype(pad)::value;
+        return virial ? (newton ? k_energy_forces<true, true, P> : k_energy_forces<false, true, P>)
+                      : (newton ? k_energy_forces<true, false, P> : k_energy_forces<false, false, P>);
+    };
+    auto kernel = padded ? pick(std::true_type{}) : pick(std::false_type{});
     UF3B_CUDA(ensure_dynamic_smem((const void *)kernel, smem));
     int per_sm = 1;
     UF3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EV_WARPS * 32, smem));
@@ -343,7 +475,7 @@ extern "C" int uf3b_energy_forces(uf3b_basis *basis, const uf3b_nlist *nl, doubl
     }
     if (newton && forces) UF3B_CUDA(cudaMemsetAsync(d_f, 0, sizeof(double) * 3 * (size_t)n, stream));
     UF3B_LAUNCH(kernel, grid, EV_WARPS * 32, smem, stream, basis->tab, view, d_f,
-                basis->partials.p, energy ? 1 : 0, forces ? 1 : 0, n_grid, grid_in_smem, st);
+                basis->partials.p, energy ? 1 : 0, forces ? 1 : 0, n_grid, grid_in_smem, st, leg_table);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
     if (energy || virial)
         UF3B_LAUNCH(k_energy_sum, virial ? 7 : 1, 256, 0, stream, basis->partials.p, n_gw, d_e);

@@ -37,8 +37,10 @@ UF3B_HD int find_interval(const double *t, int nk, double scale, double r) {
     return lo;
 }
 
-// Values and first derivatives of basis functions i-3..i at r (piece = poly + 16*(i-3)).
-// Pieces are 32-byte aligned (16 doubles each in a 32-byte aligned table).
+// Values and first derivatives of basis functions i-3..i at r (piece = poly + PS*(i-3)).
+// Pieces are 16-byte aligned (16 doubles each, PS doubles apart: 16 in the global tables; tables
+// staged in shared memory use PS = 18, because with the natural 128-byte stride every lane whose
+// distance falls into a different knot interval hits the same banks).
 // NC: read through the non-coherent global path (__ldg); false for tables staged in shared memory.
 template <bool NC = true>
 UF3B_HD void eval_piece(const double *piece, double u, double v[4], double dv[4]) {
@@ -60,12 +62,12 @@ UF3B_HD void eval_piece(const double *piece, double u, double v[4], double dv[4]
 
 // Full leg evaluation with trims (angles.py:554-565, bspline.py:840): returns the
 // first basis index or -1; basis indices outside [n_lead, n_basis - n_trail) give 0.
-template <bool NC = true>
+template <bool NC = true, int PS = 16>
 UF3B_HD int eval_leg(const double *t, int nk, double scale, const double *poly, double r, int n_lead,
                      int n_trail, double v[4], double dv[4]) {
     const int i = find_interval(t, nk, scale, r);
     if (i < 0) return -1;
-    eval_piece<NC>(poly + 16 * (i - 3), r - t[i], v, dv);
+    eval_piece<NC>(poly + PS * (i - 3), r - t[i], v, dv);
     const int idx = i - 3, nb = nk - 4;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

@@ -35,7 +35,7 @@ struct Triangle {
 // contributes nothing.
 // Same with the two neighbours given by position, parent atom and species (mj < mk by
 // supercell index, as in the centre's sorted list).
-template <bool NC = true>
+template <bool NC = true, int PS = 16>
 __device__ __forceinline__ bool eval_triangle_at(const BasisTab &B, const Vec3 &pc, int sc, Vec3 pj, int aj,
                                                  int sj, Vec3 pk, int ak, int sk, int role, int n_lead,
                                                  int n_trail, Triangle &T) {
@@ -57,9 +57,9 @@ __device__ __forceinline__ bool eval_triangle_at(const BasisTab &B, const Vec3 &
     if (!(dij >= tl[0] && dij <= tl[nkl - 1])) return false;      // angles.py:502-508
     if (!(dik >= tm[0] && dik <= tm[nkm - 1])) return false;
     if (!(djk >= tn[0] && djk <= tn[nkn - 1])) return false;
-    T.il = eval_leg<NC>(tl, nkl, __ldg(B.trio_scale + 3 * t), B.poly3 + __ldg(B.trio_poff + 3 * t), dij, n_lead, n_trail, T.v[0], T.dv[0]);
-    T.im = eval_leg<NC>(tm, nkm, __ldg(B.trio_scale + 3 * t + 1), B.poly3 + __ldg(B.trio_poff + 3 * t + 1), dik, n_lead, n_trail, T.v[1], T.dv[1]);
-    T.in = eval_leg<NC>(tn, nkn, __ldg(B.trio_scale + 3 * t + 2), B.poly3 + __ldg(B.trio_poff + 3 * t + 2), djk, n_lead, n_trail, T.v[2], T.dv[2]);
+    T.il = eval_leg<NC, PS>(tl, nkl, __ldg(B.trio_scale + 3 * t), B.poly3 + __ldg(B.trio_poff + 3 * t) / 16 * PS, dij, n_lead, n_trail, T.v[0], T.dv[0]);
+    T.im = eval_leg<NC, PS>(tm, nkm, __ldg(B.trio_scale + 3 * t + 1), B.poly3 + __ldg(B.trio_poff + 3 * t + 1) / 16 * PS, dik, n_lead, n_trail, T.v[1], T.dv[1]);
+    T.in = eval_leg<NC, PS>(tn, nkn, __ldg(B.trio_scale + 3 * t + 2), B.poly3 + __ldg(B.trio_poff + 3 * t + 2) / 16 * PS, djk, n_lead, n_trail, T.v[2], T.dv[2]);
     if (T.il < 0 || T.im < 0 || T.in < 0) return false;           // r exactly on the first knot
     T.trio = t;
     T.dim_m = nkm - 4;
@@ -93,13 +93,13 @@ __device__ __forceinline__ bool eval_triangle_at(const BasisTab &B, const Vec3 &
     return true;
 }
 
-template <bool NC = true>
+template <bool NC = true, int PS = 16>
 __device__ __forceinline__ bool eval_triangle(const BasisTab &B, const FrameView &f, const Vec3 &pc,
                                               int sc, int mj, int mk, int role, int n_lead,
                                               int n_trail, Triangle &T) {
     int aj, ak;
     const Vec3 pj = super_position(f, mj, aj), pk = super_position(f, mk, ak);
-    return eval_triangle_at<NC>(B, pc, sc, pj, aj, __ldg(f.spec + aj), pk, ak, __ldg(f.spec + ak), role, n_lead,
+    return eval_triangle_at<NC, PS>(B, pc, sc, pj, aj, __ldg(f.spec + aj), pk, ak, __ldg(f.spec + ak), role, n_lead,
                                 n_trail, T);
 }
 
