@@ -368,7 +368,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     # many ranks x pipeline workers on one host: sleeping waits instead of spinning ones
-    if world >= 4:
+    if world >= 4 or os.environ.get("UF3B_BLOCKING_SYNC") == "1":
         _native.check(_native.lib().uf3b_set_blocking_sync(1))
 
     basis = make_basis(args.basis)
@@ -405,7 +405,7 @@ def run_ours(args, rank, world, local_rank):
     # ---------------------------------------------------------------- host-buffer arms
     h_pos_np = [torch.from_numpy(fr[0]).pin_memory().numpy() for fr in frames]
     h_num_np = torch.from_numpy(frames[0][1]).pin_memory().numpy()
-    e2e_depth = 4 if world < 4 else 3
+    e2e_depth = int(os.environ.get("UF3B_E2E_DEPTH", "4" if world < 4 else "3"))
     # synthetic targets of the fit (outside the timed region): y = rows @ c_true, E = x_e @ c_true
     model = ls.WeightedLinearModel(basis, solver="cusolver", ridge_1b=1e-10, ridge_2b=1e-10, ridge_3b=1e-10)
     free = np.zeros(F)

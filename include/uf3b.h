@@ -38,7 +38,9 @@ typedef enum {
     UF3B_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError)  */
     UF3B_ERR_ELEMENT = -3,      /* atomic number not in the basis' element list    */
     UF3B_ERR_CAPACITY = -4,     /* index range exceeded (int32 offsets)            */
-    UF3B_ERR_STATE = -5         /* call order violated (e.g. coefficients not set) */
+    UF3B_ERR_STATE = -5,        /* call order violated (e.g. coefficients not set) */
+    UF3B_RETRY = 1              /* deferred list build (uf3b_basis_set_deferred_lists) was invalid: build the
+                                   lists again and re-issue the call; nothing was written that may be used */
 } uf3b_status;
 
 typedef struct uf3b_basis uf3b_basis;     /* device-resident basis tables            */
@@ -100,6 +102,11 @@ int uf3b_basis_set_coefficients(uf3b_basis *basis, const double *coefficients, i
  * working on k consecutive frames on k streams, let every uf3b_featurize launch occupy only
  * 1/k of the SM resources, so that the frames in flight share each SM.  Default 1. */
 int uf3b_basis_set_frames_in_flight(uf3b_basis *basis, int32_t k);
+/* MD loops: a list build on this basis that can reuse the cell grid of the previous one (same frame
+ * size, atoms still inside the padded box) returns WITHOUT waiting for the device — its totals /
+ * overflow flag / box check are verified by the next call that uses the list, after that call has
+ * queued its own kernels.  uf3b_energy_forces then returns UF3B_RETRY (1) if the build was invalid. */
+int uf3b_basis_set_deferred_lists(uf3b_basis *basis, int enabled);
 void uf3b_basis_destroy(uf3b_basis *basis);
 
 /* -- neighbour lists -------------------------------------------------------------- */

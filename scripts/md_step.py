@@ -11,7 +11,7 @@ basis, coeff = bench.w_model23()
 pos, numbers, cell, pbc = synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0)
 n = len(pos)
 images = geometry.image_table(cell, pbc, basis.r_cut)
-eng = Engine(basis, device=0)
+eng = Engine(basis, device=0, deferred_lists=bool(int(os.environ.get('UF3B_DEFERRED', '1'))))
 eng.set_coefficients(coeff)
 d_pos = torch.from_numpy(pos).cuda(); d_num = torch.from_numpy(numbers).cuda()
 d_e = torch.zeros(1, dtype=torch.float64, device="cuda"); d_f = torch.zeros((n, 3), dtype=torch.float64, device="cuda")

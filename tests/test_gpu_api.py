@@ -474,3 +474,45 @@ def test_singular_normal_equations_are_an_error():
     a[0, 0] = a[1, 1] = 1.0
     with pytest.raises(_native.UF3BError):
         ls.device_solve(a, np.ones(4))
+
+
+def test_deferred_list_builds_keep_the_md_loop_exact():
+    """Engine(deferred_lists=True): builds that reuse the cell grid return without a host wait and
+    are verified by energy_forces_device; a step that invalidates the cached grid (atoms leave the
+    padded box) or overflows the index arrays is repeated transparently.  Energies and forces equal
+    those of an engine that checks every build."""
+    import torch
+    from uf3_b200.engine import Engine
+    case = gu.Case("calc_syn_w54_model23")
+    basis = case.basis()
+    rng = np.random.default_rng(3)
+    pos0, numbers, cell, pbc = synthetic.bcc_w((6, 6, 6), a=3.2, sigma=0.05, seed=4)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    fast, safe = Engine(basis, deferred_lists=True), Engine(basis)
+    for eng in (fast, safe):
+        eng.set_coefficients(case["coefficients"])
+    n = len(pos0)
+    d_num = torch.from_numpy(numbers).cuda()
+    out = {k: (torch.zeros(1, dtype=torch.float64, device="cuda"), torch.zeros((n, 3), dtype=torch.float64, device="cuda"))
+           for k in ("fast", "safe")}
+    pos = pos0.copy()
+    for step in range(8):
+        if step == 4:
+            pos = pos + np.array([3.0, -2.5, 2.0])          # the whole crystal leaves the cached grid (1 A skin)
+        elif step == 6:
+            pos = pos * 0.8                                    # denser: more neighbours than the arrays were sized for
+            cell = cell * 0.8
+            images = geometry.image_table(cell, pbc, basis.r_cut)
+        else:
+            pos = pos + rng.normal(scale=0.01, size=pos.shape)
+        d_pos = torch.from_numpy(np.ascontiguousarray(pos)).cuda()
+        for key, eng in (("fast", fast), ("safe", safe)):
+            eng.build_neighbors_device(d_pos.data_ptr(), d_num.data_ptr(), n, images)
+            eng.energy_forces_device(out[key][0].data_ptr(), out[key][1].data_ptr())
+        torch.cuda.synchronize()
+        e_f, e_s = float(out["fast"][0]), float(out["safe"][0])
+        assert abs(e_f - e_s) <= 1e-12 * abs(e_s), step
+        assert gu.rel_err(out["fast"][1].cpu().numpy(), out["safe"][1].cpu().numpy()) <= 1e-11, step
+    assert fast.neighbor_count(3) == safe.neighbor_count(3)
+    fast.close()
+    safe.close()

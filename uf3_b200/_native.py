@@ -8,11 +8,12 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libuf3b.so")
+LIB_PATH = os.environ.get("UF3B_LIB") or os.path.join(_HERE, "lib", "libuf3b.so")     # UF3B_LIB: another build (bisection)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_ELEMENT, ERR_CAPACITY, ERR_STATE = -1, -2, -3, -4, -5
+RETRY = 1
 
 
 class UF3BError(RuntimeError):
@@ -52,6 +53,7 @@ SIGNATURES = {
     "uf3b_basis_create": (C.c_int, [C.POINTER(BasisDesc), C.POINTER(C.c_void_p)]),
     "uf3b_basis_set_coefficients": (C.c_int, [C.c_void_p, _f64p, C.c_int32]),
     "uf3b_basis_set_frames_in_flight": (C.c_int, [C.c_void_p, C.c_int32]),
+    "uf3b_basis_set_deferred_lists": (C.c_int, [C.c_void_p, C.c_int]),
     "uf3b_basis_destroy": (None, [C.c_void_p]),
     "uf3b_neighbors_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
@@ -109,6 +111,8 @@ def lib():
                 "g.build()'` or `make -C uf3_b200/csrc`. uf3_b200 has no CPU fallback.")
         handle = C.CDLL(LIB_PATH)
         for name, (restype, argtypes) in SIGNATURES.items():
+            if os.environ.get("UF3B_LIB") and not hasattr(handle, name):
+                continue
             fn = getattr(handle, name)
             fn.restype = restype
             fn.argtypes = argtypes

@@ -47,6 +47,7 @@ extern "C" int uf3b_pair_histogram(uf3b_basis *basis, const uf3b_nlist *nl, cons
                                    int32_t n_bins, int64_t *counts, void *stream_) {
     if (!basis || !nl || !bin_edges || !counts || n_bins < 1) return fail(UF3B_ERR_INVALID, "bad argument");
     DeviceGuard on_device(basis->device);
+    if (int rc = nlist_resolve(const_cast<uf3b_nlist *>(nl))) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n_pairs = basis->tab.n_pairs;
     const size_t n_out = (size_t)n_pairs * n_bins;

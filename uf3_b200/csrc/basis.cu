@@ -34,6 +34,8 @@ int fail(int code, const char *fmt, ...) {
 
 static std::atomic<bool> g_blocking_sync{false};
 
+bool blocking_sync_enabled() { return g_blocking_sync.load(std::memory_order_relaxed); }
+
 cudaError_t stream_sync(cudaStream_t stream) {
     if (!g_blocking_sync.load(std::memory_order_relaxed)) return cudaStreamSynchronize(stream);
     thread_local cudaEvent_t ev = nullptr;
@@ -301,6 +303,12 @@ int uf3b_basis_create(const uf3b_basis_desc *d, uf3b_basis **out) {
 int uf3b_basis_set_frames_in_flight(uf3b_basis *b, int32_t k) {
     if (!b || k < 1 || k > 8) return fail(UF3B_ERR_INVALID, "frames in flight must be 1..8");
     b->frames_in_flight = k;
+    return UF3B_OK;
+}
+
+int uf3b_basis_set_deferred_lists(uf3b_basis *b, int enabled) {
+    if (!b) return fail(UF3B_ERR_INVALID, "null basis");
+    b->deferred_lists = enabled != 0;
     return UF3B_OK;
 }
 

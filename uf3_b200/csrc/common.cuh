@@ -10,6 +10,8 @@
 
 #include "../../include/uf3b.h"
 
+struct uf3b_nlist;
+
 namespace uf3b {
 
 // ------------------------------------------------------------------ host utilities
@@ -94,6 +96,7 @@ struct DeviceGuard {
 // uf3b_set_blocking_sync(1) the thread sleeps on an event created with cudaEventBlockingSync
 // instead — for hosts where ranks x pipeline workers outnumber the cores.
 cudaError_t stream_sync(cudaStream_t stream);
+bool blocking_sync_enabled();
 
 // ------------------------------------------------------------------ device tables
 // Flattened BSplineBasis on the device.  Pair p = (a<=b) -> a*ne - a*(a-1)/2 + (b-a);
@@ -145,6 +148,13 @@ struct FrameView {
 
 }  // namespace uf3b
 
+namespace uf3b {
+// Waits for the deferred status of a list build and validates it: UF3B_OK, an error code, or
+// UF3B_RETRY when the build has to be repeated (the centres left the cached grid, or the index
+// arrays were too small — they have been regrown).  No-op for a list that is not pending.
+int nlist_resolve(uf3b_nlist *nl);
+}  // namespace uf3b
+
 // ------------------------------------------------------------------ opaque handles
 struct uf3b_basis {
     uf3b::BasisTab tab;            // device pointers into `blob`
@@ -162,6 +172,7 @@ struct uf3b_basis {
     std::vector<double> h_knots3;                  // host copy of the 3-body knot vectors
     int h_pair_nk0 = 0;                            // knots of pair 0
     bool no_tile = false;          // force the general scatter path (tests / profiling)
+    bool deferred_lists = false;   // list builds that reuse their grid return without the host wait
     int frames_in_flight = 1;      // k_featurize launches take 1/k of the resident blocks
     std::vector<double> h_bin_w;
     std::vector<int> h_numbers;
@@ -185,7 +196,16 @@ struct uf3b_nlist {
     // (bounding box, list totals) are WRITTEN there by a kernel instead of being copied, so
     // they never queue behind a large device->host row copy on the copy engine
     double *h_mapped = nullptr;
-    ~uf3b_nlist() { if (h_mapped) cudaFreeHost(h_mapped); }
+    // deferred status (uf3b_basis_set_deferred_lists): the build returned without waiting for its
+    // totals / overflow / box check; nlist_resolve() waits on `status_ev` and validates
+    bool pending = false;
+    bool ticket_zeroed = false;    // k_prepare's block counter has been cleared once
+    cudaEvent_t status_ev = nullptr;
+    cudaStream_t pending_stream = nullptr;
+    ~uf3b_nlist() {
+        if (h_mapped) cudaFreeHost(h_mapped);
+        if (status_ev) cudaEventDestroy(status_ev);
+    }
     // cell grid of the last build, reusable while the centres stay within `grid_skin` of the
     // box it was sized for (MD: one host synchronisation per build instead of two)
     bool grid_valid = false;

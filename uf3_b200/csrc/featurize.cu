@@ -1437,6 +1437,7 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                               double *x_forces, int64_t ld, void *stream_) {
     if (!basis || !nl) return fail(UF3B_ERR_INVALID, "null handle");
     DeviceGuard on_device(basis->device);
+    if (int rc = nlist_resolve(const_cast<uf3b_nlist *>(nl))) return rc;     // needs the longest row on the host
     cudaStream_t stream = (cudaStream_t)stream_;
     const int F = basis->n_feats;
     const int n = (int)nl->n;

@@ -50,49 +50,79 @@ __device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
 
 // species lookup for every atom + bounding box of the CENTRES [c_first, c_first + c_count)
 // (all real atoms unless the frame is split over ranks: the grid only has to hold what lies
-// within the search radius of this rank's centres).  bbox must hold (+inf x3, -inf x3) on
-// entry; every block folds its partial box in with six atomics.
-__global__ void __launch_bounds__(1024) k_prepare(int n, int c_first, int c_count, const int *__restrict__ z,
-                                                  const int *__restrict__ z_to_spec,
-                                                  const double *__restrict__ pos,
-                                                  int *__restrict__ spec, double *__restrict__ bbox,
-                                                  int *__restrict__ err) {
-    __shared__ double red[6][32];
-    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+// within the search radius of this rank's centres) in bbox[0..5] and of ALL atoms in bbox[8..13]
+// (the binning kernels skip whole periodic images with it).  Every block leaves its twelve bounds
+// in `partial`; the last block to finish (ticket counter, reset for the next launch) folds them —
+// one min / max atomic per bound and block on twelve shared addresses serialised in the L2 (the
+// kernel took 14-28 us for 10 000 atoms that way).
+constexpr int PREP_THREADS = 256;
+__global__ void __launch_bounds__(PREP_THREADS) k_prepare(int n, int c_first, int c_count, const int *__restrict__ z,
+                                                          const int *__restrict__ z_to_spec,
+                                                          const double *__restrict__ pos,
+                                                          int *__restrict__ spec, double *__restrict__ bbox,
+                                                          int *__restrict__ err, double *__restrict__ partial,
+                                                          unsigned *__restrict__ ticket) {
+    double v[12] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY,
+                    INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int bad = 0;
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
         const int zz = z[a];
         const int s = (zz >= 0 && zz < 128) ? z_to_spec[zz] : -1;
         spec[a] = s < 0 ? 0 : s;
         if (s < 0) bad = 1;
-        if ((unsigned)(a - c_first) >= (unsigned)c_count) continue;
+        const bool centre = (unsigned)(a - c_first) < (unsigned)c_count;
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const double v = pos[3 * a + c];
-            lo[c] = fmin(lo[c], v);
-            hi[c] = fmax(hi[c], v);
+            const double x = pos[3 * a + c];
+            v[6 + c] = fmin(v[6 + c], x);
+            v[9 + c] = fmax(v[9 + c], x);
+            if (centre) { v[c] = fmin(v[c], x); v[3 + c] = fmax(v[3 + c], x); }
         }
     }
+    __shared__ double red[12][PREP_THREADS / 32];
+    __shared__ bool last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = 0; c < 3; ++c) {
+    auto fold = [&](int c, double x) {          // warp reduction of bound c
+        const bool is_min = (c % 6) < 3;
         for (int s = 16; s > 0; s >>= 1) {
-            lo[c] = fmin(lo[c], __shfl_xor_sync(FULL, lo[c], s));
-            hi[c] = fmax(hi[c], __shfl_xor_sync(FULL, hi[c], s));
+            const double o = __shfl_xor_sync(FULL, x, s);
+            x = is_min ? fmin(x, o) : fmax(x, o);
         }
-        if (lane == 0) { red[c][warp] = lo[c]; red[3 + c][warp] = hi[c]; }
+        return x;
+    };
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+        const double x = fold(c, v[c]);
+        if (lane == 0) red[c][warp] = x;
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) *err = 1;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(err, 1);
     if (warp == 0) {
-        const int nw = blockDim.x >> 5;
-        for (int c = 0; c < 3; ++c) {
-            double l = lane < nw ? red[c][lane] : INFINITY;
-            double h = lane < nw ? red[3 + c][lane] : -INFINITY;
-            for (int s = 16; s > 0; s >>= 1) {
-                l = fmin(l, __shfl_xor_sync(FULL, l, s));
-                h = fmax(h, __shfl_xor_sync(FULL, h, s));
-            }
-            if (lane == 0) { atomic_min_f64(bbox + c, l); atomic_max_f64(bbox + 3 + c, h); }
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const bool is_min = (c % 6) < 3;
+            const double x = fold(c, lane < PREP_THREADS / 32 ? red[c][lane] : (is_min ? INFINITY : -INFINITY));
+            if (lane == 0) partial[12 * blockIdx.x + c] = x;
+        }
+        if (lane == 0) {
+            __threadfence();
+            last = atomicAdd(ticket, 1u) == gridDim.x - 1;
         }
     }
+    __syncthreads();
+    if (!last || warp != 0) return;
+    __threadfence();
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+        const bool is_min = (c % 6) < 3;
+        double x = is_min ? INFINITY : -INFINITY;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const double o = __ldcg(partial + 12 * b + c);
+            x = is_min ? fmin(x, o) : fmax(x, o);
+        }
+        x = fold(c, x);
+        if (lane == 0) bbox[c < 6 ? c : c + 2] = x;         // centres at [0..5], all atoms at [8..13]
+    }
+    if (lane == 0) *ticket = 0;
 }
 
 __device__ __forceinline__ int cell_coord(double p, double o, double edge, int n) {
@@ -100,17 +130,29 @@ __device__ __forceinline__ int cell_coord(double p, double o, double edge, int n
     return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
-// One thread per supercell atom m = g*n + a: drop ghosts outside the padded bounding box
-// of the real atoms, count the rest per cell.
-__global__ void k_bin_count(int n, long long n_sup, const double *__restrict__ pos,
-                            const double *__restrict__ img_off, GridParams G,
+// A periodic image none of whose atoms can lie in the binned region: the box of ALL atoms
+// (bbox[8..13], k_prepare) shifted by the image offset misses the grid.  With the centres of one
+// rank (a slab of the frame) almost every image of a large cell goes this way without its
+// positions being read.
+__device__ __forceinline__ bool image_outside(const double *__restrict__ bbox, const double *__restrict__ off,
+                                              const GridParams &G) {
+    return bbox[8] + off[0] > G.hx || bbox[11] + off[0] < G.ox || bbox[9] + off[1] > G.hy || bbox[12] + off[1] < G.oy
+           || bbox[10] + off[2] > G.hz || bbox[13] + off[2] < G.oz;
+}
+
+// One thread per supercell atom m = g*n + a (blockIdx.y = image g): drop ghosts outside the padded
+// bounding box of the centres, count the rest per cell.  Blocks of an image that cannot reach the
+// grid leave at once (cell_of is only read for the images that stay: k_bin_fill repeats the test).
+__global__ void k_bin_count(int n, int n_img, const double *__restrict__ pos,
+                            const double *__restrict__ img_off, GridParams G, const double *__restrict__ bbox,
                             int *__restrict__ cell_of, int *__restrict__ cell_cnt) {
-    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_sup;
-         m += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(m / n), a = (int)(m - (long long)g * n);
-        const double x = __dadd_rn(pos[3 * a + 0], img_off[3 * g + 0]);
-        const double y = __dadd_rn(pos[3 * a + 1], img_off[3 * g + 1]);
-        const double z = __dadd_rn(pos[3 * a + 2], img_off[3 * g + 2]);
+  for (int g = blockIdx.y; g < n_img; g += gridDim.y) {
+    if (g != 0 && image_outside(bbox, img_off + 3 * g, G)) continue;
+    const double ox = img_off[3 * g + 0], oy = img_off[3 * g + 1], oz = img_off[3 * g + 2];
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const double x = __dadd_rn(pos[3 * a + 0], ox);
+        const double y = __dadd_rn(pos[3 * a + 1], oy);
+        const double z = __dadd_rn(pos[3 * a + 2], oz);
         int cell = -1;
         if (g == 0 || (x >= G.ox && x <= G.hx && y >= G.oy && y <= G.hy && z >= G.oz && z <= G.hz)) {
             const int cx = cell_coord(x, G.ox, G.edge, G.nx);
@@ -119,27 +161,32 @@ __global__ void k_bin_count(int n, long long n_sup, const double *__restrict__ p
             cell = (cx * G.ny + cy) * G.nz + cz;
             atomicAdd(cell_cnt + cell, 1);
         }
-        cell_of[m] = cell;
+        cell_of[(long long)g * n + a] = cell;
     }
+  }
 }
 
-__global__ void k_bin_fill(int n, long long n_sup, const double *__restrict__ pos,
-                           const double *__restrict__ img_off, const int *__restrict__ spec,
+__global__ void k_bin_fill(int n, int n_img, const double *__restrict__ pos,
+                           const double *__restrict__ img_off, GridParams G, const double *__restrict__ bbox,
+                           const int *__restrict__ spec,
                            const int *__restrict__ cell_of, const int *__restrict__ cell_start,
                            int *__restrict__ cursor, Slot *__restrict__ slots) {
-    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_sup;
-         m += (long long)gridDim.x * blockDim.x) {
+  for (int g = blockIdx.y; g < n_img; g += gridDim.y) {
+    if (g != 0 && image_outside(bbox, img_off + 3 * g, G)) continue;
+    const double ox = img_off[3 * g + 0], oy = img_off[3 * g + 1], oz = img_off[3 * g + 2];
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const long long m = (long long)g * n + a;
         const int cell = cell_of[m];
         if (cell < 0) continue;
-        const int g = (int)(m / n), a = (int)(m - (long long)g * n);
         Slot s;
-        s.x = __dadd_rn(pos[3 * a + 0], img_off[3 * g + 0]);
-        s.y = __dadd_rn(pos[3 * a + 1], img_off[3 * g + 1]);
-        s.z = __dadd_rn(pos[3 * a + 2], img_off[3 * g + 2]);
+        s.x = __dadd_rn(pos[3 * a + 0], ox);
+        s.y = __dadd_rn(pos[3 * a + 1], oy);
+        s.z = __dadd_rn(pos[3 * a + 2], oz);
         s.m = (int)m;
         s.spec = spec[a];
         slots[cell_start[cell] + atomicAdd(cursor + cell, 1)] = s;
     }
+  }
 }
 
 // Exclusive scan of up to two int arrays (block b scans array b); out[n] = total.
@@ -567,6 +614,31 @@ __global__ void k_post_status(const int *__restrict__ claims, int *__restrict__ 
     __threadfence_system();
 }
 
+int uf3b::nlist_resolve(uf3b_nlist *nl) {
+    if (!nl || !nl->pending) return UF3B_OK;
+    nl->pending = false;
+    UF3B_CUDA(cudaEventSynchronize(nl->status_ev));
+    int h_status[8];
+    memcpy(h_status, nl->h_mapped + 8, sizeof h_status);
+    if (h_status[7] & 1) return fail(UF3B_ERR_ELEMENT, "configuration holds an element outside the basis");
+    if (h_status[7] & 2) return fail(UF3B_ERR_INVALID, "non-finite position");
+    if (h_status[0] < 0 || h_status[1] < 0) return fail(UF3B_ERR_CAPACITY, "neighbour list exceeds int32 offsets");
+    if (h_status[6]) {              // the centres left the cached box: the next build takes a fresh grid
+        nl->grid_valid = false;
+        return fail(UF3B_RETRY, "deferred list build: the atoms left the cached cell grid");
+    }
+    if (h_status[2]) {              // index arrays too small: wait for whoever reads them, then regrow
+        UF3B_CUDA(cudaStreamSynchronize(nl->pending_stream));
+        UF3B_CUDA(nl->idx2.reserve((size_t)(h_status[4] + 1) * NL_REGIONS));
+        UF3B_CUDA(nl->idx3.reserve((size_t)(h_status[5] + 1) * NL_REGIONS));
+        return fail(UF3B_RETRY, "deferred list build: index arrays regrown");
+    }
+    nl->total2 = h_status[0];
+    nl->total3 = h_status[1];
+    nl->max3 = h_status[3];
+    return UF3B_OK;
+}
+
 extern "C" {
 
 int uf3b_neighbors_build(uf3b_basis *basis, int64_t n_atoms, const double *positions,
@@ -599,6 +671,10 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
         ~Guard() { if (armed) delete p; }
     } guard{nl, created};
 
+    if (nl->pending) {          // an unverified deferred build is superseded by this one
+        const int rc = nlist_resolve(nl);
+        if (rc < 0 && rc != UF3B_ERR_CAPACITY) { guard.armed = false; return rc; }
+    }
     const int n = (int)n_atoms;
     nl->n = n_atoms;
     nl->n_img = n_images;
@@ -637,15 +713,21 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     UF3B_CUDA(nl->pos.reserve(3 * (size_t)n));
     UF3B_CUDA(nl->z.reserve(n));
     UF3B_CUDA(nl->spec.reserve(n));
-    UF3B_CUDA(nl->misc.reserve(8));
+    constexpr int PREP_BLOCKS_MAX = 256;
+    UF3B_CUDA(nl->misc.reserve(16 + 12 * PREP_BLOCKS_MAX + 2));
     UF3B_CUDA(cudaMemcpyAsync(nl->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyDefault, stream));
     UF3B_CUDA(cudaMemcpyAsync(nl->z.p, atomic_numbers, sizeof(int) * n, cudaMemcpyDefault, stream));
     int *d_err = (int *)(nl->misc.p + 6);
-    static const double bbox_init[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0};
+    static const double bbox_init[14] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0, 0.0,
+                                         INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     UF3B_CUDA(cudaMemcpyAsync(nl->misc.p, bbox_init, sizeof bbox_init, cudaMemcpyHostToDevice, stream));
-    const int prep_blocks = std::min((n + 1023) / 1024, sm_count());
-    UF3B_LAUNCH(k_prepare, prep_blocks, 1024, 0, stream, n, nl->c_first, nl->c_count, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
-                nl->spec.p, nl->misc.p, d_err);
+    const int prep_blocks = std::min((n + PREP_THREADS - 1) / PREP_THREADS, PREP_BLOCKS_MAX);
+    if (!nl->ticket_zeroed) {       // the kernel leaves the counter at zero for the next launch
+        UF3B_CUDA(cudaMemsetAsync(nl->misc.p + 16 + 12 * PREP_BLOCKS_MAX, 0, 2 * sizeof(double), stream));
+        nl->ticket_zeroed = true;
+    }
+    UF3B_LAUNCH(k_prepare, prep_blocks, PREP_THREADS, 0, stream, n, nl->c_first, nl->c_count, nl->z.p, basis->tab.z_to_spec, nl->pos.p,
+                nl->spec.p, nl->misc.p, d_err, nl->misc.p + 16, (unsigned *)(nl->misc.p + 16 + 12 * PREP_BLOCKS_MAX));
     if (!nl->h_mapped) UF3B_CUDA(cudaHostAlloc((void **)&nl->h_mapped, 16 * sizeof(double), cudaHostAllocMapped));
     // reuse the previous build's grid (no bounding-box read-back) when the problem is the same
     // and — checked on the device, read back with the list totals — the centres moved less
@@ -725,14 +807,14 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     UF3B_CUDA(nl->cell_cursor.reserve((size_t)n_cell));
     UF3B_CUDA(cudaMemsetAsync(nl->cell_start.p, 0, sizeof(int) * (n_cell + 1), stream));
     UF3B_CUDA(cudaMemsetAsync(nl->cell_cursor.p, 0, sizeof(int) * n_cell, stream));
-    const int bin_blocks = (int)std::min<long long>((n_sup + 255) / 256, 148 * 16);
-    UF3B_LAUNCH(k_bin_count, bin_blocks, 256, 0, stream, n, n_sup, nl->pos.p, nl->img_off.p, G,
+    const dim3 bin_grid((unsigned)std::min(std::max((n + 255) / 256, 1), 148 * 4), (unsigned)std::min(n_images, 65535));
+    UF3B_LAUNCH(k_bin_count, bin_grid, 256, 0, stream, n, n_images, nl->pos.p, nl->img_off.p, G, nl->misc.p,
                 nl->cell_of.p, nl->cell_start.p);
     if (int rc = scan_arrays(nl, 1, nl->cell_start.p, nl->cell_start.p, nullptr, nullptr, (int)n_cell,
                              nl->totals.p, stream)) return rc;
     // every supercell atom that survives the box test has a slot; n_sup bounds it
     UF3B_CUDA(nl->slots.reserve((size_t)n_sup));
-    UF3B_LAUNCH(k_bin_fill, bin_blocks, 256, 0, stream, n, n_sup, nl->pos.p, nl->img_off.p,
+    UF3B_LAUNCH(k_bin_fill, bin_grid, 256, 0, stream, n, n_images, nl->pos.p, nl->img_off.p, G, nl->misc.p,
                 nl->spec.p, nl->cell_of.p, nl->cell_start.p, nl->cell_cursor.p, nl->slots.p);
 
     // one pass; the index arrays keep their capacity from earlier builds (first guess below)
@@ -762,6 +844,20 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
                     nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status, claims);
         UF3B_LAUNCH(k_post_status, 1, 32, 0, stream, claims, status, (volatile int *)(nl->h_mapped + 8), nl->misc.p,
                     chk);
+        if (basis->deferred_lists && reuse && attempt == 0) {
+            // MD steady state: no host wait here — the caller queues its kernels behind the list build
+            // and the status is verified by nlist_resolve() while they run
+            if (!nl->status_ev)
+                UF3B_CUDA(cudaEventCreateWithFlags(&nl->status_ev, cudaEventDisableTiming
+                                                   | (blocking_sync_enabled() ? cudaEventBlockingSync : 0)));
+            UF3B_CUDA(cudaEventRecord(nl->status_ev, stream));
+            nl->pending = true;
+            nl->pending_stream = stream;
+            nl->grid_valid = true;
+            guard.armed = false;
+            *inout = nl;
+            return UF3B_OK;
+        }
         UF3B_CUDA(stream_sync(stream));
         memcpy(h_status, nl->h_mapped + 8, sizeof h_status);
         if (reuse) {
@@ -793,12 +889,14 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
 
 int uf3b_neighbors_count(const uf3b_nlist *nl, int which, int64_t *n_entries) {
     if (!nl || !n_entries || (which != 2 && which != 3)) return fail(UF3B_ERR_INVALID, "bad argument");
+    if (int rc = nlist_resolve(const_cast<uf3b_nlist *>(nl))) return rc;
     *n_entries = which == 2 ? nl->total2 : nl->total3;
     return UF3B_OK;
 }
 
 int uf3b_neighbors_export(const uf3b_nlist *nl, int which, int64_t *offsets, int64_t *supercell_index) {
     if (!nl || !offsets || (which != 2 && which != 3)) return fail(UF3B_ERR_INVALID, "bad argument");
+    if (int rc = nlist_resolve(const_cast<uf3b_nlist *>(nl))) return rc;
     const int64_t total = which == 2 ? nl->total2 : nl->total3;
     const size_t n = (size_t)nl->n;
     std::vector<int> start(n), count(n), idx;

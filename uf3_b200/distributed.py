@@ -174,7 +174,7 @@ class ShardedEvaluator:
         # (its share of the centres, no collective) so that one GPU shows the per-rank step
         self.fake_world = int(os.environ.get("UF3B_FAKE_WORLD", "0")) if self.world == 1 else 0
         self.device = torch.cuda.current_device() if device is None else int(device)
-        self.engine = Engine(basis, device=self.device)
+        self.engine = Engine(basis, device=self.device, deferred_lists=True)
         self.engine.set_coefficients(coefficients)
         self.out = None
 

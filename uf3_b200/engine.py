@@ -18,9 +18,12 @@ def _ptr(arr):
 
 
 class Engine:
-    def __init__(self, basis, device=None, frames_in_flight=1):
+    def __init__(self, basis, device=None, frames_in_flight=1, deferred_lists=False):
         """`frames_in_flight` = k: this engine is one of k working on consecutive frames on k
-        streams; its feature kernels then take 1/k of the SM resources per launch."""
+        streams; its feature kernels then take 1/k of the SM resources per launch.
+        `deferred_lists` (MD loops): a list build that can reuse the previous cell grid returns
+        without a host wait; `energy_forces*` verifies it after queueing its own kernels and
+        repeats build + evaluation in the rare case it was invalid (`uf3b_basis_set_deferred_lists`)."""
         self._lib = _native.lib()
         # the basis handle remembers the device it was created on and every C-ABI call that takes
         # it makes that device current for its duration (DeviceGuard), so engines on different
@@ -34,6 +37,10 @@ class Engine:
         _native.check(self._lib.uf3b_basis_create(C.byref(self.tables.desc), C.byref(self._basis)))
         if frames_in_flight != 1:
             _native.check(self._lib.uf3b_basis_set_frames_in_flight(self._basis, int(frames_in_flight)))
+        self.deferred_lists = bool(deferred_lists)
+        if self.deferred_lists:
+            _native.check(self._lib.uf3b_basis_set_deferred_lists(self._basis, 1))
+        self._last_build = None
         self._nlist = C.c_void_p()
         self.n_atoms = 0
         self.has_coefficients = False
@@ -91,11 +98,16 @@ class Engine:
         abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
         offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
         first, count = (0, int(n_atoms)) if centres is None else centres
-        _native.check(self._lib.uf3b_neighbors_build_range(
-            self._basis, int(n_atoms), C.c_void_p(positions_ptr), C.c_void_p(numbers_ptr),
-            len(offsets), _ptr(offsets), _ptr(abc), int(first), int(count), C.byref(self._nlist), stream))
+        self._last_build = (positions_ptr, numbers_ptr, int(n_atoms), offsets, abc, int(first), int(count), stream)
+        self._build_device()
         self.n_atoms = int(n_atoms)
         return self
+
+    def _build_device(self):
+        positions_ptr, numbers_ptr, n_atoms, offsets, abc, first, count, stream = self._last_build
+        _native.check(self._lib.uf3b_neighbors_build_range(
+            self._basis, n_atoms, C.c_void_p(positions_ptr), C.c_void_p(numbers_ptr),
+            len(offsets), _ptr(offsets), _ptr(abc), first, count, C.byref(self._nlist), stream))
 
     def neighbor_count(self, which):
         """Number of entries in list 2 or 3 of the current configuration."""
@@ -161,9 +173,16 @@ class Engine:
 
     def energy_forces_device(self, energy_ptr, forces_ptr, stream=None):
         """Device-pointer form (energy: 1 double, forces: [N,3]); asynchronous on `stream`."""
-        _native.check(self._lib.uf3b_energy_forces(
-            self._basis, self._nlist, C.c_void_p(energy_ptr) if energy_ptr else None,
-            C.c_void_p(forces_ptr) if forces_ptr else None, None, stream))
+        for attempt in range(3):
+            rc = self._lib.uf3b_energy_forces(
+                self._basis, self._nlist, C.c_void_p(energy_ptr) if energy_ptr else None,
+                C.c_void_p(forces_ptr) if forces_ptr else None, None, stream)
+            if rc != _native.RETRY or self._last_build is None:
+                break
+            # the deferred list build was invalid (atoms left the cached grid / arrays regrown): the
+            # library has dropped the grid or grown the arrays, so the next build is a checked one
+            self._build_device()
+        _native.check(rc)
 
     # ------------------------------------------------------------------ instrumentation
     def launch_count(self):
