@@ -11,6 +11,7 @@
 #include "../../include/uf3b.h"
 
 struct uf3b_nlist;
+struct uf3b_gram;
 
 namespace uf3b {
 
@@ -153,6 +154,9 @@ namespace uf3b {
 // UF3B_RETRY when the build has to be repeated (the centres left the cached grid, or the index
 // arrays were too small — they have been regrown).  No-op for a list that is not pending.
 int nlist_resolve(uf3b_nlist *nl);
+// uf3b_gram_accumulate whose kernels leave at once when *invalid != 0 (device flag of a deferred list build)
+int gram_accumulate_guarded(uf3b_gram *gram, const double *x, const double *y, int64_t rows, int64_t ld,
+                            int is_force, void *stream, const int *invalid);
 }  // namespace uf3b
 
 // ------------------------------------------------------------------ opaque handles
@@ -199,6 +203,8 @@ struct uf3b_nlist {
     // deferred status (uf3b_basis_set_deferred_lists): the build returned without waiting for its
     // totals / overflow / box check; nlist_resolve() waits on `status_ev` and validates
     bool pending = false;
+    int max3_hint = 0;             // longest 3-body row of the last verified build
+    bool hint_used = false;        // a consumer sized itself by max3_hint while the build was pending
     bool ticket_zeroed = false;    // k_prepare's block counter has been cleared once
     cudaEvent_t status_ev = nullptr;
     cudaStream_t pending_stream = nullptr;
@@ -224,4 +230,6 @@ struct uf3b_nlist {
     uf3b::DevBuf<double> misc;     // bbox (6) on device
     uf3b::DevBuf<long long> totals, tile_sums;
     uf3b::FrameView view() const;
+    // device flag (1 = a consumer queued behind a deferred build must skip the frame), or null
+    const int *invalid_flag() const { return totals.p ? reinterpret_cast<const int *>(totals.p + 1) + 8 : nullptr; }
 };

@@ -1437,7 +1437,14 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
                               double *x_forces, int64_t ld, void *stream_) {
     if (!basis || !nl) return fail(UF3B_ERR_INVALID, "null handle");
     DeviceGuard on_device(basis->device);
-    if (int rc = nlist_resolve(const_cast<uf3b_nlist *>(nl))) return rc;     // needs the longest row on the host
+    // A deferred list build (uf3b_basis_set_deferred_lists) is not waited for when the tiled kernels
+    // take the frame with DEVICE outputs: they size their shared memory by the previous frame's longest
+    // 3-body row and the caller verifies the build afterwards (nlist_resolve -> UF3B_RETRY).
+    uf3b_nlist *nl_rw = const_cast<uf3b_nlist *>(nl);
+    bool deferred = nl->pending && basis->deferred_lists && nl->max3_hint >= 2
+                    && (!x_energy || is_device_pointer(x_energy)) && (!x_forces || is_device_pointer(x_forces));
+    if (!deferred)
+        if (int rc = nlist_resolve(nl_rw)) return rc;     // needs the longest row on the host
     cudaStream_t stream = (cudaStream_t)stream_;
     const int F = basis->n_feats;
     const int n = (int)nl->n;
@@ -1457,8 +1464,10 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
 
     // small 3-body grids of a unary, symmetry-2 basis: the register-tiled kernel (featurize_tiled.cu)
     {
-        const int rc = featurize_tiled(basis, nl, x_energy, x_forces, ld, stream);
+        const int rc = featurize_tiled(basis, nl, x_energy, x_forces, ld, stream, deferred);
         if (rc <= 0) return rc;
+        if (deferred)       // another path takes the frame: it needs the verified lists
+            if (int rc2 = nlist_resolve(nl_rw)) return rc2;
     }
     // launch shape: as many warps per SM as shared memory and registers allow, grid sized to
     // the SM count

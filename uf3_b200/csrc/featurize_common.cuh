@@ -91,6 +91,6 @@ int finish_featurize(uf3b_basis *basis, double *x_energy, double *x_forces, int6
 
 // featurize_tiled.cu: takes the frame when the basis fits the register-tiled kernel, else returns 1
 int featurize_tiled(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, double *x_forces, int64_t ld,
-                    cudaStream_t stream);
+                    cudaStream_t stream, bool deferred);
 
 }  // namespace uf3b

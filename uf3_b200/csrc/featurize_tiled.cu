@@ -320,7 +320,9 @@ k_rows_nbr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
     __syncwarp();
 
     for (int a = gw; a < f.n; a += n_gw) {
-        const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
+        const int row0 = __ldg(f.off3 + a);
+        int n3a = __ldg(f.cnt3 + a);
+        if (n3a > ps) n3a = 0;      // only behind a deferred list build whose frame will be repeated
         double fr[3][NS];           // force tile [c][{l, m}] of the lane's (g, n)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
@@ -624,7 +626,9 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
         // is a chain of dependent gathers otherwise (58 % of the stall samples were long-scoreboard
         // waits): (1) row bounds, (2) the lane's own 3-body entry and its pair-list entries of the
         // first two passes, (3) the planes and the pair partners' positions.
-        const int row0 = __ldg(f.off3 + a), n3a = __ldg(f.cnt3 + a);
+        const int row0 = __ldg(f.off3 + a);
+        int n3a = __ldg(f.cnt3 + a);
+        if (n3a > tg.ps) n3a = 0;   // only behind a deferred list build whose frame will be repeated
         const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
         const int sa = __ldg(f.spec + a);
         const Vec3 pa = real_position(f, a);
@@ -818,7 +822,7 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
 // ---------------------------------------------------------------- host side
 template <int LM, int NA>
 static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, double *x_energy, double *x_forces,
-                        int64_t ld, cudaStream_t stream) {
+                        int64_t ld, cudaStream_t stream, int max3_in) {
     using S = TiledShape<LM, NA>;
     const int F = basis->n_feats, n = (int)nl->n;
     const bool e_dev = x_energy && is_device_pointer(x_energy);
@@ -828,7 +832,7 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     UF3B_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     UF3B_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
 
-    const int max3 = std::max(nl->max3, 2);
+    const int max3 = std::max(max3_in, 2);
     tg.ps = max3;                   // one slot per position of the longest row
     tg.sl_shift = tg.ps <= 16 ? 4 : 5;
     tg.all_orphans = getenv("UF3B_TILED_ORPHANS") ? 1 : 0;
@@ -955,12 +959,15 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
 // weights, untrimmed grid la x la x na with la <= 4, na <= 10, rows of at most 32 entries.
 // Returns 1 when it does not apply (the caller goes on to the other paths); error codes are <= 0.
 int featurize_tiled(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, double *x_forces, int64_t ld,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, bool deferred) {
     const BasisTab &T = basis->tab;
     if (T.n_trios != 1 || T.ne != 1 || !T.unit_weights || basis->no_tile || getenv("UF3B_NO_TILED") || getenv("UF3B_NO_LEGS")
         || getenv("UF3B_PLANES"))
         return 1;
-    if (basis->h_trio_sym[0] != 2 || nl->max3 > TL_MAX_ROW) return 1;
+    // deferred list build: the longest row is not known on the host yet; the kernels are sized by the
+    // previous frame's and skip longer rows (the device flag of the build then marks the frame invalid)
+    const int max3_in = deferred ? nl->max3_hint : nl->max3;
+    if (basis->h_trio_sym[0] != 2 || max3_in > TL_MAX_ROW) return 1;
     const int lead = T.lead3, trail = T.trail3;
     const int L = basis->h_trio_dims[0], M = basis->h_trio_dims[1], N = basis->h_trio_dims[2];
     TiledGeom tg = {};
@@ -1003,9 +1010,10 @@ int featurize_tiled(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, d
         for (int c = 0; c < n_cols3; ++c)
             if (seen[c] != 1) return 1;
     }
-    if (tg.la <= 2 && tg.na <= 7) return launch_tiled<2, 7>(basis, nl, tg, x_energy, x_forces, ld, stream);
-    if (tg.la <= 3 && tg.na <= 9) return launch_tiled<3, 9>(basis, nl, tg, x_energy, x_forces, ld, stream);
-    return launch_tiled<4, 10>(basis, nl, tg, x_energy, x_forces, ld, stream);
+    if (deferred) const_cast<uf3b_nlist *>(nl)->hint_used = true;
+    if (tg.la <= 2 && tg.na <= 7) return launch_tiled<2, 7>(basis, nl, tg, x_energy, x_forces, ld, stream, max3_in);
+    if (tg.la <= 3 && tg.na <= 9) return launch_tiled<3, 9>(basis, nl, tg, x_energy, x_forces, ld, stream, max3_in);
+    return launch_tiled<4, 10>(basis, nl, tg, x_energy, x_forces, ld, stream, max3_in);
 }
 
 }  // namespace uf3b

@@ -48,9 +48,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 
 __global__ void __launch_bounds__(256)
 k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols, int rows_per_block,
-       double *__restrict__ g) {
+       double *__restrict__ g, const int *__restrict__ invalid) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bi > bj) return;
+    if (invalid && *invalid) return;        // rows behind a deferred list build that turned out invalid
     __shared__ __align__(16) double sa[GK][GS], sb[GK][GS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wi = warp >> 2, wj = warp & 3;            // warp tile origin (32 wi, 16 wj)
@@ -109,7 +110,8 @@ constexpr int OROWS = 256;    // rows per block of k_ordinate
 // 256-byte reads), the eight per-warp sums are combined in shared memory.
 __global__ void __launch_bounds__(256)
 k_ordinate(const double *__restrict__ x, long long ld, const double *__restrict__ y, long long rows,
-           int n_cols, double *__restrict__ b) {
+           int n_cols, double *__restrict__ b, const int *__restrict__ invalid) {
+    if (invalid && *invalid) return;
     __shared__ double red[8][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + lane;
@@ -159,6 +161,13 @@ int uf3b_gram_create(int32_t n_cols, uf3b_gram **out) {
 
 int uf3b_gram_accumulate(uf3b_gram *gm, const double *x, const double *y, int64_t rows, int64_t ld,
                          int is_force, void *stream_) {
+    return uf3b::gram_accumulate_guarded(gm, x, y, rows, ld, is_force, stream_, nullptr);
+}
+
+}  // extern "C"
+
+int uf3b::gram_accumulate_guarded(uf3b_gram *gm, const double *x, const double *y, int64_t rows, int64_t ld,
+                                  int is_force, void *stream_, const int *invalid) {
     if (!gm || !x || !y) return fail(UF3B_ERR_INVALID, "null argument");
     if (rows < 0 || ld < gm->n_cols) return fail(UF3B_ERR_INVALID, "bad rows / ld");
     if (rows == 0) return UF3B_OK;
@@ -203,14 +212,16 @@ int uf3b_gram_accumulate(uf3b_gram *gm, const double *x, const double *y, int64_
     while ((rows + rpb - 1) / rpb > 65535) rpb *= 2;
     const unsigned nz = (unsigned)((rows + rpb - 1) / rpb);
     UF3B_LAUNCH(k_gram, dim3(nb, nb, nz), 256, 0, stream, dx, dld, (long long)rows, gm->n_cols, (int)rpb,
-                gm->g[which]);
+                gm->g[which], invalid);
     const unsigned ny = (unsigned)((rows + OROWS - 1) / OROWS);
     if (ny > 65535) return fail(UF3B_ERR_CAPACITY, "too many rows in one call (max %d)", 65535 * OROWS);
     UF3B_LAUNCH(k_ordinate, dim3((gm->n_cols + 31) / 32, ny), 256, 0, stream, dx, dld, dy, (long long)rows,
-                gm->n_cols, gm->b[which]);
+                gm->n_cols, gm->b[which], invalid);
     if (dx != x || dy != y) UF3B_CUDA(stream_sync(stream));
     return UF3B_OK;
 }
+
+extern "C" {
 
 int uf3b_gram_export(const uf3b_gram *gm, int is_force, double *gram_out, double *ord_out) {
     if (!gm) return fail(UF3B_ERR_INVALID, "null handle");

@@ -578,8 +578,11 @@ __global__ void k_post_small(const double *__restrict__ src, volatile double *ds
 // position error flags of k_prepare (only checked here when the grid was reused)
 struct BoxCheck { int active; double lo[3], hi[3], skin; };
 
+// status[8]: 1 when a consumer queued behind a DEFERRED build must not use it — overflow, stale grid,
+// bad input, or a 3-body row longer than `max3_hint` (the longest row of the previous build, which the
+// feature kernels size their shared memory by when they cannot wait for this build's own value).
 __global__ void k_post_status(const int *__restrict__ claims, int *__restrict__ status, volatile int *dst,
-                              const double *__restrict__ misc, const BoxCheck chk) {
+                              const double *__restrict__ misc, const BoxCheck chk, int max3_hint) {
     const int lane = threadIdx.x;
     if (chk.active && lane == 0) {
         int stale = 0, bad = ((const int *)(misc + 6))[0] ? 1 : 0;
@@ -609,8 +612,10 @@ __global__ void k_post_status(const int *__restrict__ claims, int *__restrict__ 
         status[4] = m2;
         status[5] = m3;
     }
+    if (lane == 0)
+        status[8] = (status[2] != 0 || status[6] != 0 || status[7] != 0 || status[3] > max3_hint) ? 1 : 0;
     __syncwarp();
-    if (lane < 8) dst[lane] = status[lane];
+    if (lane < 9) dst[lane] = status[lane];
     __threadfence_system();
 }
 
@@ -636,6 +641,11 @@ int uf3b::nlist_resolve(uf3b_nlist *nl) {
     nl->total2 = h_status[0];
     nl->total3 = h_status[1];
     nl->max3 = h_status[3];
+    if (nl->max3 > nl->max3_hint) {     // a consumer that sized itself by the hint skipped this frame
+        nl->max3_hint = nl->max3;
+        if (nl->hint_used) return fail(UF3B_RETRY, "deferred list build: a 3-body row outgrew the previous frame's longest");
+    }
+    nl->max3_hint = nl->max3;
     return UF3B_OK;
 }
 
@@ -829,7 +839,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     for (int attempt = 0; attempt < 2; ++attempt) {
         UF3B_CUDA(nl->scratch2.reserve(nl->idx2.cap));
         UF3B_CUDA(nl->scratch3.reserve(nl->idx3.cap));
-        UF3B_CUDA(cudaMemsetAsync(status, 0, 8 * sizeof(int), stream));
+        UF3B_CUDA(cudaMemsetAsync(status, 0, 9 * sizeof(int), stream));
         UF3B_CUDA(cudaMemsetAsync(claims, 0, 2 * NL_REGIONS * sizeof(int), stream));
         if (nl->c_count < n) {      // rows of the atoms other ranks own stay empty
             UF3B_CUDA(cudaMemsetAsync(nl->cnt2.p, 0, sizeof(int) * n, stream));
@@ -843,7 +853,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
                     nl->cell_start.p, nl->c_first, nl->c_count, nl->off2.p, nl->cnt2.p, nl->off3.p, nl->cnt3.p, nl->idx2.p,
                     nl->idx3.p, nl->scratch2.p, nl->scratch3.p, cap2, cap3, status, claims);
         UF3B_LAUNCH(k_post_status, 1, 32, 0, stream, claims, status, (volatile int *)(nl->h_mapped + 8), nl->misc.p,
-                    chk);
+                    chk, nl->max3_hint);
         if (basis->deferred_lists && reuse && attempt == 0) {
             // MD steady state: no host wait here — the caller queues its kernels behind the list build
             // and the status is verified by nlist_resolve() while they run
@@ -852,6 +862,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
                                                    | (blocking_sync_enabled() ? cudaEventBlockingSync : 0)));
             UF3B_CUDA(cudaEventRecord(nl->status_ev, stream));
             nl->pending = true;
+            nl->hint_used = false;
             nl->pending_stream = stream;
             nl->grid_valid = true;
             guard.armed = false;
@@ -881,6 +892,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     nl->total2 = h_status[0];
     nl->total3 = h_status[1];
     nl->max3 = h_status[3];
+    nl->max3_hint = nl->max3;
     nl->grid_valid = true;
     guard.armed = false;
     *inout = nl;
