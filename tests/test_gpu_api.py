@@ -516,3 +516,56 @@ def test_deferred_list_builds_keep_the_md_loop_exact():
     assert fast.neighbor_count(3) == safe.neighbor_count(3)
     fast.close()
     safe.close()
+
+
+def test_pipeline_repeats_frames_whose_deferred_lists_were_invalid():
+    """Same-size frames reuse their slot's cell grid and run without host waits; a frame whose 3-body
+    rows outgrow the previous frame's longest one, or whose atoms leave the cached grid, is detected
+    by the device-side flag and repeated — rows and normal equations equal the checked calls."""
+    import torch
+    from uf3_b200.engine import Engine
+    from uf3_b200.pipeline import NativePipeline
+    basis = synthetic.w_basis("demo")
+    F = basis.n_feats
+    specs = [(3.165, 0.05, 0.0), (3.165, 0.05, 0.0), (3.165, 0.05, 0.0), (2.95, 0.05, 0.0), (3.165, 0.05, 0.0),
+             (3.165, 0.05, 4.0), (3.165, 0.2, 4.0), (3.165, 0.05, 0.0)]
+    frames = []
+    for k, (a, sigma, shift) in enumerate(specs):
+        pos, numbers, cell, pbc = synthetic.bcc_w((4, 4, 5), a=a, sigma=sigma, seed=20 + k)
+        frames.append((np.ascontiguousarray(pos + shift), numbers, cell, pbc))
+    rng = np.random.default_rng(9)
+    eng = Engine(basis)
+    for depth in (1, 2):
+        pipe = NativePipeline(basis, depth=depth)
+        outs, pending = [], []
+        for pos, numbers, cell, pbc in frames:
+            n = len(pos)
+            xe = torch.empty(F, dtype=torch.float64).pin_memory().numpy()
+            xf = torch.empty((3 * n, F), dtype=torch.float64).pin_memory().numpy()
+            pending.append(pipe.submit(pos, numbers, geometry.image_table(cell, pbc, basis.r_cut), xe, xf))
+            outs.append((xe, xf))
+            if len(pending) == depth:
+                pipe.wait(pending.pop(0))
+        for t in pending:
+            pipe.wait(t)
+        host = ls.GramStats(F)
+        ys = []
+        for (pos, numbers, cell, pbc), (xe, xf) in zip(frames, outs):
+            eng.build_neighbors(pos, numbers, images=geometry.image_table(cell, pbc, basis.r_cut))
+            want_e, want_f = eng.featurize()
+            assert np.array_equal(xe, want_e) and np.array_equal(xf, want_f)
+            y = rng.normal(size=3 * len(pos))
+            ys.append(y)
+            host.add_force_rows(want_f, y)
+        # fit mode over the same frames
+        pending = []
+        for (pos, numbers, cell, pbc), y in zip(frames, ys):
+            pending.append(pipe.submit_fit(pos, numbers, geometry.image_table(cell, pbc, basis.r_cut), y, np.zeros(F)))
+            if len(pending) == depth:
+                pipe.wait(pending.pop(0))
+        gram, ordinate, moments = pipe.export_gram()
+        assert np.abs(gram - host.gram_f).max() <= 1e-9 * np.abs(host.gram_f).max()
+        assert np.abs(ordinate - host.ord_f).max() <= 1e-9 * np.abs(host.ord_f).max()
+        assert moments[0] == sum(len(y) for y in ys)
+        pipe.close()
+    eng.close()

@@ -326,7 +326,11 @@ int uf3b_pipeline_export_gram(uf3b_pipeline *p, double *gram_out, double *ord_ou
     if (moments_out) moments_out[0] = moments_out[1] = moments_out[2] = 0.0;
     std::vector<double> g(gram_out ? F * F : 0), b(ord_out ? F : 0);
     std::unique_lock<std::mutex> lk(p->m);
-    p->cv.wait(lk, [&] { return p->queue.empty() && p->inflight.empty(); });       // every frame is out
+    p->cv.wait(lk, [&] {                                                            // every frame is out
+        for (const PipeSlot *s : p->slots)
+            if (s->state == QUEUED || s->state == INFLIGHT) return false;
+        return true;
+    });
     for (PipeSlot *s : p->slots) {
         if (s->rc != UF3B_OK) return fail(s->rc, "a frame failed: %s", s->err.c_str());
         if (moments_out)
