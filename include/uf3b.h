@@ -85,6 +85,9 @@ int uf3b_abi_version(void);
 
 /* Device used by subsequent create calls (default: current device). */
 int uf3b_set_device(int device);
+/* Number of CUDA devices this process can see (BasisFeaturizer.evaluate_parallel deals its
+ * batches over them; the reference deals them over worker processes, process.py:196-254). */
+int uf3b_device_count(int32_t *count);
 /* Host waits inside the library sleep on a blocking event instead of spinning in
  * cudaStreamSynchronize (process-wide; for hosts where ranks x pipeline workers outnumber cores). */
 int uf3b_set_blocking_sync(int enabled);

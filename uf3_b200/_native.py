@@ -49,6 +49,7 @@ SIGNATURES = {
     "uf3b_last_error": (C.c_char_p, []),
     "uf3b_abi_version": (C.c_int, []),
     "uf3b_set_device": (C.c_int, [C.c_int]),
+    "uf3b_device_count": (C.c_int, [_i32p]),
     "uf3b_set_blocking_sync": (C.c_int, [C.c_int]),
     "uf3b_basis_create": (C.c_int, [C.POINTER(BasisDesc), C.POINTER(C.c_void_p)]),
     "uf3b_basis_set_coefficients": (C.c_int, [C.c_void_p, _f64p, C.c_int32]),

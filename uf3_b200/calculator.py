@@ -179,3 +179,92 @@ class UFCalculator(_Base):
         _, _, w = eng.energy_forces(energy=False, forces=False, virial=True)
         volume = abs(np.linalg.det(np.asarray(cell, dtype=np.float64)))
         return (w / volume).flat[[0, 4, 8, 5, 2, 1]]
+
+    # ------------------------------------------------------------------ relaxation
+    def relax_fmax(self, geom, fmax=0.05, relax_cell=True, verbose=False, timeout=60.0, max_steps=2000,
+                   **kwargs):
+        """Minimise the largest force (calculator.py:406-436).  With ASE installed this is the
+        reference's recipe (BFGSLineSearch on an ExpCellFilter when the cell is periodic and
+        `relax_cell`).  Without ASE the same degrees of freedom — atoms in the frame of the initial
+        cell plus the deformation gradient, scaled by the atom count as ASE's cell filters do — are
+        relaxed with FIRE; the cell gradient comes from the ANALYTIC virial of the evaluator kernel,
+        one launch per step, where the reference takes twelve strained-cell energies.  Returns the
+        relaxed copy of `geom`; warns and returns the current state after `timeout` seconds."""
+        import time
+        import warnings
+        geom = geom.copy()
+        periodic_cell = bool(np.all(geom.get_pbc())) and relax_cell
+        try:  # pragma: no cover - ASE is optional
+            from ase import constraints as ase_constraints, optimize as ase_optim
+            import os
+            geom.calc = self
+            target = ase_constraints.ExpCellFilter(geom) if periodic_cell else geom
+            optimizer = ase_optim.BFGSLineSearch(target, logfile="-" if verbose else os.devnull, **kwargs)
+            t0 = time.time()
+            for _ in optimizer.irun(fmax=fmax):
+                if time.time() - t0 > timeout:
+                    warnings.warn("Relaxation timed out.", RuntimeWarning)
+                    break
+            return geom
+        except ImportError:
+            pass
+
+        positions, numbers, cell0, pbc = frame_arrays(geom)
+        cell0 = np.array(cell0, dtype=np.float64)
+        n = len(positions)
+        ref = np.array(positions, dtype=np.float64)          # atoms in the frame of the initial cell
+        deform = np.eye(3)
+        scale = float(n)                                     # ASE's cell_factor
+        eng = self.engine
+
+        def gradients():
+            pos = ref @ deform.T
+            cell = cell0 @ deform.T
+            images = geometry.image_table(cell, pbc, self.r_cut) if np.any(pbc) else None
+            eng.build_neighbors(pos, numbers, images=images)
+            if periodic_cell:
+                energy, forces, virial = eng.energy_forces(energy=True, forces=True, virial=True)
+                g_cell = -(virial @ np.linalg.inv(deform).T) / scale
+            else:
+                energy, forces = eng.energy_forces(energy=True, forces=True)
+                g_cell = np.zeros((3, 3))
+            return energy, np.vstack([forces @ deform, g_cell]), pos, cell
+
+        # FIRE (Bitzek et al. 2006) with ASE's default parameters
+        dt, dt_max, n_min, f_inc, f_dec, a_start, f_a, max_move = 0.1, 1.0, 5, 1.1, 0.5, 0.1, 0.99, 0.2
+        alpha, uphill_free = a_start, 0
+        velocity = np.zeros((n + 3, 3))
+        t0 = time.time()
+        for step in range(max_steps):
+            energy, force, pos, cell = gradients()
+            residual = float(np.sqrt((force ** 2).sum(axis=1).max()))
+            if verbose:
+                print(f"relax_fmax step {step:4d}  E = {energy:.8f}  fmax = {residual:.6f}")
+            if residual < fmax:
+                break
+            if time.time() - t0 > timeout:
+                warnings.warn("Relaxation timed out.", RuntimeWarning)
+                break
+            power = float(np.vdot(force, velocity))
+            if power > 0.0:
+                f_norm = np.sqrt(np.vdot(force, force))
+                velocity = (1.0 - alpha) * velocity + alpha * force / f_norm * np.sqrt(np.vdot(velocity, velocity))
+                if uphill_free > n_min:
+                    dt = min(dt * f_inc, dt_max)
+                    alpha *= f_a
+                uphill_free += 1
+            else:
+                velocity[:] = 0.0
+                alpha, dt, uphill_free = a_start, dt * f_dec, 0
+            velocity += dt * force
+            move = dt * velocity
+            longest = float(np.sqrt(np.vdot(move, move)))
+            if longest > max_move:
+                move *= max_move / longest
+            ref += move[:n]
+            deform += move[n:] / scale
+        else:
+            warnings.warn("Relaxation stopped after max_steps.", RuntimeWarning)
+        geom.set_cell(cell0 @ deform.T, scale_atoms=False)
+        geom.set_positions(ref @ deform.T)
+        return geom

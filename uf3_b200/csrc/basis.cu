@@ -113,6 +113,14 @@ int uf3b_set_device(int device) {
     return UF3B_OK;
 }
 
+int uf3b_device_count(int32_t *count) {
+    if (!count) return fail(UF3B_ERR_INVALID, "count is null");
+    int n = 0;
+    UF3B_CUDA(cudaGetDeviceCount(&n));
+    *count = n;
+    return UF3B_OK;
+}
+
 int uf3b_host_eval_basis(const double *knots, int32_t n_knots, double r, double *v, double *dv) {
     if (!knots || n_knots < 8 || !v || !dv) return fail(UF3B_ERR_INVALID, "bad knot vector");
     std::vector<double> poly;

@@ -1,8 +1,9 @@
 // gram.cu — normal-equation accumulation  G += X^T X,  b += X^T y  in float64.
 //
 // Default: the hand-written k_gram / k_ordinate below.  UF3B_GRAM_KERNEL=cublas selects cuBLAS
-// dsyrk + dgemv instead (a plain library rank-k update; measured 10 % faster at 456 columns,
-// 35 % slower at 73 — 30 000 x F is a skinny shape for it); the tests hold both paths equal.
+// dsyrk + dgemv instead (a plain library rank-k update; measured SLOWER than the DMMA kernel below
+// at both widths — 30 000 x F is a skinny shape for it; profiles/README.md); the tests hold both
+// paths equal.
 //
 // Replaces regression/least_squares.py:733-771 (batched_moore_penrose) for feature rows
 // that are already on the device, so a frame's 3N x F force rows never have to be

@@ -303,6 +303,67 @@ class WeightedLinearModel:
             gram, ordinate = self.combine_weighted_gram(gram, gram_f, ordinate, ord_f, w_e, w_f, weight)
         self.fit_with_gram(gram, ordinate)
 
+    def fit_from_file(self, filename, subset, weight=0.5, batch_size=2500, sample_weights=None,
+                      energy_key="energy", progress="bar", drop_columns=None, gram="auto"):
+        """Fit from a chunked feature store written by `BasisFeaturizer.batched_to_hdf`
+        (least_squares.py:355-433): the tables are read in sorted order, the rows of the
+        configurations in `subset` are folded into the energy / force normal equations together
+        with the running target statistics, and the regularised system is solved once.
+        `gram`: "device" folds the force rows on the GPU (`uf3b_gram_accumulate` reads the host
+        rows of a chunk; FP64 tensor cores), "host" uses numpy as the reference does, "auto" takes
+        the device when the model was created with solver="cusolver"."""
+        import os
+        from uf3_b200 import store
+        if not os.path.isfile(filename):
+            raise FileNotFoundError(filename)
+        on_device = gram == "device" or (gram == "auto" and getattr(self, "solver", "host") == "cusolver")
+        n_tables, _, table_names, _ = store.analyze_hdf_tables(filename)
+        n_elements = len(self.bspline_config.element_list)
+        stats = None
+        subset = list(subset)
+        for table_name in table_names:
+            df = store.load_feature_db(filename, table_name)
+            keys = df.index.unique(level=0).intersection(subset)
+            if len(keys) == 0:
+                continue
+            if drop_columns is not None:
+                df = df.drop(columns=drop_columns)
+            x_e, y_e, x_f, y_f = dataframe_to_tuples(df.loc[keys], n_elements=n_elements, energy_key=energy_key,
+                                                     sample_weights=sample_weights)
+            if stats is None:
+                stats = (GramAccumulator if on_device else GramStats)(x_e.shape[1])
+            stats.add_rows(x_e, y_e, is_force=False)
+            if len(y_f):
+                stats.add_rows(x_f, y_f, is_force=True)
+        if stats is None:
+            raise ValueError("no configuration of `subset` is in " + str(filename))
+        self.fit_from_accumulator(stats, weight=weight)
+        if on_device:
+            stats.close()
+
+    def batched_predict(self, filename, keys=None, table_names=None, score=True, drop_columns=None):
+        """Targets and predictions of the rows of a feature store (least_squares.py:486-526, :1060-1118)."""
+        from uf3_b200 import store
+        if table_names is None:
+            _, _, table_names, _ = store.analyze_hdf_tables(filename)
+        n_elements = len(self.bspline_config.element_list)
+        y_e, p_e, y_f, p_f = [], [], [], []
+        for df in store.dataframe_batch_loader(filename, table_names):
+            if keys is not None:
+                found = df.index.unique(level=0).intersection(keys)
+                if len(found) == 0:
+                    continue
+                df = df.loc[found]
+            if drop_columns is not None:
+                df = df.drop(columns=drop_columns)
+            x_e, t_e, x_f, t_f = dataframe_to_tuples(df, n_elements=n_elements)
+            y_e.append(t_e); p_e.append(self.predict(x_e))
+            y_f.append(t_f); p_f.append(self.predict(x_f))
+        y_e, p_e, y_f, p_f = (np.concatenate(v) if v else np.zeros(0) for v in (y_e, p_e, y_f, p_f))
+        if score:
+            return y_e, p_e, y_f, p_f, rmse_metric(y_e, p_e), rmse_metric(y_f, p_f)
+        return y_e, p_e, y_f, p_f
+
     def predict(self, x):
         return np.dot(x, self.coefficients)
 
@@ -344,6 +405,16 @@ class GramStats:
         self.gram_f += x.T @ x
         self.ord_f += x.T @ y
         self._count(y, True)
+
+    def add_rows(self, x, y, is_force):
+        """Rows that are already in fit form (energy rows divided by the atom count)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        if is_force:
+            return self.add_force_rows(x, y)
+        self.gram_e += x.T @ x
+        self.ord_e += x.T @ y
+        self._count(y, False)
 
     def _blocks(self):
         return self.gram_e, self.gram_f, self.ord_e, self.ord_f
@@ -420,6 +491,16 @@ class GramAccumulator(GramStats):
             raise ValueError("one target per force row is required")
         self._native.check(self._lib.uf3b_gram_accumulate(
             self._handle, C.c_void_p(x_ptr), C.c_void_p(y.ctypes.data), int(rows), int(ld), 1, stream))
+        self._count(y, True)
+
+    def add_force_rows(self, x_forces, y_forces):
+        """Host rows folded by the device kernel (the C ABI takes host or device pointers)."""
+        x = np.ascontiguousarray(x_forces, dtype=np.float64)
+        y = np.ascontiguousarray(y_forces, dtype=np.float64).reshape(-1)
+        if x.ndim != 2 or x.shape[1] != self.n_feats or len(y) != len(x):
+            raise ValueError("force rows must be (rows, n_feats) with one target per row")
+        self._native.check(self._lib.uf3b_gram_accumulate(
+            self._handle, C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), len(y), x.shape[1], 1, None))
         self._count(y, True)
 
     def _device_force_block(self):

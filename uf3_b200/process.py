@@ -189,14 +189,87 @@ class BasisFeaturizer:
         df = pd.DataFrame.from_dict(eval_map, orient="index", columns=self.columns)
         return df.set_index(pd.MultiIndex.from_tuples(df.index))
 
+    def _visible_devices(self):
+        import ctypes as C
+        from uf3_b200 import _native
+        count = C.c_int32()
+        _native.check(_native.lib().uf3b_device_count(C.byref(count)))
+        return int(count.value)
+
+    def _on_device(self, device):
+        """A copy of this featurizer bound to `device` (its engine is created where it is used)."""
+        clone = BasisFeaturizer(self.bspline_config, fit_forces=self.fit_forces, prefix=self.prefix,
+                                device=device)
+        return clone
+
     def evaluate_parallel(self, df_data, client=None, atoms_key="geometry", energy_key="energy",
                           n_jobs=2, shuffle=True, progress="bar"):
-        """Reference signature (process.py:196-254).  The reference fans batches out to a
-        process pool because one configuration costs seconds of CPU; here one GPU keeps up
-        with the whole stream, so `client` / `n_jobs` are accepted and batches are run in
-        order on this process's device.  Multi-GPU fits shard frames over ranks instead
-        (`uf3_b200.distributed`)."""
-        return self.evaluate(df_data, atoms_key=atoms_key, energy_key=energy_key, progress=progress)
+        """Reference signature and semantics (process.py:196-254): the data frame is cut into
+        `n_jobs` batches (shuffled first when `shuffle`), the batches are evaluated concurrently and
+        the result is returned in the order of `df_data`.  The reference deals the batches over the
+        worker processes of `client`; here batch k runs on visible GPU k mod n_gpus, each with its own
+        engine.  `client` may be a `concurrent.futures` executor (a process pool receives pickled
+        featurizers, which re-create their device handles in the worker, as the reference's do);
+        with `client=None` one thread per GPU drives the batches (the C ABI releases the GIL)."""
+        import pandas as pd
+        if n_jobs < 2:
+            warnings.warn("Processing in serial.", RuntimeWarning)
+            return self.evaluate(df_data, atoms_key=atoms_key, energy_key=energy_key)
+        order = np.arange(len(df_data))
+        if shuffle:
+            np.random.shuffle(order)
+        batches = [df_data.iloc[part] for part in np.array_split(order, n_jobs) if len(part)]
+        n_gpus = max(self._visible_devices(), 1)
+        workers = [self._on_device(k % n_gpus) for k in range(len(batches))]
+        kwargs = dict(atoms_key=atoms_key, energy_key=energy_key, progress=False)
+        own_pool = None
+        if client is None:
+            from concurrent.futures import ThreadPoolExecutor
+            client = own_pool = ThreadPoolExecutor(max_workers=min(n_gpus, len(batches)))
+        try:
+            futures = [client.submit(_evaluate_batch, worker, batch, kwargs)
+                       for worker, batch in zip(workers, batches)]
+            frames = [future.result() for future in futures]
+        finally:
+            if own_pool is not None:
+                own_pool.shutdown()
+        df_features = pd.concat(frames)
+        names = df_features.index.get_level_values(0)
+        # rows of one configuration stay together, configurations in the order of df_data
+        rank = {name: k for k, name in enumerate(df_data.index)}
+        position = np.argsort(np.array([rank[name] for name in names]), kind="stable")
+        return df_features.iloc[position]
+
+    def batched_to_hdf(self, filename, df_data, client=None, n_jobs=16, batch_size=50, progress="bar",
+                       table_template="features_{}", **kwargs):
+        """Stream the feature rows of `df_data` into a chunked store, `batch_size` configurations per
+        table (process.py:256-291).  Tables that are already in `filename` are skipped, so an
+        interrupted run resumes where it stopped.  The store is the reference's HDF5 layout when
+        PyTables is present and a chunk archive otherwise (`uf3_b200.store`); either is what
+        `WeightedLinearModel.fit_from_file` reads."""
+        import os
+        from uf3_b200 import store
+        idx_all = np.arange(len(df_data))
+        idx_batches = np.array_split(idx_all, idx_all[batch_size::batch_size])
+        digits = max(int(np.ceil(np.log10(len(idx_batches)) + 0.1)), 3)
+        if os.path.isfile(filename):
+            n_chunks, _, chunk_names, _ = store.analyze_hdf_tables(filename)
+            warnings.warn(f"File already exists: contains {n_chunks} chunks.", RuntimeWarning)
+        else:
+            chunk_names = []
+        kwargs["progress"] = False
+        kwargs["n_jobs"] = n_jobs
+        for j, idx_batch in enumerate(idx_batches):
+            table_name = table_template.format(str(j).rjust(digits, "0"))
+            if table_name in chunk_names:
+                continue
+            df_features = self.evaluate_parallel(df_data.iloc[idx_batch], client, **kwargs)
+            store.save_feature_db(df_features, filename, table_name=table_name)
+
+
+def _evaluate_batch(featurizer, batch, kwargs):
+    """Module-level so that a process pool can pickle the call (util/parallel.py:182)."""
+    return featurizer.evaluate(batch, **kwargs)
 
 
 def flatten_by_interactions(vector_map, pair_tuples):
