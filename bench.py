@@ -30,6 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "bulk bcc W 10x20x25 cells (10000 atoms/frame), sigma=0.05 A, 2+3-body featurization"
+# --basis binary: the Fe-C basis of the reference's own golden rows (tests/test_representation.py:605-648,
+# six trios, two of symmetry 1, F = 609) on a B2 lattice of the same 10x20x25 cells
+WORKLOAD_BINARY = ("B2 Fe-C 10x20x25 cells (10000 atoms/frame), a=2.87 A, sigma=0.05 A, 2+3-body featurization "
+                   "(55 neighbours inside the 5 A three-body cutoff)")
 N_POOL = 8          # distinct frames (inputs AND output row buffers) per rank, cycled
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the
 # `ncu --set full` captures summarised under profiles/ (r01_k_featurize_v20_legcache_details.txt,
@@ -49,7 +53,7 @@ except (OSError, ValueError):
 
 def bench_config(basis_name, n_feats):
     """`config` of the JSON line: the same dictionary in both arms (the driver compares them)."""
-    return {"workload": WORKLOAD, "basis": basis_name, "n_feats": int(n_feats),
+    return {"workload": WORKLOAD_BINARY if basis_name == "binary" else WORKLOAD, "basis": basis_name, "n_feats": int(n_feats),
             "step": "one 10000-atom frame per rank: neighbour lists + energy row + 3N force rows"}
 
 
@@ -159,13 +163,18 @@ class ClockSampler:
         return out
 
 
+BASIS_KIND = "demo"      # set from --basis: frame() follows it
+
+
 def make_basis(kind):
     from uf3_b200 import synthetic
-    return synthetic.w_basis(kind)
+    return synthetic.fec_basis() if kind == "binary" else synthetic.w_basis(kind)
 
 
 def frame(seed):
     from uf3_b200 import synthetic
+    if BASIS_KIND == "binary":
+        return synthetic.b2_fec((10, 20, 25), seed=seed)
     return synthetic.bcc_w((10, 20, 25), seed=seed)
 
 
@@ -500,7 +509,7 @@ def run_ours(args, rank, world, local_rank):
     # taking half of an SM's resources (frames_in_flight=2): two frames' kernels share every SM, so
     # one frame's tail and the next frame's list build (which ends in a host wait) fill each other's
     # gaps.  (The block-per-atom kernel of the manuscript basis measured slower that way.)
-    n_slots = int(os.environ.get("UF3B_BENCH_SLOTS", "3" if args.basis == "demo" else "2"))
+    n_slots = int(os.environ.get("UF3B_BENCH_SLOTS", "3" if args.basis == "demo" else ("1" if args.basis == "binary" else "2")))
     in_flight = int(os.environ.get("UF3B_BENCH_IN_FLIGHT", "2" if args.basis == "demo" else "1"))
     slots = [(Engine(basis, device=local_rank, frames_in_flight=in_flight), torch.cuda.Stream(dev))
              for _ in range(n_slots)]
@@ -587,7 +596,7 @@ def run_ours(args, rank, world, local_rank):
     fp64_achieved = fp64_flop / (k_ms * 1e-3) / 1e12 if fp64_flop else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu_frames = 4
+        n_cpu_frames = 1 if args.basis == "binary" else 4
         t_cpu = oracle_frames_per_second(basis, n_cpu_frames, 1)
         cpu = {"value": n_cpu_frames * n_atoms / t_cpu, "unit": "atom-steps/s", "cores": 1,
                "kind": "port",
@@ -624,7 +633,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm",
                      "kernel": ("k_centre_legs + k_rows_nbr<3,9> + k_rows_ctr<3,9>" if tiled
-                                else "k_leg_cache + k_featurize_coop<8>"),
+                                else ("k_rows_multi<1>" if args.basis == "binary" else "k_leg_cache + k_featurize_coop<8>")),
                      "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES.get(args.basis),
@@ -845,7 +854,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--basis", default="demo", choices=["demo", "manuscript"])
+    ap.add_argument("--basis", default="demo", choices=["demo", "manuscript", "binary"],
+                    help="demo / manuscript: the two W bases of BASELINE.json configs[1]; binary: the reference's Fe-C "
+                         "test basis (six trios) on a B2 lattice — the several-species kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
     ap.add_argument("--extra", dest="extra", action="store_true", default=True,
                     help="also time the inference configs: Ne/Xe 50k and W 100k at one GPU, the 100k-atom MD "
@@ -856,6 +867,8 @@ def main():
                     help="featurize = BASELINE.json headline (default); md = configs[4] MD loop, strong scaling; "
                          "fit = configs[3] featurize + normal equations + all-reduce + solve")
     args = ap.parse_args()
+    global BASIS_KIND
+    BASIS_KIND = args.basis
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

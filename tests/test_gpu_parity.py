@@ -202,6 +202,29 @@ def test_tile_paths_and_scatter_path_agree(name, monkeypatch):
         assert gu.rel_err(outs[other][0], outs[2][0]) <= 1e-11
 
 
+@pytest.mark.parametrize("name", ["ref_steel_pbc", "syn_ternary_triclinic", "syn_ternary_mixed_pbc", "ref_h2o_trimA",
+                                  "ref_ch4_trimB", "dev_w16_sym1"])
+def test_general_leg_grouped_kernel_and_scatter_path_agree(name, monkeypatch):
+    """Several species, trios of symmetry 1 and long rows take k_rows_multi (featurize_multi.cu: planes per
+    leg group and partner class); UF3B_NO_MULTI sends the frame to the per-triangle scatter path.  The two
+    share no 3-body code beyond the leg evaluation."""
+    case = gu.Case(name)
+    outs = []
+    for env in ({}, {"UF3B_NO_MULTI": "1"}):
+        monkeypatch.delenv("UF3B_NO_MULTI", raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        _, eng, _ = _engine_for(case)
+        outs.append(eng.featurize())
+        xe_only, _ = eng.featurize(energy=True, forces=False)
+        assert gu.rel_err(xe_only, outs[-1][0]) <= 1e-13
+        eng.close()
+    assert gu.rel_err(outs[0][0], outs[1][0]) <= 1e-11 and gu.rel_err(outs[0][1], outs[1][1]) <= 1e-11
+    assert gu.rel_err(outs[0][0], case["x_energy"]) <= REL
+    if not name.startswith("dev_"):         # the documented deviation: tests/test_deviation_fixture.py
+        assert gu.rel_err(outs[0][1], case["x_forces"]) <= REL
+
+
 def test_grid_reuse_between_builds_keeps_the_lists_exact():
     """Consecutive builds on one handle reuse the cell grid while the atoms stay within its
     skin (MD steps) and fall back to a fresh grid when they leave it; the lists stay the
@@ -301,10 +324,37 @@ def test_headline_frame_10k_atoms_manuscript_basis_matches_oracle():
     eng.close()
 
 
+def test_binary_fec_10k_atoms_matches_oracle():
+    """The reference's Fe-C test basis (tests/test_representation.py:605-648: six trios, two of symmetry 1,
+    609 columns) on a 10 000-atom B2 lattice, 55 neighbours inside the three-body cutoff: k_rows_multi at
+    full size against the oracle, plus translation invariance and bit reproducibility."""
+    from uf3_b200 import synthetic
+    basis = synthetic.fec_basis()
+    pos, numbers, cell, pbc = synthetic.b2_fec((10, 20, 25), seed=3)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    packed = orc.PackedBasis(basis)
+    eng = Engine(basis)
+    eng.build_neighbors(pos, numbers, images=images)
+    for which in (2, 3):
+        off, idx = eng.neighbor_list(which)
+        want_off, want_idx = orc.neighbor_lists(packed, pos, numbers, images[1], which)
+        assert np.array_equal(off, want_off) and np.array_equal(idx, want_idx)
+    assert int(np.diff(eng.neighbor_list(3)[0]).max()) > 32
+    xe, xf = eng.featurize()
+    want_e, want_f = orc.featurize(packed, pos, numbers, images[1])
+    assert gu.rel_err(xe, want_e) <= REL and gu.rel_err(xf, want_f) <= REL
+    n = len(pos)
+    assert np.abs(xf.reshape(3, n, -1).sum(axis=1)).max() <= 1e-9 * np.abs(xf).max() * n
+    assert xe[0] == n // 2 and xe[1] == n // 2
+    xe2, xf2 = eng.featurize()
+    assert np.array_equal(xe, xe2) and np.array_equal(xf, xf2)
+    eng.close()
+
+
 @pytest.mark.parametrize("kind,a,sigma,expect", [
     ("demo", 2.45, 0.04, "rows of ~26 entries: leg cache with long rows"),
     ("manuscript", 2.95, 0.05, "rows of ~26 entries: cooperative kernel with 28-32 record slots"),
-    ("demo", 2.10, 0.03, "rows above 32 entries: per-triangle fallback path"),
+    ("demo", 2.10, 0.03, "rows above 32 entries: the general leg-grouped kernel (k_rows_multi)"),
     ("manuscript", 3.165, 0.30, "strongly rattled: ragged rows, legs outside the knot range"),
 ])
 def test_dense_and_ragged_lattices_match_oracle(kind, a, sigma, expect):

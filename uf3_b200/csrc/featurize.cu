@@ -1469,6 +1469,11 @@ extern "C" int uf3b_featurize(uf3b_basis *basis, const uf3b_nlist *nl, double *x
         if (deferred)       // another path takes the frame: it needs the verified lists
             if (int rc2 = nlist_resolve(nl_rw)) return rc2;
     }
+    // several species, symmetry-1 trios, long rows: the general leg-grouped kernel (featurize_multi.cu)
+    if (!basis->no_tile) {
+        const int rc = featurize_multi(basis, nl, x_energy, x_forces, ld, stream);
+        if (rc <= 0) return rc;
+    }
     // launch shape: as many warps per SM as shared memory and registers allow, grid sized to
     // the SM count
     int dev = 0, smem_max = 0, smem_sm = 0;

@@ -93,4 +93,8 @@ int finish_featurize(uf3b_basis *basis, double *x_energy, double *x_forces, int6
 int featurize_tiled(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, double *x_forces, int64_t ld,
                     cudaStream_t stream, bool deferred);
 
+// featurize_multi.cu: several species / symmetry-1 trios / long rows; returns 1 when it does not apply
+int featurize_multi(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, double *x_forces, int64_t ld,
+                    cudaStream_t stream);
+
 }  // namespace uf3b

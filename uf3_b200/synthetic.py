@@ -58,3 +58,31 @@ def nexe(reps=(25, 25, 10), a=8.0, sigma=0.1, seed=0):
     pos = pos + rng.normal(0, sigma, pos.shape)
     numbers = np.array([10] * len(ne) + [54] * len(xe), dtype=np.int32)
     return pos, numbers, np.diag(np.array(reps) * a), np.ones(3, bool)
+
+
+# tests/test_representation.py:605-648 of the reference (the Fe-C basis of its committed golden rows,
+# rattled_steel_features.json): six trios, two of them of symmetry 1; F = 609
+_FEC_PAIRS = [("Fe", "Fe"), ("Fe", "C"), ("C", "C")]
+_FEC_TRIOS = [("Fe", "Fe", "Fe"), ("Fe", "Fe", "C"), ("Fe", "C", "C"),
+              ("C", "Fe", "Fe"), ("C", "Fe", "C"), ("C", "C", "C")]
+FEC = dict(r_min_map={**{p: 0.1 for p in _FEC_PAIRS}, **{t: [1.5, 1.5, 1.5] for t in _FEC_TRIOS}},
+           r_max_map={**{p: 6.0 for p in _FEC_PAIRS}, **{t: [5.0, 5.0, 10.0] for t in _FEC_TRIOS}},
+           resolution_map={**{p: 12 for p in _FEC_PAIRS}, **{t: [4, 4, 8] for t in _FEC_TRIOS}},
+           knot_strategy="linear", offset_1b=True, leading_trim=0, trailing_trim=3)
+
+
+def fec_basis():
+    chem = composition.ChemicalSystem(["Fe", "C"], degree=3)
+    return bspline.BSplineBasis(chem, **FEC)
+
+
+def b2_fec(reps=(10, 20, 25), a=2.87, sigma=0.05, seed=0):
+    """B2 (CsCl-type) Fe-C: Fe on the cube corners, C on the body centres; N = 2 * prod(reps).
+    At a = 2.87 A every atom has 58 neighbours inside the 5 A three-body cutoff of `FEC`
+    (1 653 triangles per centre, against 91 in bulk W with the demo basis)."""
+    rng = np.random.default_rng(seed)
+    cells = _cells(reps)
+    pos = np.concatenate([cells, cells + 0.5]) * a
+    pos = pos + rng.normal(0, sigma, pos.shape)
+    numbers = np.array([26] * len(cells) + [6] * len(cells), dtype=np.int32)
+    return pos, numbers, np.diag(np.array(reps) * a), np.ones(3, bool)
