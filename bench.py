@@ -376,9 +376,14 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # many ranks x pipeline workers on one host: sleeping waits instead of spinning ones
-    if world >= 4 or os.environ.get("UF3B_BLOCKING_SYNC") == "1":
-        _native.check(_native.lib().uf3b_set_blocking_sync(1))
+    # many ranks x pipeline threads on one host: sleeping waits instead of spinning ones — for the
+    # host-buffer arms only; the resident arm and the MD loop have one driving thread per rank, which spins
+    # (a sleeping wait costs its wake-up latency on every list build: measured 0.42 vs 0.25 ms per step at 8 ranks)
+    env_block = os.environ.get("UF3B_BLOCKING_SYNC")
+    blocking_e2e = (world >= 4 and env_block != "0") or env_block == "1"
+
+    def blocking(enabled):
+        _native.check(_native.lib().uf3b_set_blocking_sync(1 if (enabled and blocking_e2e) else 0))
 
     basis = make_basis(args.basis)
     eng = Engine(basis, device=local_rank)
@@ -427,7 +432,9 @@ def run_ours(args, rank, world, local_rank):
         h_y.append((d_xf @ c_dev).cpu().pin_memory().numpy())
         e_target.append(float(d_xe @ c_dev))
     h_xf_check = d_xf.cpu().numpy()         # rows of the last pool frame, for the sanity check of the fit
+    blocking(True)          # the pipeline's events take their wait mode when they are created
     pipe = NativePipeline(basis, depth=e2e_depth, device=local_rank)
+    blocking(False)
     h_xe = [torch.empty(F, dtype=torch.float64).pin_memory().numpy() for _ in range(e2e_depth)]
     fit_info = {}
 
@@ -462,7 +469,7 @@ def run_ours(args, rank, world, local_rank):
         # the force targets of a frame (columns without signal — trimmed, frozen — are free to differ)
         y_fit = h_xf_check @ model.coefficients
         fit_info.update(frames_ms=(t1 - t0) * 1e3, all_reduce_ms=(t2 - t1) * 1e3, solve_ms=(t3 - t2) * 1e3,
-                        frames_only_value=world * n_atoms * steps / ((t1 - t0) * 1e-3),
+                        frames_only_value=world * n_atoms * steps / (t1 - t0),
                         force_prediction_error_rel=float(np.linalg.norm(y_fit - h_y[N_POOL - 1])
                                                          / np.linalg.norm(h_y[N_POOL - 1])))
         return max_over_ranks((t3 - t0) * 1e3)
@@ -552,11 +559,13 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     total_ms, launches = timed(args.steps, args.warmup)
+    blocking(True)
     run_e2e_fit(max(args.warmup, e2e_depth))        # warm-up: buffers, NCCL connections, cuSOLVER handle
     e2e_ms = run_e2e_fit(args.steps)
     clocks = sampler.stop() if rank == 0 else None
     run_e2e_rows(args.warmup)
     rows_ms = run_e2e_rows(args.steps)
+    blocking(False)
     copy_gbs = d2h_ceiling()
 
     # dominant kernels (the row kernels of Kernel B), timed alone with CUDA events on their stream
@@ -633,7 +642,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm",
                      "kernel": ("k_centre_legs + k_rows_nbr<3,9> + k_rows_ctr<3,9>" if tiled
-                                else ("k_rows_multi<1>" if args.basis == "binary" else "k_leg_cache + k_featurize_coop<8>")),
+                                else ("k_rows_multi2<4>" if args.basis == "binary" else "k_leg_cache + k_featurize_coop<8>")),
                      "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES.get(args.basis),

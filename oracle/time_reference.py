@@ -3,7 +3,7 @@
 container only; the reference cannot travel to the GPU box and cannot hold frames above
 ~2 000 atoms: dense M x M distance matrices).
 
-    python oracle/time_reference.py > profiles/r01_reference_as_is_cpu.json
+    python oracle/time_reference.py [--parallel] > profiles/r02_reference_as_is_cpu.json
 
 Rattled bcc W (a = 3.165 A, sigma = 0.05 A), demo 2+3-body basis (73 columns), energy row +
 3N force rows through `BasisFeaturizer.evaluate_configuration` (process.py:293), one process,
@@ -61,7 +61,37 @@ def main():
         t = statistics.median(times)
         out["runs"].append({"n_atoms": n, "seconds_per_frame": t, "atom_steps_per_s": n / t, "repeats": repeats})
         print(f"{n} atoms: {t:.3f} s/frame, {n / t:.1f} atom-steps/s", file=sys.stderr)
+    if "--parallel" in sys.argv:
+        out["parallel"] = parallel_runs(feat)
     print(json.dumps(out, indent=1))
+
+
+def parallel_runs(feat):
+    """The reference's own parallel mode: `BasisFeaturizer.evaluate_parallel`
+    (process.py:196-254) over a `ProcessPoolExecutor(max_workers=cores)`, 4 x cores frames of 128 atoms
+    (the size its example data set has), every host core busy."""
+    import pandas as pd
+    from concurrent.futures import ProcessPoolExecutor
+    cores = os.cpu_count() or 1
+    n_frames = 4 * cores
+    rows = {}
+    for k in range(n_frames):
+        geom = bcc_w((4, 4, 4), seed=100 + k)
+        n = len(geom)
+        rows[f"w_{k}"] = {"geometry": geom, "energy": 0.0, "fx": np.zeros(n), "fy": np.zeros(n), "fz": np.zeros(n)}
+    df = pd.DataFrame.from_dict(rows, orient="index")
+    runs = []
+    with ProcessPoolExecutor(max_workers=cores) as pool:
+        feat.evaluate_parallel(df.iloc[:cores], pool, n_jobs=cores, progress=False)        # numba warm-up per worker
+        t0 = time.perf_counter()
+        table = feat.evaluate_parallel(df, pool, n_jobs=cores, progress=False)
+        t = time.perf_counter() - t0
+    assert len(table) == n_frames * (1 + 3 * n)
+    runs.append({"n_atoms": n, "frames": n_frames, "workers": cores, "seconds": t,
+                 "atom_steps_per_s": n_frames * n / t})
+    print(f"parallel: {n_frames} frames x {n} atoms on {cores} workers: {t:.1f} s, {n_frames * n / t:.1f} atom-steps/s",
+          file=sys.stderr)
+    return runs
 
 
 if __name__ == "__main__":

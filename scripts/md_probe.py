@@ -21,6 +21,9 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+if os.environ.get("UF3B_BLOCKING_SYNC") == "1":
+    from uf3_b200 import _native
+    _native.check(_native.lib().uf3b_set_blocking_sync(1))
 basis, coeff = bench.w_model23()
 pos, numbers, cell, pbc = synthetic.bcc_w((25, 40, 50), a=3.206, sigma=0.15, seed=0)
 n = len(pos)

@@ -250,6 +250,13 @@ int uf3b_pipeline_create(const uf3b_basis_desc *desc, int32_t depth, uf3b_pipeli
         PipeSlot *s = new PipeSlot();
         p->slots.push_back(s);
         int rc = uf3b_basis_create(desc, &s->basis);
+        // consecutive frames run on different slots' streams: each launch takes half of the SM resources, so
+        // that the tail of one frame's kernels and the list build of the next share the chip
+        // (uf3b_basis_set_frames_in_flight; UF3B_PIPE_IN_FLIGHT overrides)
+        if (rc == UF3B_OK && depth >= 2) {
+            const char *env = getenv("UF3B_PIPE_IN_FLIGHT");
+            rc = uf3b_basis_set_frames_in_flight(s->basis, env ? std::max(1, atoi(env)) : 2);
+        }
         if (rc == UF3B_OK && cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
             rc = fail(UF3B_ERR_CUDA, "cudaStreamCreate failed");
         if (rc == UF3B_OK && cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming

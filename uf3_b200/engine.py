@@ -95,8 +95,13 @@ class Engine:
 
     def build_neighbors_device(self, positions_ptr, numbers_ptr, n_atoms, images, stream=None, centres=None):
         """Same with DEVICE pointers for positions (n,3 float64) and numbers (n int32)."""
-        abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
-        offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
+        cached = getattr(self, "_images_cache", None)
+        if cached is not None and cached[0] is images:      # MD loops pass the same table every step
+            abc, offsets = cached[1], cached[2]
+        else:
+            abc = np.ascontiguousarray(images[0], dtype=np.int32).reshape(-1, 3)
+            offsets = np.ascontiguousarray(images[1], dtype=np.float64).reshape(-1, 3)
+            self._images_cache = (images, abc, offsets)
         first, count = (0, int(n_atoms)) if centres is None else centres
         self._last_build = (positions_ptr, numbers_ptr, int(n_atoms), offsets, abc, int(first), int(count), stream)
         self._build_device()
