@@ -105,6 +105,101 @@ k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols, i
             }
 }
 
+// Narrow rows (n_cols + 1 <= 80: the 73-column demo basis): ONE pass over the rows gives G and b —
+// the block keeps the whole augmented product [X | y]^T [X | y] (80 x 80 after padding) in the
+// registers of its 8 warps.  The 10 x 10 grid of m8n8 tiles is cut into 5 x 5 macro tiles of 16 x 16; the
+// 15 macro tiles with I <= J are dealt to the warps two at a time, so every staged row is read from
+// shared memory 8 times per warp for 8 DMMA (k_gram spends a 64 x 64 tile grid of 2 x 2 on 73 columns:
+// three quarters of its products are padding, and b costs k_ordinate a second pass over the rows).
+constexpr int GN = 80;        // padded width of the augmented rows
+constexpr int GNS = GN + 4;   // shared-memory row stride (doubles): = 4 mod 16, as GS
+
+__global__ void __launch_bounds__(256)
+k_gram_narrow(const double *__restrict__ x, long long ld, const double *__restrict__ y, long long rows, int n_cols,
+              int rows_per_block, double *__restrict__ g, double *__restrict__ b, const int *__restrict__ invalid) {
+    if (invalid && *invalid) return;
+    __shared__ __align__(16) double sx[GK][GNS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane & 3, fc = lane >> 2;            // fragment row (k) and column
+    const long long r_begin = (long long)blockIdx.x * rows_per_block;
+    const long long r_end = r_begin + rows_per_block < rows ? r_begin + rows_per_block : rows;
+    if (r_begin >= r_end) return;
+    // macro tiles (I <= J) of the 5 x 5 grid, row-major: t -> (I, J); warp w takes t = w and t = w + 8
+    int mi_[2], mj_[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int t = warp + 8 * q, I = 0;
+        if (t > 14) t = 14;                     // warp 7 repeats the last tile and drops the copy below
+        while (t >= 5 - I) { t -= 5 - I; ++I; }
+        mi_[q] = I;
+        mj_[q] = I + t;
+    }
+    const bool second = warp + 8 <= 14;
+    // element e = threadIdx.x + 256 i of a stage (GK x GN): row e / GN, column e % GN
+    double reg[5];
+    auto fetch = [&](long long r0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int e = threadIdx.x + 256 * i, row = e / GN, col = e - row * GN;
+            const long long r = r0 + row;
+            double v = 0.0;
+            if (r < r_end) {
+                if (col < n_cols) v = __ldg(x + r * ld + col);
+                else if (col == n_cols) v = __ldg(y + r);
+            }
+            reg[i] = v;
+        }
+    };
+    double acc[2][2][2][2] = {};
+    fetch(r_begin);
+    for (long long r0 = r_begin; r0 < r_end; r0 += GK) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int e = threadIdx.x + 256 * i, row = e / GN, col = e - row * GN;
+            sx[row][col] = reg[i];
+        }
+        __syncthreads();
+        if (r0 + GK < r_end) fetch(r0 + GK);
+#pragma unroll
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double fa[2], fb[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    fa[h] = sx[k4 + fr][mi_[q] * 16 + h * 8 + fc];
+                    fb[h] = sx[k4 + fr][mj_[q] * 16 + h * 8 + fc];
+                }
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) dmma_m8n8k4(acc[q][a][c][0], acc[q][a][c][1], fa[a], fb[c]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q == 1 && !second) continue;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double v = acc[q][a][c][h];
+                    const int row = mi_[q] * 16 + a * 8 + fc, col = mj_[q] * 16 + c * 8 + 2 * fr + h;
+                    if (v == 0.0 || row >= n_cols) continue;
+                    if (col < n_cols) {
+                        atomicAdd(g + (size_t)row * n_cols + col, v);
+                        if (mi_[q] != mj_[q]) atomicAdd(g + (size_t)col * n_cols + row, v);   // mirror of an off-diagonal macro tile
+                    } else if (col == n_cols) {
+                        atomicAdd(b + row, v);
+                    }
+                }
+    }
+}
+
 constexpr int OROWS = 256;    // rows per block of k_ordinate
 
 // b += X^T y: block = 32 columns x OROWS rows; warp w takes rows w, w + 8, ... (coalesced
@@ -202,6 +297,18 @@ int uf3b::gram_accumulate_guarded(uf3b_gram *gm, const double *x, const double *
                              gm->b[which], 1);
         if (st != CUBLAS_STATUS_SUCCESS) return fail(UF3B_ERR_CUDA, "cuBLAS dsyrk/dgemv status %d", (int)st);
         g_launches.fetch_add(2, std::memory_order_relaxed);
+        if (dx != x || dy != y) UF3B_CUDA(stream_sync(stream));
+        return UF3B_OK;
+    }
+    static const bool generic_only = getenv("UF3B_GRAM_GENERIC") != nullptr;
+    if (gm->n_cols + 1 <= GN && !generic_only) {
+        // about two blocks per SM, whole stages each
+        static const long long bps = getenv("UF3B_GRAM_BPS") ? std::max(1, atoi(getenv("UF3B_GRAM_BPS"))) : 2;
+        long long rpb = (rows + bps * sm_count() - 1) / (bps * sm_count());
+        rpb = std::max<long long>(2 * GK, (rpb + GK - 1) / GK * GK);
+        const unsigned nblk = (unsigned)((rows + rpb - 1) / rpb);
+        UF3B_LAUNCH(k_gram_narrow, nblk, 256, 0, stream, dx, dld, dy, (long long)rows, gm->n_cols, (int)rpb,
+                    gm->g[which], gm->b[which], invalid);
         if (dx != x || dy != y) UF3B_CUDA(stream_sync(stream));
         return UF3B_OK;
     }
