@@ -376,11 +376,11 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # many ranks x pipeline threads on one host: sleeping waits instead of spinning ones — for the
-    # host-buffer arms only; the resident arm and the MD loop have one driving thread per rank, which spins
-    # (a sleeping wait costs its wake-up latency on every list build: measured 0.42 vs 0.25 ms per step at 8 ranks)
-    env_block = os.environ.get("UF3B_BLOCKING_SYNC")
-    blocking_e2e = (world >= 4 and env_block != "0") or env_block == "1"
+    # Host waits spin by default.  Sleeping waits (uf3b_set_blocking_sync, UF3B_BLOCKING_SYNC=1) are for hosts
+    # where ranks x threads outnumber the cores; on the 32-core 8-GPU box they cost their wake-up latency on
+    # every wait: e2e 201 M (sleeping) against 255 M atom-steps/s (spinning), resident arm 0.42 against 0.26 ms
+    # per step (profiles/README.md).
+    blocking_e2e = os.environ.get("UF3B_BLOCKING_SYNC") == "1"
 
     def blocking(enabled):
         _native.check(_native.lib().uf3b_set_blocking_sync(1 if (enabled and blocking_e2e) else 0))
