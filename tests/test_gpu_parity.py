@@ -324,6 +324,78 @@ def test_headline_frame_10k_atoms_manuscript_basis_matches_oracle():
     eng.close()
 
 
+def _alloy(reps, species, a, sigma, seed):
+    """Random alloy on a bcc lattice: positions as bcc_w, species drawn per site."""
+    pos, _, cell, pbc = _bcc_w(reps, a=a, sigma=sigma, seed=seed)
+    rng = np.random.default_rng(seed + 1000)
+    return pos, rng.choice(np.array(species, dtype=np.int32), size=len(pos)), cell, pbc
+
+
+def test_ternary_alloy_mid_size_matches_oracle():
+    """Three species (six pair and eighteen trio interactions, nine of them of symmetry 1, one with its own
+    grid) on a 432-atom random bcc alloy, planes of at most 20 cells: k_rows_multi2 with ne = 3 against the
+    oracle."""
+    from uf3_b200 import bspline, composition
+    chem = composition.ChemicalSystem(["H", "C", "O"], degree=3)
+    trios = chem.interactions_map[3]
+    basis = bspline.BSplineBasis(
+        chem, r_min_map={("H", "H"): 0.3, ("C", "H"): 0.4},
+        r_max_map={**{t: [3.4, 3.4, 6.8] for t in trios}, ("H", "H"): 4.5, ("C", "O"): 5.0, ("C", "H", "O"): [3.0, 3.6, 5.5]},
+        resolution_map={**{t: [3, 3, 5] for t in trios}, ("C", "H", "O"): [3, 4, 5]},
+        leading_trim={2: 1, 3: 0}, trailing_trim={2: 2, 3: 3})
+    assert sorted(set(basis.symmetry.values())) == [1, 2]
+    pos, numbers, cell, pbc = _alloy((6, 6, 6), [1, 6, 8], a=2.9, sigma=0.06, seed=41)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    packed = orc.PackedBasis(basis)
+    eng = Engine(basis)
+    eng.build_neighbors(pos, numbers, images=images)
+    for which in (2, 3):
+        off, idx = eng.neighbor_list(which)
+        want_off, want_idx = orc.neighbor_lists(packed, pos, numbers, images[1], which)
+        assert np.array_equal(off, want_off) and np.array_equal(idx, want_idx)
+    xe, xf = eng.featurize()
+    want_e, want_f = orc.featurize(packed, pos, numbers, images[1])
+    assert gu.rel_err(xe, want_e) <= REL and gu.rel_err(xf, want_f) <= REL
+    assert np.allclose(xf, want_f, rtol=1e-5, atol=1e-8)
+    xe2, xf2 = eng.featurize()
+    assert np.array_equal(xe, xe2) and np.array_equal(xf, xf2)
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1"])
+def test_symmetry1_same_species_trio_mid_size_paths_agree(variant, monkeypatch):
+    """The basis of the deviation fixture (one species, l and m knots differ) on 250 atoms: both forms of the
+    general leg-grouped kernel against the per-triangle scatter path, and the force rows against central
+    differences of the energy row (the oracle follows the reference, which is inconsistent here)."""
+    basis = gu.Case("dev_w16_sym1").basis()
+    pos, numbers, cell, pbc = _bcc_w((5, 5, 5), sigma=0.08, seed=77)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+
+    def rows(p, env):
+        for key in ("UF3B_NO_MULTI", "UF3B_MULTI_V1"):
+            monkeypatch.delenv(key, raising=False)
+        for key in env:
+            monkeypatch.setenv(key, "1")
+        eng = Engine(basis)
+        eng.build_neighbors(p, numbers, images=images)
+        out = eng.featurize()
+        eng.close()
+        return out
+
+    xe, xf = rows(pos, ["UF3B_MULTI_V1"] if variant == "v1" else [])
+    se, sf = rows(pos, ["UF3B_NO_MULTI"])
+    assert gu.rel_err(xe, se) <= 1e-11 and gu.rel_err(xf, sf) <= 1e-11
+    n, delta = len(pos), 1e-5
+    for atom, axis in ((3, 0), (101, 2)):
+        moved = pos.copy()
+        moved[atom, axis] += delta
+        plus = rows(moved, [])[0]
+        moved[atom, axis] -= 2 * delta
+        minus = rows(moved, [])[0]
+        fd = -(plus - minus) / (2 * delta)
+        assert np.abs(xf[axis * n + atom] - fd).max() <= 1e-6 * np.abs(fd).max()
+
+
 def test_binary_fec_10k_atoms_matches_oracle():
     """The reference's Fe-C test basis (tests/test_representation.py:605-648: six trios, two of symmetry 1,
     609 columns) on a 10 000-atom B2 lattice, 55 neighbours inside the three-body cutoff: k_rows_multi at

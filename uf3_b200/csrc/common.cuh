@@ -188,6 +188,7 @@ struct uf3b_basis {
     uf3b::DevBuf<unsigned char> leg_cache;   // k_leg_cache records of the current frame
     uf3b::DevBuf<double> legv, legd, epos;   // k_centre_legs tables of the current frame (tiled path)
     uf3b::DevBuf<double> planes;             // plane table of the current frame (tiled path)
+    uf3b::DevBuf<double> tile3;              // neighbour-role force tiles handed from k_rows_nbr to k_rows_ctr
 };
 
 struct uf3b_nlist {

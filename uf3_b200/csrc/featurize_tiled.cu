@@ -50,6 +50,7 @@ struct TiledGeom {
     int all_orphans;                // test hook: k_rows_ctr recomputes every plane itself
     const double *legv, *legd, *epos;   // k_centre_legs tables
     double *planes;                 // [entry][LM][NA] plane table
+    double *tile3;                  // [atom][n][c][{l, m}]: neighbour-role force tiles, k_rows_nbr -> k_rows_ctr
 };
 
 template <int LM, int NA>
@@ -431,30 +432,22 @@ k_rows_nbr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
             __syncwarp();
         }
 
-        // ---- 3-body columns of rows fx_a, fy_a, fz_a (k_rows_ctr adds the centre role): lanes of
-        // different g are summed, lane n < na then owns every bin of its n — (l, m, n) and (m, l, n)
-        // share a column — and stores it straight into the rows
+        // ---- the neighbour-role force tile of the atom: lanes of different g are summed, lane n < na then
+        // holds every {l, m} of its n and leaves them, 3 NS doubles in a row, in the tile buffer; k_rows_ctr
+        // starts its own tile from these values and writes the rows ONCE (storing them into the rows here
+        // and adding the centre role there cost k_rows_ctr a read of every 3-body column: 16 % of its stall
+        // samples and 26 MB of DRAM traffic per frame)
         if (want_f) {
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int s = 0; s < NS; ++s) fr[c][s] = fold_groups<S::G, NA>(fr[c][s]);
             if (lane < tg.na) {
+                double *dst = tg.tile3 + ((size_t)a * NA + lane) * (3 * NS);
 #pragma unroll
-                for (int l = 0; l < LM; ++l)
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int m = l; m < LM; ++m) {
-                        if (m < tg.la) {
-                            const int col = cell_col(B, tg, l, m, lane);
-                            if (col >= 0) {
-                                double *dst = xf + (long long)a * ld + tg.col0 + col;
-                                const int s = sym_idx(l, m, LM);
-                                dst[0] = fr[0][s];
-                                dst[(long long)f.n * ld] = fr[1][s];
-                                dst[2 * (long long)f.n * ld] = fr[2][s];
-                            }
-                        }
-                    }
+                    for (int s = 0; s < NS; ++s) dst[c * NS + s] = fr[c][s];
             }
         }
         __syncwarp();
@@ -632,22 +625,19 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
         const int r0 = __ldg(f.off2 + a), r1 = r0 + __ldg(f.cnt2 + a);
         const int sa = __ldg(f.spec + a);
         const Vec3 pa = real_position(f, a);
-        if (want_f && lane < tg.na) {       // the 3-body columns k_rows_nbr stored are updated at the end: touch them
-#pragma unroll                              // now (loads to nowhere), so that the update finds them in L1
-            for (int l = 0; l < LM; ++l)
+        // the neighbour-role tile k_rows_nbr left for this atom: the lane's 3 NS values start the lane's own
+        // tile (lanes of g = 0 only: fold_groups sums over g at the end)
+        double fr[3][NS];
 #pragma unroll
-                for (int m = l; m < LM; ++m)
-                    if (m < tg.la) {
-                        const int col = cell_col(B, tg, l, m, lane);
-                        if (col >= 0) {
-                            const double *src = xf + (long long)a * ld + tg.col0 + col;
-                            const long long cs = (long long)f.n * ld;
-                            double sink;
-                            asm volatile("ld.global.f64 %0, [%1];" : "=d"(sink) : "l"(src));
-                            asm volatile("ld.global.f64 %0, [%1];" : "=d"(sink) : "l"(src + cs));
-                            asm volatile("ld.global.f64 %0, [%1];" : "=d"(sink) : "l"(src + 2 * cs));
-                        }
-                    }
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) fr[c][s] = 0.0;
+        if (want_f && lane < tg.na) {
+            const double *src = tg.tile3 + ((size_t)a * NA + lane) * (3 * NS);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int s = 0; s < NS; ++s) fr[c][s] = __ldcs(src + c * NS + s);
         }
         const bool pv0 = r0 + lane < r1, pv1 = r0 + 32 + lane < r1;
         const int m0 = pv0 ? __ldg(f.idx2 + r0 + lane) : 0, m1 = pv1 ? __ldg(f.idx2 + r0 + 32 + lane) : 0;
@@ -702,11 +692,6 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
 
         // ------------------------------------------------ 3-body, centre role: x_a += u_aj dB_l (x) P_j,
         // e += 1/2 B_l (x) P_j with the planes k_rows_nbr left in the table
-        double fr[3][NS];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int s = 0; s < NS; ++s) fr[c][s] = 0.0;
         if (c_on && n3a > 1) {
             for (int j = c_g; j < n3a; j += S::G) {
                 const unsigned oj = own_s + OWN_REC * (unsigned)j;
@@ -763,7 +748,7 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int s = 0; s < NS; ++s) fr[c][s] = fold_groups<S::G, NA>(fr[c][s]);
-            if (lane < tg.na) {         // 3-body columns: add the centre role to what k_rows_nbr stored
+            if (lane < tg.na) {         // 3-body columns: neighbour role (loaded above) + centre role, written once
 #pragma unroll
                 for (int l = 0; l < LM; ++l)
 #pragma unroll
@@ -774,10 +759,9 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
                                 double *dst = xf + (long long)a * ld + tg.col0 + col;
                                 const long long cs = (long long)f.n * ld;
                                 const int s = sym_idx(l, m, LM);
-                                const double x0 = dst[0], x1 = dst[cs], x2 = dst[2 * cs];
-                                __stcs(dst, x0 + fr[0][s]);
-                                __stcs(dst + cs, x1 + fr[1][s]);
-                                __stcs(dst + 2 * cs, x2 + fr[2][s]);
+                                __stcs(dst, fr[0][s]);
+                                __stcs(dst + cs, fr[1][s]);
+                                __stcs(dst + 2 * cs, fr[2][s]);
                             }
                         }
                     }
@@ -914,10 +898,12 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     UF3B_CUDA(basis->legd.reserve(8 * entries));
     UF3B_CUDA(basis->epos.reserve(4 * entries));
     UF3B_CUDA(basis->planes.reserve((size_t)S::PL * entries));
+    if (x_forces) UF3B_CUDA(basis->tile3.reserve((size_t)n * NA * 3 * S::NS));
     tg.legv = basis->legv.p;
     tg.legd = basis->legd.p;
     tg.epos = basis->epos.p;
     tg.planes = basis->planes.p;
+    tg.tile3 = basis->tile3.p;
 
     double *d_xf = x_forces;
     long long d_ld = ld;
@@ -946,7 +932,7 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     UF3B_LAUNCH(k_centre_legs, (unsigned)((threads + 255) / 256), 256, 0, stream, basis->tab, view, tg, sub_shift,
                 basis->legv.p, basis->legd.p, basis->epos.p);
     UF3B_LAUNCH(k_nbr, grid_n, warps * 32, smem_n, stream, basis->tab, view, tg, d_xf, d_ld, x_forces ? 1 : 0);
-    tgc.legv = tg.legv; tgc.legd = tg.legd; tgc.epos = tg.epos; tgc.planes = tg.planes;
+    tgc.legv = tg.legv; tgc.legd = tg.legd; tgc.epos = tg.epos; tgc.planes = tg.planes; tgc.tile3 = tg.tile3;
     UF3B_LAUNCH(k_ctr, grid_c, warps_c * 32, smem_c, stream, basis->tab, view, tgc, d_xf, d_ld, basis->partials.p,
                 x_energy ? 1 : 0, x_forces ? 1 : 0);
     if (g_timing) UF3B_CUDA(cudaEventRecord(ev1, stream));
