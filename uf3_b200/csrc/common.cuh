@@ -223,6 +223,9 @@ struct uf3b_nlist {
     double grid_rsearch = 0.0;
     int grid_cfirst = 0, grid_ccount = 0;
     std::vector<double> grid_imgoff;
+    std::vector<double> img_host;                  // image table that is on the device (img_off / img_inv) ...
+    std::vector<int32_t> abc_host;
+    int img_uploaded = 0;                          // ... and its length, 0 = none
     uf3b::DevBuf<double> pos, img_off;
     uf3b::DevBuf<int> z, spec, img_inv;
     uf3b::DevBuf<int> off2, off3, cnt2, cnt3, idx2, idx3, scratch2, scratch3;

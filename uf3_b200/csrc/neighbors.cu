@@ -111,15 +111,21 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(int n, int c_first, in
     __syncthreads();
     if (!last || warp != 0) return;
     __threadfence();
+    // all twelve bounds of a block's partial row are loaded together (one bound at a time the loop was a
+    // chain of twelve dependent L2 round trips: 10 of the kernel's 15 us)
+    double t[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) t[c] = (c % 6) < 3 ? INFINITY : -INFINITY;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+        double o[12];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) o[c] = __ldcg(partial + 12 * b + c);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) t[c] = (c % 6) < 3 ? fmin(t[c], o[c]) : fmax(t[c], o[c]);
+    }
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
-        const bool is_min = (c % 6) < 3;
-        double x = is_min ? INFINITY : -INFINITY;
-        for (int b = lane; b < (int)gridDim.x; b += 32) {
-            const double o = __ldcg(partial + 12 * b + c);
-            x = is_min ? fmin(x, o) : fmax(x, o);
-        }
-        x = fold(c, x);
+        const double x = fold(c, t[c]);
         if (lane == 0) bbox[c < 6 ? c : c + 2] = x;         // centres at [0..5], all atoms at [8..13]
     }
     if (lane == 0) *ticket = 0;
@@ -693,9 +699,15 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     nl->c_first = (int)first_centre;
     nl->c_count = (int)n_centres;
 
-    // periodic image table: pair every image with the one of negated coordinates
-    std::vector<int> inv(n_images, 0);
-    {
+    // periodic image table: pair every image with the one of negated coordinates.  An unchanged table (MD
+    // loops, streams of frames of one cell) is already on the device: no inversion map, no two copies
+    const bool same_images = nl->img_uploaded == n_images && !is_device_pointer(image_offsets)
+                             && nl->img_host.size() == 3 * (size_t)n_images
+                             && memcmp(nl->img_host.data(), image_offsets, sizeof(double) * 3 * n_images) == 0
+                             && nl->abc_host.size() == 3 * (size_t)n_images
+                             && memcmp(nl->abc_host.data(), image_abc, sizeof(int32_t) * 3 * n_images) == 0;
+    std::vector<int> inv(same_images ? 0 : n_images, 0);
+    if (!same_images) {
         std::map<std::tuple<int, int, int>, int> rank;
         for (int g = 0; g < n_images; ++g)
             rank[std::make_tuple(image_abc[3 * g], image_abc[3 * g + 1], image_abc[3 * g + 2])] = g;
@@ -712,8 +724,17 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     UF3B_CUDA(nl->off2.reserve((size_t)n + 1));
     UF3B_CUDA(nl->off3.reserve((size_t)n + 1));
     UF3B_CUDA(nl->totals.reserve(8 + NL_REGIONS));      // [0] scan total, [1..4] status (8 ints), [8..] claims
-    UF3B_CUDA(cudaMemcpyAsync(nl->img_off.p, image_offsets, sizeof(double) * 3 * n_images, cudaMemcpyDefault, stream));
-    UF3B_CUDA(cudaMemcpyAsync(nl->img_inv.p, inv.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, stream));
+    if (!same_images) {
+        UF3B_CUDA(cudaMemcpyAsync(nl->img_off.p, image_offsets, sizeof(double) * 3 * n_images, cudaMemcpyDefault, stream));
+        UF3B_CUDA(cudaMemcpyAsync(nl->img_inv.p, inv.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, stream));
+        nl->img_uploaded = 0;
+        if (!is_device_pointer(image_offsets)) {
+            // pageable sources are staged by the runtime before the call returns: `inv` may go out of scope
+            nl->img_host.assign(image_offsets, image_offsets + 3 * (size_t)n_images);
+            nl->abc_host.assign(image_abc, image_abc + 3 * (size_t)n_images);
+            nl->img_uploaded = n_images;
+        }
+    }
     if (n == 0) {
         UF3B_CUDA(stream_sync(stream));
         guard.armed = false;
@@ -728,9 +749,8 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
     UF3B_CUDA(cudaMemcpyAsync(nl->pos.p, positions, sizeof(double) * 3 * n, cudaMemcpyDefault, stream));
     UF3B_CUDA(cudaMemcpyAsync(nl->z.p, atomic_numbers, sizeof(int) * n, cudaMemcpyDefault, stream));
     int *d_err = (int *)(nl->misc.p + 6);
-    static const double bbox_init[14] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0, 0.0,
-                                         INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    UF3B_CUDA(cudaMemcpyAsync(nl->misc.p, bbox_init, sizeof bbox_init, cudaMemcpyHostToDevice, stream));
+    // k_prepare's last block writes all twelve bounds; only the error words have to be cleared
+    UF3B_CUDA(cudaMemsetAsync(nl->misc.p + 6, 0, 2 * sizeof(double), stream));
     const int prep_blocks = std::min((n + PREP_THREADS - 1) / PREP_THREADS, PREP_BLOCKS_MAX);
     if (!nl->ticket_zeroed) {       // the kernel leaves the counter at zero for the next launch
         UF3B_CUDA(cudaMemsetAsync(nl->misc.p + 16 + 12 * PREP_BLOCKS_MAX, 0, 2 * sizeof(double), stream));
