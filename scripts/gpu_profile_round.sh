@@ -1,6 +1,6 @@
 #!/bin/bash
 # Usage (via gpurun): scripts/gpu_profile_round.sh <tag>  — one `ncu --set full` capture per kernel of
-# the round (caches NOT flushed between kernels: the three row kernels feed each other through L2).
+# the round (caches NOT flushed between kernels: the row kernels feed each other through L2).
 tag=$1
 mkdir -p gpurun_out
 cap() {  # name regex skip args...
@@ -15,6 +15,8 @@ cap centre_legs k_centre_legs 3 $B
 cap rows_nbr k_rows_nbr 3 $B
 cap rows_ctr k_rows_ctr 3 $B
 cap neighbors k_neighbors 3 $B
+cap gram_narrow k_gram_narrow 3 $B
 cap coop k_featurize_coop 3 $B --basis manuscript
-cap gram k_gram 3 python bench.py --workload fit --basis manuscript --steps 3 --warmup 2
+cap gram k_gram\$ 3 python bench.py --workload fit --basis manuscript --steps 3 --warmup 2
+cap multi2 k_rows_multi2 1 python scripts/binary_step.py --steps 1
 cap energy_forces k_energy_forces 8 python scripts/md_step.py

@@ -21,7 +21,7 @@ def num(m, key):
     v, u = m[key]
     x = float(v.replace(",", ""))
     scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3,
-             "nsecond": 1e-9, "second": 1.0}.get(u, 1.0)
+             "nsecond": 1e-9, "second": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(u, 1.0)
     return x * scale
 
 

@@ -48,6 +48,7 @@ struct TiledGeom {
     int off_zero, off_aw, off_vn;   // inside a warp's region: [legs centre(e) -> a'] zero word, (A, w) records,
                                     // n-leg records
     int all_orphans;                // test hook: k_rows_ctr recomputes every plane itself
+    int discard;                    // k_rows_ctr drops consumed scratch lines from the L2 (UF3B_NO_DISCARD: off)
     const double *legv, *legd, *epos;   // k_centre_legs tables
     double *planes;                 // [entry][LM][NA] plane table
     double *tile3;                  // [atom][n][c][{l, m}]: neighbour-role force tiles, k_rows_nbr -> k_rows_ctr
@@ -63,7 +64,16 @@ struct TiledShape {
                                                       // then {first basis index - n0, pad}
     static constexpr int NS = LM * (LM + 1) / 2;      // unordered pairs {l, m}
     static constexpr int PL = LM * NA;                // doubles per plane
+    // doubles per atom of the tile buffer (3 NS per lane n), rounded up to whole 128-byte lines so that the
+    // consumer can drop an atom's lines from the L2 once it has read them
+    static constexpr int TS = (NA * 3 * NS + 15) / 16 * 16;
 };
+
+// Drops a 128-byte line from the L2 WITHOUT writing it back (the data becomes undefined): for scratch that
+// the producer rewrites before anybody reads it again.  `p` must be 128-byte aligned.
+__device__ __forceinline__ void discard_line(const void *p) {
+    asm volatile("discard.global.L2 [%0], 128;" :: "l"(p) : "memory");
+}
 constexpr unsigned OWN_REC = 96;                      // v[4] dv[4] u[3] pad
 constexpr int TL_MAX_ROW = 32;                        // longest 3-body row the kernels take
 constexpr int TL_DEAD = -(1 << 20);                   // first basis index of a leg that contributes nothing
@@ -443,7 +453,7 @@ k_rows_nbr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
 #pragma unroll
                 for (int s = 0; s < NS; ++s) fr[c][s] = fold_groups<S::G, NA>(fr[c][s]);
             if (lane < tg.na) {
-                double *dst = tg.tile3 + ((size_t)a * NA + lane) * (3 * NS);
+                double *dst = tg.tile3 + (size_t)a * S::TS + lane * (3 * NS);
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -633,7 +643,7 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
 #pragma unroll
             for (int s = 0; s < NS; ++s) fr[c][s] = 0.0;
         if (want_f && lane < tg.na) {
-            const double *src = tg.tile3 + ((size_t)a * NA + lane) * (3 * NS);
+            const double *src = tg.tile3 + (size_t)a * S::TS + lane * (3 * NS);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -779,6 +789,19 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
                 __stcs(xf + ((long long)c * f.n + a) * ld + col, t);     // written once: streaming
             }
         }
+        // the atom's tile and planes have been consumed and are rewritten before they are read again (next
+        // frame): their whole lines are dropped from the L2 instead of being written back to HBM
+        if (tg.discard) {
+            __syncwarp();
+            if (want_f) {
+                const char *t0 = reinterpret_cast<const char *>(tg.tile3 + (size_t)a * S::TS);
+                for (int k = lane; k < S::TS / 16; k += 32) discard_line(t0 + 128 * k);
+            }
+            const size_t b0 = ((size_t)row0 * S::PL * 8 + 127) & ~size_t(127);
+            const size_t b1 = ((size_t)(row0 + n3a) * S::PL * 8) & ~size_t(127);
+            const char *p0 = reinterpret_cast<const char *>(tg.planes);
+            for (size_t b = b0 + 128 * (size_t)lane; b < b1; b += 128 * 32) discard_line(p0 + b);
+        }
         __syncwarp();
     }
     if (want_e) {
@@ -820,6 +843,7 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     tg.ps = max3;                   // one slot per position of the longest row
     tg.sl_shift = tg.ps <= 16 ? 4 : 5;
     tg.all_orphans = getenv("UF3B_TILED_ORPHANS") ? 1 : 0;
+    tg.discard = getenv("UF3B_NO_DISCARD") ? 0 : 1;
     // a chunk of cg groups holds whole contraction rounds (G groups); the larger candidate also holds
     // whole evaluation passes (32 >> sl_shift groups) and is taken when it does not cost resident warps
     const int cg_env = getenv("UF3B_TILED_CG") ? atoi(getenv("UF3B_TILED_CG")) : 0;
@@ -898,7 +922,7 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     UF3B_CUDA(basis->legd.reserve(8 * entries));
     UF3B_CUDA(basis->epos.reserve(4 * entries));
     UF3B_CUDA(basis->planes.reserve((size_t)S::PL * entries));
-    if (x_forces) UF3B_CUDA(basis->tile3.reserve((size_t)n * NA * 3 * S::NS));
+    if (x_forces) UF3B_CUDA(basis->tile3.reserve((size_t)n * S::TS + 16));
     tg.legv = basis->legv.p;
     tg.legd = basis->legd.p;
     tg.epos = basis->epos.p;
