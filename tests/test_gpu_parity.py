@@ -210,8 +210,9 @@ def test_general_leg_grouped_kernel_and_scatter_path_agree(name, monkeypatch):
     share no 3-body code beyond the leg evaluation."""
     case = gu.Case(name)
     outs = []
-    for env in ({}, {"UF3B_NO_MULTI": "1"}):
+    for env in ({}, {"UF3B_NO_MULTI": "1"}, {"UF3B_MULTI_V1": "1"}):
         monkeypatch.delenv("UF3B_NO_MULTI", raising=False)
+        monkeypatch.delenv("UF3B_MULTI_V1", raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
         _, eng, _ = _engine_for(case)
@@ -219,7 +220,8 @@ def test_general_leg_grouped_kernel_and_scatter_path_agree(name, monkeypatch):
         xe_only, _ = eng.featurize(energy=True, forces=False)
         assert gu.rel_err(xe_only, outs[-1][0]) <= 1e-13
         eng.close()
-    assert gu.rel_err(outs[0][0], outs[1][0]) <= 1e-11 and gu.rel_err(outs[0][1], outs[1][1]) <= 1e-11
+    for other in (1, 2):        # kind-outer form (default) against the scatter path and the group-outer form
+        assert gu.rel_err(outs[0][0], outs[other][0]) <= 1e-11 and gu.rel_err(outs[0][1], outs[other][1]) <= 1e-11
     assert gu.rel_err(outs[0][0], case["x_energy"]) <= REL
     if not name.startswith("dev_"):         # the documented deviation: tests/test_deviation_fixture.py
         assert gu.rel_err(outs[0][1], case["x_forces"]) <= REL
@@ -426,7 +428,8 @@ def test_binary_fec_10k_atoms_matches_oracle():
 @pytest.mark.parametrize("kind,a,sigma,expect", [
     ("demo", 2.45, 0.04, "rows of ~26 entries: leg cache with long rows"),
     ("manuscript", 2.95, 0.05, "rows of ~26 entries: cooperative kernel with 28-32 record slots"),
-    ("demo", 2.10, 0.03, "rows above 32 entries: the general leg-grouped kernel (k_rows_multi)"),
+    ("demo", 2.10, 0.03, "rows above 32 entries: the general leg-grouped kernel, kind-outer form (k_rows_multi2)"),
+    ("demo", 1.60, 0.02, "rows above 32 entries, and above the 64 of its row table: group-outer form (k_rows_multi)"),
     ("manuscript", 3.165, 0.30, "strongly rattled: ragged rows, legs outside the knot range"),
 ])
 def test_dense_and_ragged_lattices_match_oracle(kind, a, sigma, expect):
@@ -442,6 +445,7 @@ def test_dense_and_ragged_lattices_match_oracle(kind, a, sigma, expect):
     off3, _ = eng.neighbor_list(3)
     longest = int(np.diff(off3).max())
     assert (longest > 32) == ("above 32" in expect), (longest, expect)
+    assert (longest > 64) == ("above the 64" in expect), (longest, expect)
     xe, xf = eng.featurize()
     want_e, want_f = orc.featurize(packed, pos, numbers, images[1])
     assert gu.rel_err(xe, want_e) <= REL and gu.rel_err(xf, want_f) <= REL

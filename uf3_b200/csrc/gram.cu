@@ -28,7 +28,10 @@ struct uf3b_gram {
 namespace uf3b {
 
 constexpr int GT = 64;        // output tile edge
-constexpr int GK = 16;        // rows per shared-memory stage
+#ifndef UF3B_GK
+#define UF3B_GK 32
+#endif
+constexpr int GK = UF3B_GK;   // rows per shared-memory stage (32: two barriers per 64 DMMA of a warp; 16 measured 5 % slower at 456 columns)
 
 // Tile (bi <= bj) of X^T X over rows [z*rows_per_block, (z+1)*rows_per_block), on the FP64
 // tensor cores: mma.sync m8n8k4 (DMMA).  This IS a dense contraction, unlike the rest of the
@@ -63,10 +66,11 @@ k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols, i
     const int l_row = threadIdx.x >> 6, l_col = threadIdx.x & 63;
     const int ca = bi * GT + l_col, cb = bj * GT + l_col;
     const bool a_ok = ca < n_cols, b_ok = cb < n_cols;
-    double ra[4], rb[4];
+    constexpr int NR = GK / 4;              // rows of a stage per thread and panel
+    double ra[NR], rb[NR];
     auto fetch = [&](long long r0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NR; ++i) {
             const long long r = r0 + l_row + 4 * i;
             ra[i] = (r < r_end && a_ok) ? __ldg(x + r * ld + ca) : 0.0;
             rb[i] = (r < r_end && b_ok) ? __ldg(x + r * ld + cb) : 0.0;
@@ -76,7 +80,7 @@ k_gram(const double *__restrict__ x, long long ld, long long rows, int n_cols, i
     fetch(r_begin);
     for (long long r0 = r_begin; r0 < r_end; r0 += GK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { sa[l_row + 4 * i][l_col] = ra[i]; sb[l_row + 4 * i][l_col] = rb[i]; }
+        for (int i = 0; i < NR; ++i) { sa[l_row + 4 * i][l_col] = ra[i]; sb[l_row + 4 * i][l_col] = rb[i]; }
         __syncthreads();
         if (r0 + GK < r_end) fetch(r0 + GK);
 #pragma unroll
@@ -136,10 +140,12 @@ k_gram_narrow(const double *__restrict__ x, long long ld, const double *__restri
     }
     const bool second = warp + 8 <= 14;
     // element e = threadIdx.x + 256 i of a stage (GK x GN): row e / GN, column e % GN
-    double reg[5];
+    constexpr int NE = GK * GN / 256;       // elements of a stage per thread
+    static_assert(GK * GN % 256 == 0, "a stage must divide over the block");
+    double reg[NE];
     auto fetch = [&](long long r0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < NE; ++i) {
             const int e = threadIdx.x + 256 * i, row = e / GN, col = e - row * GN;
             const long long r = r0 + row;
             double v = 0.0;
@@ -154,7 +160,7 @@ k_gram_narrow(const double *__restrict__ x, long long ld, const double *__restri
     fetch(r_begin);
     for (long long r0 = r_begin; r0 < r_end; r0 += GK) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < NE; ++i) {
             const int e = threadIdx.x + 256 * i, row = e / GN, col = e - row * GN;
             sx[row][col] = reg[i];
         }
