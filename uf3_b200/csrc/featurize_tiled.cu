@@ -64,6 +64,7 @@ struct TiledShape {
                                                       // then {first basis index - n0, pad}
     static constexpr int NS = LM * (LM + 1) / 2;      // unordered pairs {l, m}
     static constexpr int PL = LM * NA;                // doubles per plane
+    static constexpr int PLS = (PL + 1) & ~1;         // ... per plane of the table: whole 16-byte words (bulk copies)
     // doubles per atom of the tile buffer (3 NS per lane n), rounded up to whole 128-byte lines so that the
     // consumer can drop an atom's lines from the L2 once it has read them
     static constexpr int TS = (NA * 3 * NS + 15) / 16 * 16;
@@ -414,7 +415,7 @@ k_rows_nbr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
                                                   on ? ni : 0, c_pick, zero_s, P, Q);
                 if (on) {
                     // the plane of (centre i, neighbour a') for the centre role of atom i
-                    double *pl = tg.planes + (size_t)(rowi + qa) * S::PL + c_n;
+                    double *pl = tg.planes + (size_t)(rowi + qa) * S::PLS + c_n;
 #pragma unroll
                     for (int m = 0; m < LM; ++m) pl[m * NA] = P[m];
                 }
@@ -613,7 +614,12 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
     const unsigned slot_stride = 32u * (unsigned)tg.col0;
     const unsigned slot_s = smem_s + (unsigned)tg.off_warps + (unsigned)warp * (unsigned)tg.warp_bytes;
     const unsigned rec_s = slot_s + PR_SLOTS * slot_stride;       // pair records of a pass, or (before them) the row tables:
-    const unsigned own_s = rec_s, pl_s = rec_s + OWN_REC * (unsigned)tg.ps;     // legs a -> e, planes of the row
+    // row tables of the atom, staged by three TMA bulk copies (contiguous blocks of the global tables):
+    // legs a -> e as values (32 B per entry) and derivatives + unit vector + tag (64 B), then the planes
+    const unsigned ov_s = rec_s, od_s = rec_s + 32u * (unsigned)tg.ps, pl_s = rec_s + OWN_REC * (unsigned)tg.ps;
+    const unsigned bar_s = pl_s + 8u * (unsigned)(S::PLS * tg.ps);
+    unsigned parity = 0;
+    if (lane == 0) mbar_init(bar_s, 1);
     const int c_g = lane / NA, c_n = lane - c_g * NA;
     const bool c_on = c_g < S::G && c_n < tg.na;
     const double half_e = want_e ? 0.5 : 0.0;
@@ -651,52 +657,23 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
         }
         const bool pv0 = r0 + lane < r1, pv1 = r0 + 32 + lane < r1;
         const int m0 = pv0 ? __ldg(f.idx2 + r0 + lane) : 0, m1 = pv1 ? __ldg(f.idx2 + r0 + 32 + lane) : 0;
-        // own entry (leg a -> e and the validity of its plane) and the planes of the row — n3a x PL
-        // doubles, contiguous in the table; loads first, stores behind the position gathers
-        double2 ow[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ow[i] = make_double2(0.0, 0.0);
-        if (lane < n3a) {
-            const size_t p = (size_t)(row0 + lane);
-            const double2 *gv = reinterpret_cast<const double2 *>(tg.legv + 4 * p);
-            const double2 *gd = reinterpret_cast<const double2 *>(tg.legd + 8 * p);
-            ow[0] = __ldg(gv); ow[1] = __ldg(gv + 1); ow[2] = __ldg(gd); ow[3] = __ldg(gd + 1);
-            ow[4] = __ldg(gd + 2); ow[5] = __ldg(gd + 3);
-        }
-        constexpr int PB = 12;              // plane doubles per lane and batch (14 x 27 = 378 <= 384)
-        const double *pl = tg.planes + (size_t)row0 * S::PL;
-        const int n_pl = n3a * S::PL;
-        double pb[PB];
-#pragma unroll
-        for (int k = 0; k < PB; ++k) {
-            const int i = 32 * k + lane;
-            pb[k] = i < n_pl ? __ldg(pl + i) : 0.0;
+        // the row tables of the atom: bulk copies issued by lane 0 (cp.async.bulk, completion counted on the
+        // warp's mbarrier), waited for behind the pair-list gathers
+        if (n3a > 0 && lane == 0) {
+            fence_proxy_async();        // the pair records of the previous atom lived in the same memory
+            const unsigned n = (unsigned)n3a;
+            mbar_expect_tx(bar_s, n * (OWN_REC + 8u * (unsigned)S::PLS));
+            bulk_copy_g2s(ov_s, tg.legv + 4 * (size_t)row0, 32u * n, bar_s);
+            bulk_copy_g2s(od_s, tg.legd + 8 * (size_t)row0, 64u * n, bar_s);
+            bulk_copy_g2s(pl_s, tg.planes + (size_t)row0 * S::PLS, 8u * (unsigned)S::PLS * n, bar_s);
         }
         int dummy;
         Vec3 pj0 = pa, pj1 = pa;
         if (pv0) pj0 = super_position(f, m0, dummy);
         if (pv1) pj1 = super_position(f, m1, dummy);
-        if (lane < n3a) {
-            const unsigned o = own_s + OWN_REC * (unsigned)lane;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) sts128(o + 16u * i, ow[i]);
-        }
-#pragma unroll
-        for (int k = 0; k < PB; ++k) {
-            const int i = 32 * k + lane;
-            if (i < n_pl) sts64(pl_s + 8u * (unsigned)i, pb[k]);
-        }
-        for (int i0 = 32 * PB; i0 < n_pl; i0 += 32 * PB) {      // long rows
-#pragma unroll
-            for (int k = 0; k < PB; ++k) {
-                const int i = i0 + 32 * k + lane;
-                pb[k] = i < n_pl ? __ldg(pl + i) : 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < PB; ++k) {
-                const int i = i0 + 32 * k + lane;
-                if (i < n_pl) sts64(pl_s + 8u * (unsigned)i, pb[k]);
-            }
+        if (n3a > 0) {
+            mbar_wait(bar_s, parity);
+            parity ^= 1u;
         }
         __syncwarp();
 
@@ -704,14 +681,15 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
         // e += 1/2 B_l (x) P_j with the planes k_rows_nbr left in the table
         if (c_on && n3a > 1) {
             for (int j = c_g; j < n3a; j += S::G) {
-                const unsigned oj = own_s + OWN_REC * (unsigned)j;
                 double2 q[6];
+                q[0] = lds128(ov_s + 32u * (unsigned)j);
+                q[1] = lds128(ov_s + 32u * (unsigned)j + 16u);
 #pragma unroll
-                for (int i = 0; i < 6; ++i) q[i] = lds128(oj + 16u * i);
+                for (int i = 0; i < 4; ++i) q[2 + i] = lds128(od_s + 64u * (unsigned)j + 16u * i);
                 const int qa = (int)(__double_as_longlong(q[5].y) >> 32);
                 double P[LM];
                 if (qa >= 0 && !tg.all_orphans) {
-                    const unsigned pj_ = pl_s + 8u * (unsigned)(j * S::PL + c_n);
+                    const unsigned pj_ = pl_s + 8u * (unsigned)(j * S::PLS + c_n);
 #pragma unroll
                     for (int m = 0; m < LM; ++m) P[m] = lds64(pj_ + 8u * (unsigned)(m * NA));
                 } else {
@@ -797,8 +775,8 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
                 const char *t0 = reinterpret_cast<const char *>(tg.tile3 + (size_t)a * S::TS);
                 for (int k = lane; k < S::TS / 16; k += 32) discard_line(t0 + 128 * k);
             }
-            const size_t b0 = ((size_t)row0 * S::PL * 8 + 127) & ~size_t(127);
-            const size_t b1 = ((size_t)(row0 + n3a) * S::PL * 8) & ~size_t(127);
+            const size_t b0 = ((size_t)row0 * S::PLS * 8 + 127) & ~size_t(127);
+            const size_t b1 = ((size_t)(row0 + n3a) * S::PLS * 8) & ~size_t(127);
             const char *p0 = reinterpret_cast<const char *>(tg.planes);
             for (size_t b = b0 + 128 * (size_t)lane; b < b1; b += 128 * 32) discard_line(p0 + b);
         }
@@ -897,7 +875,7 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     const int warps_c = 4;
     const int nk2 = basis->h_pair_nk0;
     const size_t tab_c = ((8 * (size_t)((nk2 + 1) & ~1) + (size_t)PIECE_B * (nk2 - 7)) + 15) & ~size_t(15);
-    const size_t rows_c = (size_t)OWN_REC * tg.ps + 8 * (size_t)S::PL * tg.ps;
+    const size_t rows_c = (size_t)OWN_REC * tg.ps + 8 * (size_t)S::PLS * tg.ps + 16;     // + the warp's mbarrier
     const size_t warp_c = ((size_t)PR_SLOTS * 32 * tg.col0 + std::max<size_t>(32 * PR_REC, rows_c) + 15) & ~size_t(15);
     const size_t smem_c = tab_c + (size_t)warps_c * warp_c;
     if (smem_c > (size_t)smem_max) return 1;
@@ -921,7 +899,7 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     UF3B_CUDA(basis->legv.reserve(4 * entries));
     UF3B_CUDA(basis->legd.reserve(8 * entries));
     UF3B_CUDA(basis->epos.reserve(4 * entries));
-    UF3B_CUDA(basis->planes.reserve((size_t)S::PL * entries));
+    UF3B_CUDA(basis->planes.reserve((size_t)S::PLS * entries));
     if (x_forces) UF3B_CUDA(basis->tile3.reserve((size_t)n * S::TS + 16));
     tg.legv = basis->legv.p;
     tg.legd = basis->legd.p;

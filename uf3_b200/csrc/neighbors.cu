@@ -345,28 +345,6 @@ __device__ __forceinline__ void warp_rank_sort(const int *src, int *dst, int n, 
 constexpr int NL_WARPS = 4;
 constexpr int NL_TILE = 1024;     // slots staged per block (32 KB); larger tiles fall back to global reads
 
-// ---- TMA bulk copy (cp.async.bulk, completion counted on an mbarrier)
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-
 constexpr int NL_BUF2 = 160, NL_BUF3 = 96;     // hits buffered per centre before the row is placed
 constexpr int NL_REGIONS = 128;                // independent claim regions per list
 constexpr int NL_PAIRS = 36;                   // pair bounds staged in shared memory (up to 8 elements)
