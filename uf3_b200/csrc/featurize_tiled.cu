@@ -617,7 +617,7 @@ k_rows_ctr(const BasisTab B, const FrameView f, const TiledGeom tg, double *__re
     // row tables of the atom, staged by three TMA bulk copies (contiguous blocks of the global tables):
     // legs a -> e as values (32 B per entry) and derivatives + unit vector + tag (64 B), then the planes
     const unsigned ov_s = rec_s, od_s = rec_s + 32u * (unsigned)tg.ps, pl_s = rec_s + OWN_REC * (unsigned)tg.ps;
-    const unsigned bar_s = pl_s + 8u * (unsigned)(S::PLS * tg.ps);
+    const unsigned bar_s = slot_s + (unsigned)tg.warp_bytes - 16u;      // the warp's mbarrier: behind everything that is reused
     unsigned parity = 0;
     if (lane == 0) mbar_init(bar_s, 1);
     const int c_g = lane / NA, c_n = lane - c_g * NA;
@@ -875,8 +875,9 @@ static int launch_tiled(uf3b_basis *basis, const uf3b_nlist *nl, TiledGeom tg, d
     const int warps_c = 4;
     const int nk2 = basis->h_pair_nk0;
     const size_t tab_c = ((8 * (size_t)((nk2 + 1) & ~1) + (size_t)PIECE_B * (nk2 - 7)) + 15) & ~size_t(15);
-    const size_t rows_c = (size_t)OWN_REC * tg.ps + 8 * (size_t)S::PLS * tg.ps + 16;     // + the warp's mbarrier
-    const size_t warp_c = ((size_t)PR_SLOTS * 32 * tg.col0 + std::max<size_t>(32 * PR_REC, rows_c) + 15) & ~size_t(15);
+    const size_t rows_c = (size_t)OWN_REC * tg.ps + 8 * (size_t)S::PLS * tg.ps;
+    // [slot accumulators][pair records of a pass | row tables of the atom][mbarrier of the bulk copies]
+    const size_t warp_c = (((size_t)PR_SLOTS * 32 * tg.col0 + std::max<size_t>(32 * PR_REC, rows_c) + 15) & ~size_t(15)) + 16;
     const size_t smem_c = tab_c + (size_t)warps_c * warp_c;
     if (smem_c > (size_t)smem_max) return 1;
     TiledGeom tgc = tg;
