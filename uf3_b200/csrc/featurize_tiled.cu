@@ -561,19 +561,24 @@ __device__ __forceinline__ void pair_pass(const PairTab &T, const Vec3 &pa, cons
     }
     asm volatile("st.shared.s32 [%0], %1;" :: "r"(rec_s + PR_REC * (unsigned)lane + 128u), "r"(col0) : "memory");
     __syncwarp();
-    for (int t = s; t < count; t += PR_SLOTS) {
-        const unsigned rec = rec_s + PR_REC * (unsigned)t;
-        const int c = lds32(rec + 128u);
-        if (c >= 0) {
-            const unsigned ad = my_slot + 32u * (unsigned)(c + q);
-            const double2 r01 = lds128(rec + 32u * q), r23 = lds128(rec + 32u * q + 16u);
-            double2 a01 = lds128(ad), a23 = lds128(ad + 16u);
-            a01.x += r01.x; a01.y += r01.y; a23.x += r23.x; a23.y += r23.y;
-            sts128(ad, a01);
-            sts128(ad + 16u, a23);
+    // consecutive pairs of a slot can touch the same column from different lanes (pair t: column c + q, pair
+    // t + 8: column c' + q'): the warp-wide barrier per round orders them (uniform trip count)
+    for (int t0 = 0; t0 < count; t0 += PR_SLOTS) {
+        const int t = t0 + s;
+        if (t < count) {
+            const unsigned rec = rec_s + PR_REC * (unsigned)t;
+            const int c = lds32(rec + 128u);
+            if (c >= 0) {
+                const unsigned ad = my_slot + 32u * (unsigned)(c + q);
+                const double2 r01 = lds128(rec + 32u * q), r23 = lds128(rec + 32u * q + 16u);
+                double2 a01 = lds128(ad), a23 = lds128(ad + 16u);
+                a01.x += r01.x; a01.y += r01.y; a23.x += r23.x; a23.y += r23.y;
+                sts128(ad, a01);
+                sts128(ad + 16u, a23);
+            }
         }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 // Block = W independent warps, warp = one atom at a time.  Per-block shared memory: the pair spline
