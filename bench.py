@@ -426,7 +426,8 @@ def run_ours(args, rank, world, local_rank):
     h_num_np = torch.from_numpy(frames[0][1]).pin_memory().numpy()
     # frames in flight in the host-buffer arms: 6 slots (depth sweep on the 8-GPU box: 3 -> 270 M, 4 -> 303 M,
     # 6 -> 345 M atom-steps/s; one GPU: 4 -> 33-42 M, 6 -> 40 M, 8 -> 37 M, run-to-run spread of the 25 ms window)
-    e2e_depth = int(os.environ.get("UF3B_E2E_DEPTH", "6"))
+    # (wide rows: four — six slots of 110 MB rows each measured 5.1 against 5.8 M with the 456-column basis)
+    e2e_depth = int(os.environ.get("UF3B_E2E_DEPTH", "6" if F <= 128 else "4"))
     # synthetic targets of the fit (outside the timed region): y = rows @ c_true, E = x_e @ c_true
     model = ls.WeightedLinearModel(basis, solver="cusolver", ridge_1b=1e-10, ridge_2b=1e-10, ridge_3b=1e-10)
     free = np.zeros(F)
