@@ -526,10 +526,16 @@ def run_ours(args, rank, world, local_rank):
     # taking half of an SM's resources (frames_in_flight=2): two frames' kernels share every SM, so
     # one frame's tail and the next frame's list build (which ends in a host wait) fill each other's
     # gaps.  (The block-per-atom kernel of the manuscript basis measured slower that way.)
-    n_slots = int(os.environ.get("UF3B_BENCH_SLOTS", "3" if args.basis == "demo" else ("1" if args.basis == "binary" else "2")))
+    n_slots = int(os.environ.get("UF3B_BENCH_SLOTS", "4" if args.basis == "demo" else ("1" if args.basis == "binary" else "2")))
     in_flight = int(os.environ.get("UF3B_BENCH_IN_FLIGHT", "2" if args.basis == "demo" else "1"))
-    slots = [(Engine(basis, device=local_rank, frames_in_flight=in_flight), torch.cuda.Stream(dev))
-             for _ in range(n_slots)]
+    # Deferred list builds: a build that reuses its slot's cell grid returns without a host wait, the feature
+    # kernels run behind it, and its status is checked when the slot's NEXT build is issued (an invalid build
+    # there raises: UF3B_RETRY) and, for the last frame of every slot, right after the timed region.  The host
+    # never waits inside the loop, so a descheduled rank does not stall its GPU (0.27 -> 0.25 ms per step at
+    # eight ranks).
+    deferred_slots = os.environ.get("UF3B_BENCH_DEFERRED", "1") == "1"
+    slots = [(Engine(basis, device=local_rank, frames_in_flight=in_flight, deferred_lists=deferred_slots),
+              torch.cuda.Stream(dev)) for _ in range(n_slots)]
     out_pool = [(torch.empty(F, dtype=torch.float64, device=dev),
                  torch.empty((3 * n_atoms, F), dtype=torch.float64, device=dev)) for _ in range(N_POOL)]
     pool_bytes = N_POOL * (3 * n_atoms * F * 8 + n_atoms * 24)
@@ -562,6 +568,8 @@ def run_ours(args, rank, world, local_rank):
             main.wait_stream(st)
         stop.record(main)
         barrier()
+        for e, _ in slots:          # the last frame of every slot: raises if its deferred build was invalid
+            e.neighbor_count(3)
         launches = eng.launch_count() - launches0
         return max_over_ranks(start.elapsed_time(stop)), launches
 
@@ -636,7 +644,9 @@ def run_ours(args, rank, world, local_rank):
                   "l2": "inputs larger than L2: every step uses its own frame and row buffer out of a pool of "
                         f"{len(out_pool)} ({pool_bytes / 1e6:.0f} MB > 126 MB L2); no explicit flush",
                   "streams": f"{n_slots} slots alternate frames (one engine + stream each), "
-                             f"each launch on 1/{in_flight} of the SM resources"},
+                             f"each launch on 1/{in_flight} of the SM resources; list builds "
+                             + ("verified when the slot's next build is issued (deferred status check)" if deferred_slots
+                                else "verified by a host wait per frame")},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "ms_per_step": e2e_ms / args.steps,
                 "how": f"uf3b_pipeline_submit_fit ({e2e_depth} slots): pinned host positions and force targets in "
                        "every step, rows folded into the normal equations on the device, the frame's energy row "

@@ -569,3 +569,47 @@ def test_pipeline_repeats_frames_whose_deferred_lists_were_invalid():
         assert moments[0] == sum(len(y) for y in ys)
         pipe.close()
     eng.close()
+
+
+def test_deferred_feature_rows_are_verified_at_the_next_build():
+    """Engine(deferred_lists=True) with device outputs (the resident arm of bench.py): the row kernels run
+    behind an unverified list build; the slot's NEXT build verifies it and raises (UF3B_RETRY) if the rows
+    that were produced from it are invalid, and neighbor_count does the same for the last frame."""
+    import torch
+    from uf3_b200 import _native
+    from uf3_b200.engine import Engine
+    basis = synthetic.w_basis("demo")
+    F = basis.n_feats
+    pos, numbers, cell, pbc = synthetic.bcc_w((4, 4, 5), seed=31)
+    images = geometry.image_table(cell, pbc, basis.r_cut)
+    n = len(pos)
+    safe = Engine(basis)
+    safe.build_neighbors(pos, numbers, images=images)
+    want_e, want_f = safe.featurize()
+    eng = Engine(basis, deferred_lists=True)
+    d_num = torch.from_numpy(numbers).cuda()
+    xe = torch.empty(F, dtype=torch.float64, device="cuda")
+    xf = torch.empty((3 * n, F), dtype=torch.float64, device="cuda")
+
+    def frame(p):
+        d_pos = torch.from_numpy(np.ascontiguousarray(p)).cuda()
+        eng.build_neighbors_device(d_pos.data_ptr(), d_num.data_ptr(), n, images)
+        eng.featurize_device(xe.data_ptr(), xf.data_ptr(), F)
+        torch.cuda.synchronize()
+
+    frame(pos)                                   # first build of the handle: checked
+    frame(pos + 0.01)                            # deferred, valid
+    assert np.allclose(xf.cpu().numpy(), want_f, rtol=1e-6, atol=1e-6 * np.abs(want_f).max())
+    frame(pos)                                   # verifies the previous build: fine
+    assert np.array_equal(xf.cpu().numpy(), want_f) and np.array_equal(xe.cpu().numpy(), want_e)
+    frame(pos + 4.0)                             # the atoms leave the cached grid: rows of this frame are invalid
+    with pytest.raises(_native.UF3BError) as err:
+        frame(pos)                               # ... and the next build says so
+    assert err.value.code == _native.RETRY
+    frame(pos)                                   # the grid was dropped: a checked build
+    assert np.array_equal(xf.cpu().numpy(), want_f)
+    frame(pos + 4.0)
+    with pytest.raises(_native.UF3BError):
+        eng.neighbor_count(3)                    # the last frame of a stream is verified the same way
+    eng.close()
+    safe.close()

@@ -206,6 +206,7 @@ struct uf3b_nlist {
     bool pending = false;
     int max3_hint = 0;             // longest 3-body row of the last verified build
     bool hint_used = false;        // a consumer sized itself by max3_hint while the build was pending
+    bool consumed_pending = false; // feature rows were produced from a build that is still pending
     bool ticket_zeroed = false;    // k_prepare's block counter has been cleared once
     cudaEvent_t status_ev = nullptr;
     cudaStream_t pending_stream = nullptr;

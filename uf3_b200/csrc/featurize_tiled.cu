@@ -1004,7 +1004,10 @@ int featurize_tiled(uf3b_basis *basis, const uf3b_nlist *nl, double *x_energy, d
         for (int c = 0; c < n_cols3; ++c)
             if (seen[c] != 1) return 1;
     }
-    if (deferred) const_cast<uf3b_nlist *>(nl)->hint_used = true;
+    if (deferred) {
+        const_cast<uf3b_nlist *>(nl)->hint_used = true;
+        const_cast<uf3b_nlist *>(nl)->consumed_pending = true;
+    }
     if (tg.la <= 2 && tg.na <= 7) return launch_tiled<2, 7>(basis, nl, tg, x_energy, x_forces, ld, stream, max3_in);
     if (tg.la <= 3 && tg.na <= 9) return launch_tiled<3, 9>(basis, nl, tg, x_energy, x_forces, ld, stream, max3_in);
     return launch_tiled<4, 10>(basis, nl, tg, x_energy, x_forces, ld, stream, max3_in);

@@ -665,9 +665,18 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
         ~Guard() { if (armed) delete p; }
     } guard{nl, created};
 
-    if (nl->pending) {          // an unverified deferred build is superseded by this one
+    if (nl->pending) {          // an unverified deferred build is superseded by this one ...
+        const bool consumed = nl->consumed_pending;
+        nl->consumed_pending = false;
         const int rc = nlist_resolve(nl);
         if (rc < 0 && rc != UF3B_ERR_CAPACITY) { guard.armed = false; return rc; }
+        // ... unless feature rows were produced from it (uf3b_featurize with device outputs does not wait
+        // for the build): an invalid build then means invalid rows, and the caller has to hear about it
+        if (rc == UF3B_RETRY && consumed) {
+            guard.armed = false;
+            return fail(UF3B_RETRY, "the previous frame's deferred list build was invalid: its feature rows must "
+                                    "not be used; repeat that frame, then this build");
+        }
     }
     const int n = (int)n_atoms;
     nl->n = n_atoms;
@@ -861,6 +870,7 @@ int uf3b_neighbors_build_range(uf3b_basis *basis, int64_t n_atoms, const double 
             UF3B_CUDA(cudaEventRecord(nl->status_ev, stream));
             nl->pending = true;
             nl->hint_used = false;
+            nl->consumed_pending = false;
             nl->pending_stream = stream;
             nl->grid_valid = true;
             guard.armed = false;
