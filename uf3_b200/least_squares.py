@@ -250,7 +250,23 @@ class WeightedLinearModel:
 
     @property
     def mask(self):
-        return get_freezing_mask(self.n_feats, self.col_idx)
+        # cached per (n_feats, frozen columns): the fit at the end of a stream of frames reads it several
+        # times and np.setdiff1d costs 0.15 ms a call
+        key = (int(self.n_feats), tuple(int(c) for c in np.atleast_1d(self.col_idx)))
+        cached = getattr(self, "_mask_cache", None)
+        if cached is None or cached[0] != key:
+            cached = (key, get_freezing_mask(self.n_feats, self.col_idx))
+            self._mask_cache = cached
+        return cached[1]
+
+    def _regularizer_gram(self, mask):
+        """R^T R on the unfrozen columns, cached while the regularizer object and the mask stay the same."""
+        cached = getattr(self, "_reg_cache", None)
+        if cached is None or cached[0] is not self.regularizer or cached[1] is not mask:
+            reg = freeze_regularizer(self.regularizer, mask)
+            cached = (self.regularizer, mask, np.dot(reg.T, reg))
+            self._reg_cache = cached
+        return cached[2]
 
     def __repr__(self):
         return "\n".join(["WeightedLinearModel:", f"    Fit: {self.coefficients is not None}",
@@ -262,9 +278,8 @@ class WeightedLinearModel:
         coverage = revert_frozen_coefficients(np.sum(gram, axis=0) != 0, self.n_feats, self.mask,
                                               self.frozen_c, self.col_idx)
         self.data_coverage = np.logical_or(self.data_coverage, coverage)
-        reg = freeze_regularizer(self.regularizer, self.mask)
         solve = device_solve if getattr(self, "solver", "host") == "cusolver" else lu_factorization
-        solution = solve(gram + np.dot(reg.T, reg), ordinate)
+        solution = solve(gram + self._regularizer_gram(self.mask), ordinate)
         self.coefficients = revert_frozen_coefficients(solution, self.n_feats, self.mask,
                                                        self.frozen_c, self.col_idx)
 
