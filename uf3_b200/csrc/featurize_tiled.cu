@@ -11,7 +11,7 @@
 //   energy          e   += sum_{j in row(a)}   1/2 B_l(r_aj)  (x) P_(a,j)   (both orders of a pair fold onto one column)
 // The plane P_(i,j) is needed twice: by atom j in its neighbour role and by atom i in its centre
 // role.  It is computed ONCE — by j, whose neighbour role needs the legs (j, k) anyway — and left in
-// an L2-resident table (216 B per list entry); the centre role of every atom is then 14 plane reads
+// an L2-resident table (224 B per list entry); the centre role of every atom is then 14 plane reads
 // and outer products instead of a second round of leg evaluations and contractions.
 //
 //   k_centre_legs   one thread per 3-body list entry: the leg (centre, entry) dense by basis index,
@@ -25,10 +25,14 @@
 //                   the previous kernel read both factors of EVERY product from shared memory and
 //                   sat at 88 % of the L1/LSU pipe with the FP64 pipe at 10 %), stores P to the
 //                   plane table and adds the outer products to the folded [c][{l, m}] force tile of
-//                   its n, which lives in registers for the whole atom and is stored straight into
-//                   the rows.
-//   k_rows_ctr      warp = atom, centre role from the plane table + pair rows + composition columns;
-//                   completes the rows k_rows_nbr started and produces the energy-row partials.
+//                   its n, which lives in registers for the whole atom and is left, 3 NS doubles per
+//                   lane, in an L2-resident tile buffer.
+//   k_rows_ctr      warp = atom.  Three TMA bulk copies (cp.async.bulk + per-warp mbarrier) stage the
+//                   atom's row tables — leg values, derivatives, planes — while the lanes gather the
+//                   pair partners; centre role from the planes, pair rows + composition columns; the
+//                   force tile starts from the one k_rows_nbr left, the rows are written ONCE
+//                   (streaming stores), the consumed tile and plane lines are dropped from the L2, and
+//                   the energy-row partials are produced.
 #include <algorithm>
 #include <cstdlib>
 
