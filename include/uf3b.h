@@ -108,7 +108,11 @@ int uf3b_basis_set_frames_in_flight(uf3b_basis *basis, int32_t k);
 /* MD loops: a list build on this basis that can reuse the cell grid of the previous one (same frame
  * size, atoms still inside the padded box) returns WITHOUT waiting for the device — its totals /
  * overflow flag / box check are verified by the next call that uses the list, after that call has
- * queued its own kernels.  uf3b_energy_forces then returns UF3B_RETRY (1) if the build was invalid. */
+ * queued its own kernels.  uf3b_energy_forces then returns UF3B_RETRY (1) if the build was invalid.
+ * uf3b_featurize with DEVICE outputs does not wait either (a device-side flag makes its kernels leave at
+ * once behind an invalid build); the rows it produced are verified by the handle's NEXT
+ * uf3b_neighbors_build*, which returns UF3B_RETRY when they must not be used (repeat that frame, then
+ * the build), and by uf3b_neighbors_count / uf3b_neighbors_export for the last frame of a stream. */
 int uf3b_basis_set_deferred_lists(uf3b_basis *basis, int enabled);
 void uf3b_basis_destroy(uf3b_basis *basis);
 
