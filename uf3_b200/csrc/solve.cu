@@ -39,21 +39,39 @@ extern "C" int uf3b_solve(const double *a, const double *b, int32_t n, int32_t n
     cudaGetDevice(&dev);
     cusolverDnHandle_t local = nullptr;
     cusolverDnHandle_t &handle = (dev >= 0 && dev < 16) ? t_handle[dev] : local;
+    // device scratch of the solve, kept per host thread and device like the handle (grow-only; five
+    // cudaMalloc / cudaFree pairs cost more than the factorisation of a 70 x 70 system)
+    struct Scratch { void *p = nullptr; size_t cap = 0; };
+    static thread_local Scratch t_scratch[16][5];
+    Scratch local_scratch[5];
+    Scratch *scratch = (dev >= 0 && dev < 16) ? t_scratch[dev] : local_scratch;
+    auto reserve = [&](int k, size_t bytes, void **out) -> cudaError_t {
+        if (bytes > scratch[k].cap) {
+            if (scratch[k].p) cudaFree(scratch[k].p);
+            scratch[k].p = nullptr;
+            scratch[k].cap = 0;
+            cudaError_t e = cudaMalloc(&scratch[k].p, bytes + bytes / 4);
+            if (e != cudaSuccess) return e;
+            scratch[k].cap = bytes + bytes / 4;
+        }
+        *out = scratch[k].p;
+        return cudaSuccess;
+    };
     double *d_a = nullptr, *d_b = nullptr, *d_work = nullptr;
     int *d_piv = nullptr, *d_info = nullptr;
     int lwork = 0, h_info = 0;
     const size_t a_bytes = sizeof(double) * (size_t)n * n, b_bytes = sizeof(double) * (size_t)n * n_rhs;
-    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_a, a_bytes));
-    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_b, b_bytes));
-    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_piv, sizeof(int) * n));
-    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_info, sizeof(int)));
+    UF3B_CUDA_GOTO(reserve(0, a_bytes, (void **)&d_a));
+    UF3B_CUDA_GOTO(reserve(1, b_bytes, (void **)&d_b));
+    UF3B_CUDA_GOTO(reserve(2, sizeof(int) * n, (void **)&d_piv));
+    UF3B_CUDA_GOTO(reserve(3, sizeof(int), (void **)&d_info));
     // `a` is row-major: LAPACK sees its transpose, so the solve below uses op = T
     UF3B_CUDA_GOTO(cudaMemcpyAsync(d_a, a, a_bytes, cudaMemcpyDefault, stream));
     UF3B_CUDA_GOTO(cudaMemcpyAsync(d_b, b, b_bytes, cudaMemcpyDefault, stream));   // [n_rhs][n]: column-major n x n_rhs
     if (!handle) UF3B_SOLVER(cusolverDnCreate(&handle));
     UF3B_SOLVER(cusolverDnSetStream(handle, stream));
     UF3B_SOLVER(cusolverDnDgetrf_bufferSize(handle, n, n, d_a, n, &lwork));
-    UF3B_CUDA_GOTO(cudaMalloc((void **)&d_work, sizeof(double) * (size_t)std::max(lwork, 1)));
+    UF3B_CUDA_GOTO(reserve(4, sizeof(double) * (size_t)std::max(lwork, 1), (void **)&d_work));
     UF3B_SOLVER(cusolverDnDgetrf(handle, n, n, d_a, n, d_work, d_piv, d_info));
     // the factorisation's status is read before getrs overwrites devInfo with its own: a zero pivot
     // (all-zero regulariser with uncovered columns) must not come back as inf / NaN coefficients
@@ -70,10 +88,7 @@ extern "C" int uf3b_solve(const double *a, const double *b, int32_t n, int32_t n
     if (h_info != 0) rc = fail(UF3B_ERR_INVALID, "getrs rejected its arguments (info %d)", h_info);
 done:
     if (local) cusolverDnDestroy(local);
-    cudaFree(d_a);
-    cudaFree(d_b);
-    cudaFree(d_work);
-    cudaFree(d_piv);
-    cudaFree(d_info);
+    if (scratch == local_scratch)
+        for (int k = 0; k < 5; ++k) cudaFree(local_scratch[k].p);
     return rc;
 }
