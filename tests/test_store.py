@@ -105,3 +105,17 @@ def test_batched_store_resumes_and_fit_from_file_matches_fit(tmp_path):
         from_file.fit_from_file(str(tmp_path / "missing.h5"), subset)
     with pytest.raises(ValueError):
         from_file.fit_from_file(path, ["not there"], gram="host")
+
+
+def test_training_tuples_weights():
+    """process.dataframe_to_training_tuples (process.py:574-616): weights per sample class."""
+    case = gu.Case("syn_w54_demo")
+    df = _feature_frame(case, ["a", "b", "c"])
+    x, y, w = process.dataframe_to_training_tuples(df, kappa=0.25)
+    is_e = np.asarray(df.index.get_level_values(-1) == "energy")
+    assert x.shape == (len(df), df.shape[1] - 1) and np.array_equal(y, df.to_numpy()[:, 0])
+    assert np.isclose(w[is_e].sum(), 0.25 / np.std(y[is_e])) and np.isclose(w[~is_e].sum(), 0.75 / np.std(y[~is_e]))
+    with pytest.raises(ValueError):
+        process.dataframe_to_training_tuples(df, kappa=1.5)
+    with pytest.raises(ValueError):
+        process.dataframe_to_training_tuples(df.iloc[:1])

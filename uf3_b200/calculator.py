@@ -180,6 +180,15 @@ class UFCalculator(_Base):
         volume = abs(np.linalg.det(np.asarray(cell, dtype=np.float64)))
         return (w / volume).flat[[0, 4, 8, 5, 2, 1]]
 
+    knot_subintervals = property(lambda self: self.bspline_config.knot_subintervals)
+
+    def calculation_required(self, atoms, quantities):
+        """ASE's legacy protocol (calculator.py:438-447): everything but energy / forces / stress is not
+        available; otherwise a calculation is needed when the atoms changed."""
+        if any(q in quantities for q in ("magmom", "charges")):
+            return True
+        return self.atoms is None or self.atoms != atoms or any(q not in self.results for q in quantities)
+
     # ------------------------------------------------------------------ relaxation
     def relax_fmax(self, geom, fmax=0.05, relax_cell=True, verbose=False, timeout=60.0, max_steps=2000,
                    **kwargs):

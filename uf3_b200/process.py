@@ -240,6 +240,11 @@ class BasisFeaturizer:
         position = np.argsort(np.array([rank[name] for name in names]), kind="stable")
         return df_features.iloc[position]
 
+    def get_training_tuples(self, df_features, kappa, data_coordinator):
+        """Deprecated in the reference as well (process.py:508-535)."""
+        warnings.warn("get_training_tuples() is deprecated.", DeprecationWarning)
+        return dataframe_to_training_tuples(df_features, kappa=kappa, energy_key=data_coordinator.energy_key)
+
     def batched_to_hdf(self, filename, df_data, client=None, n_jobs=16, batch_size=50, progress="bar",
                        table_template="features_{}", **kwargs):
         """Stream the feature rows of `df_data` into a chunked store, `batch_size` configurations per
@@ -270,6 +275,35 @@ class BasisFeaturizer:
 def _evaluate_batch(featurizer, batch, kwargs):
     """Module-level so that a process pool can pickle the call (util/parallel.py:182)."""
     return featurizer.evaluate(batch, **kwargs)
+
+
+def save_feature_db(dataframe, filename, table_name="features"):
+    """Reference name (process.py:538-548); the container is chosen by `uf3_b200.store`."""
+    from uf3_b200 import store
+    store.save_feature_db(dataframe, filename, table_name=table_name)
+
+
+def load_feature_db(filename, table_name="features"):
+    """Reference name (process.py:550-562)."""
+    from uf3_b200 import store
+    return store.load_feature_db(filename, table_name=table_name)
+
+
+def dataframe_to_training_tuples(df_features, kappa=0.5, energy_key="energy"):
+    """(x, y, w) of a feature DataFrame for a weighted fit (process.py:574-616): the first column is the
+    target; energy rows weigh kappa / (n_e std_e) each, force rows (1 - kappa) / (n_f std_f)."""
+    if kappa < 0 or kappa > 1:
+        raise ValueError("Invalid domain for kappa weighting parameter.")
+    if len(df_features) <= 1:
+        raise ValueError(f"Not enough samples ({len(df_features)} provided)")
+    is_energy = np.asarray(df_features.index.get_level_values(-1) == energy_key)
+    data = df_features.to_numpy()
+    y, x = data[:, 0], data[:, 1:]
+    n_e, n_f = int(is_energy.sum()), int((~is_energy).sum())
+    w = np.zeros(len(y))
+    w[is_energy] = kappa / np.std(y[is_energy]) / n_e
+    w[~is_energy] = (1 - kappa) / np.std(y[~is_energy]) / n_f
+    return x, y, w
 
 
 def flatten_by_interactions(vector_map, pair_tuples):
