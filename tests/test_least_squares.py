@@ -2,6 +2,7 @@
 Gram statistics that multi-GPU fits all-reduce.  The reference behaviour restated here is
 regression/least_squares.py:248-353, :666-771, :817-890, :1147-1168."""
 import numpy as np
+import pytest
 
 import golden_util as gu
 from uf3_b200 import least_squares as ls
@@ -89,3 +90,42 @@ def test_fit_reproduces_the_reference_fit_on_its_own_rows():
     assert np.isfinite(model.coefficients).all() and np.all(model.coefficients[basis.col_idx] == 0)
     # the reference model (fitted on energies AND forces) predicts the same energies to the noise level
     assert np.abs(model.predict(fix["x_e"]) - fix["predict_e"]).max() < 5e-3
+
+
+def test_variance_recorder_and_gram_from_df_reproduce_fit():
+    """The reference's streaming pieces (least_squares.py:19-68, :425-483): Gram blocks per chunk + running
+    target statistics give the coefficients of the one-shot fit."""
+    import pandas as pd
+    case, n_atoms, x_e, y_e, x_f, y_f = _rows()
+    basis = case.basis()
+    rec = ls.VarianceRecorder()
+    for part in np.array_split(y_f, 5):
+        rec.update(part)
+    assert rec.n == len(y_f) and np.isclose(rec.mean, y_f.mean()) and np.isclose(rec.std, y_f.std())
+    # two configurations as a feature frame (target first, then the row)
+    rows, index = [], []
+    half = len(x_f) // 2
+    for k, name in enumerate(("a", "b")):
+        rows.append(np.insert(x_e[k], 0, y_e[k])); index.append((name, "energy"))
+        for j, (xr, yr) in enumerate(zip(x_f[k * half:(k + 1) * half], y_f[k * half:(k + 1) * half])):
+            rows.append(np.insert(xr, 0, yr)); index.append((name, f"fx_{j}"))
+    df = pd.DataFrame(np.array(rows), index=pd.MultiIndex.from_tuples(index))
+    params = dict(ridge_1b=1e-3, ridge_2b=1e-3, ridge_3b=1e-3, curvature_2b=1e-3)
+    model = ls.WeightedLinearModel(basis, **params)
+    gram_e, gram_f, ord_e, ord_f = model.initialize_gram_ordinate()
+    e_var, f_var = ls.VarianceRecorder(), ls.VarianceRecorder()
+    for name in ("a", "b"):
+        g_e, g_f, o_e, o_f = model.gram_from_df(df, [name], e_variance=e_var, f_variance=f_var)
+        gram_e += g_e; gram_f += g_f; ord_e += o_e; ord_f += o_f
+    w_e, w_f = ls.calc_E_F_weights(e_var.n, f_var.n, e_var.std, f_var.std)
+    model.fit_with_gram(*model.combine_weighted_gram(gram_e, gram_f, ord_e, ord_f, w_e, w_f, 0.4))
+    direct = ls.WeightedLinearModel(basis, **params)
+    t_e, u_e, t_f, u_f = ls.dataframe_to_tuples(df, n_elements=1)
+    direct.fit(t_e, u_e, t_f, u_f, weight=0.4)
+    assert np.allclose(model.coefficients, direct.coefficients, rtol=1e-6, atol=1e-9)
+    y1, p1, y2, p2 = ls.subset_prediction(df, model, subset_keys=["b"], n_elements=1)
+    assert len(y1) == 1 and len(y2) == half and np.allclose(p2, t_f[half:] @ model.coefficients)
+    sol = ls.weighted_least_squares(x_f[:, 1:19], y_f, weights=np.ones(len(y_f)), regularizer=1e-3 * np.eye(18))
+    assert sol.shape == (18,) and np.all(np.isfinite(sol))
+    with pytest.raises(ValueError):
+        ls.validate_regularizer(np.eye(4), 5)

@@ -107,6 +107,95 @@ def device_solve(a, b, stream=None):
     return x.T.copy() if b.ndim == 2 else x
 
 
+class VarianceRecorder:
+    """Running mean / standard deviation / count over batches (least_squares.py:19-68).  Batches are merged
+    with the pairwise update of Chan et al., so the result does not depend on how the samples were cut."""
+
+    def __init__(self, mean=0, std=0, n=0):
+        self.mean, self.std, self.n = mean, std, int(n)
+
+    def update(self, batch):
+        batch = np.asarray(batch, dtype=np.float64)
+        k = len(batch)
+        if k == 0:
+            return self.mean, self.std, self.n
+        b_mean, b_var = np.mean(batch, axis=0), np.var(batch, axis=0)
+        if self.n == 0:
+            self.mean, self.std, self.n = b_mean, np.sqrt(b_var), k
+            return self.mean, self.std, self.n
+        m, total = float(self.n), float(self.n + k)
+        var = m / total * self.std ** 2 + k / total * b_var + m * k / total ** 2 * (self.mean - b_mean) ** 2
+        self.mean = (m * self.mean + k * b_mean) / total
+        self.std = np.sqrt(var)
+        self.n += k
+        return self.mean, self.std, self.n
+
+    def update_with_components(self, df, keys=None):
+        """Force components of a data frame (columns fx, fy, fz holding scalars or per-atom arrays)."""
+        values = []
+        for row in df[list(keys or ("fx", "fy", "fz"))].itertuples(index=False):
+            if any(component is np.nan for component in row):
+                continue
+            for component in row:
+                values.extend(np.ravel(component))
+        return self.update(values)
+
+
+def apply_weights(x, y, weights=None):
+    """Rows and targets scaled by per-sample weights (least_squares.py:892-913)."""
+    if weights is None:
+        return np.asarray(x), np.asarray(y)
+    weights = np.asarray(weights, dtype=np.float64)
+    if weights.shape != np.shape(y) or np.any(weights < 0):
+        raise ValueError("weights must be non-negative, one per sample")
+    return np.asarray(x) * weights[:, None], np.asarray(y) * weights
+
+
+def validate_regularizer(regularizer, n_feats):
+    n_row, n_col = np.shape(regularizer)
+    if n_col != n_feats:
+        raise ValueError(f"Expected regularizer shape: N x {n_feats}. Provided: {n_row} x {n_col}")
+
+
+def linear_least_squares(x, y):
+    """Normal-equation solve of x c = y (least_squares.py:774-787); a Tikhonov matrix is appended by the caller."""
+    return lu_factorization(*moore_penrose_components(x, y))
+
+
+def weighted_least_squares(x, y, weights=None, regularizer=None):
+    """Weighted rows with an optional regularizer stacked below them (least_squares.py:790-814)."""
+    x_fit, y_fit = apply_weights(x, y, weights)
+    if regularizer is not None:
+        x_fit = np.concatenate([x_fit, regularizer])
+        y_fit = np.concatenate([y_fit, np.zeros(len(regularizer))])
+    return linear_least_squares(x_fit, y_fit)
+
+
+def subset_prediction(df, model, subset_keys=None, **kwargs):
+    """(y_e, p_e, y_f, p_f) of the configurations `subset_keys` of a feature frame (least_squares.py:933-962)."""
+    if subset_keys is not None:
+        found = df.index.unique(level=0).intersection(subset_keys)
+        if len(found) == 0:
+            return [], [], [], []
+        df = df.loc[found]
+    x_e, y_e, x_f, y_f = dataframe_to_tuples(df, **kwargs)
+    return y_e, model.predict(x_e), y_f, model.predict(x_f)
+
+
+def batched_prediction(model, filename, table_names=None, subset_keys=None, drop_columns=None, **kwargs):
+    """The same over the tables of a feature store (least_squares.py:965-1010)."""
+    from uf3_b200 import store
+    if table_names is None:
+        _, _, table_names, _ = store.analyze_hdf_tables(filename)
+    parts = [[], [], [], []]
+    for df in store.dataframe_batch_loader(filename, table_names):
+        if drop_columns is not None:
+            df = df.drop(columns=drop_columns)
+        for part, values in zip(parts, subset_prediction(df, model, subset_keys=subset_keys, **kwargs)):
+            part.append(np.asarray(values))
+    return tuple(np.concatenate(part) if part else np.zeros(0) for part in parts)
+
+
 def calc_E_F_weights(n_e, n_f, std_e, std_f):
     """Weights of the energy / force blocks (least_squares.py:1147-1168)."""
     if std_e == 0:
@@ -317,6 +406,26 @@ class WeightedLinearModel:
             w_e, w_f = calc_E_F_weights(stats["n_e"], stats["n_f"], stats["std_e"], stats["std_f"])
             gram, ordinate = self.combine_weighted_gram(gram, gram_f, ordinate, ord_f, w_e, w_f, weight)
         self.fit_with_gram(gram, ordinate)
+
+    def initialize_gram_ordinate(self):
+        """Zero Gram blocks and ordinates over the unfrozen columns (least_squares.py:425-433)."""
+        p = self.n_feats - len(self.col_idx)
+        return np.zeros((p, p)), np.zeros((p, p)), np.zeros(p), np.zeros(p)
+
+    def gram_from_df(self, df, keys, e_variance=None, f_variance=None, sample_weights=None, energy_key="energy",
+                     batch_size=2500):
+        """(gram_e, gram_f, ord_e, ord_f) of the configurations `keys` of a feature frame, frozen columns
+        eliminated; the variance recorders, if given, see the targets (least_squares.py:435-483)."""
+        x_e, y_e, x_f, y_f = dataframe_to_tuples(df.loc[keys], n_elements=len(self.bspline_config.element_list),
+                                                 energy_key=energy_key, sample_weights=sample_weights)
+        x_e, y_e = freeze_columns(x_e, y_e, self.mask, self.frozen_c, self.col_idx)
+        x_f, y_f = freeze_columns(x_f, y_f, self.mask, self.frozen_c, self.col_idx)
+        if e_variance is not None and f_variance is not None:
+            e_variance.update(y_e)
+            f_variance.update(y_f)
+        gram_e, ord_e = batched_moore_penrose(x_e, y_e, batch_size=batch_size)
+        gram_f, ord_f = batched_moore_penrose(x_f, y_f, batch_size=batch_size)
+        return gram_e, gram_f, ord_e, ord_f
 
     def fit_from_file(self, filename, subset, weight=0.5, batch_size=2500, sample_weights=None,
                       energy_key="energy", progress="bar", drop_columns=None, gram="auto"):
