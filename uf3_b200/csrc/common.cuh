@@ -157,6 +157,8 @@ int nlist_resolve(uf3b_nlist *nl);
 // uf3b_gram_accumulate whose kernels leave at once when *invalid != 0 (device flag of a deferred list build)
 int gram_accumulate_guarded(uf3b_gram *gram, const double *x, const double *y, int64_t rows, int64_t ld,
                             int is_force, void *stream, const int *invalid);
+int gram_clear(uf3b_gram *gram, cudaStream_t stream);                           // both accumulators = 0
+int gram_add(uf3b_gram *dst, const uf3b_gram *src, cudaStream_t stream);        // dst += src
 }  // namespace uf3b
 
 // ------------------------------------------------------------------ opaque handles

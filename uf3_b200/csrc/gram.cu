@@ -206,6 +206,11 @@ k_gram_narrow(const double *__restrict__ x, long long ld, const double *__restri
     }
 }
 
+__global__ void __launch_bounds__(256) k_add_into(double *__restrict__ dst, const double *__restrict__ src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
 constexpr int OROWS = 256;    // rows per block of k_ordinate
 
 // b += X^T y: block = 32 columns x OROWS rows; warp w takes rows w, w + 8, ... (coalesced
@@ -267,6 +272,29 @@ int uf3b_gram_accumulate(uf3b_gram *gm, const double *x, const double *y, int64_
 }
 
 }  // extern "C"
+
+// dst (+)= src for both accumulators (energy and force rows) on `stream`; clear = true: dst = src's sum
+// starts from zero.  Used by the frame pipeline to add its slots' normal equations on the device, so
+// that an export is ONE synchronisation and two copies instead of that per slot.
+int uf3b::gram_clear(uf3b_gram *gm, cudaStream_t stream) {
+    if (!gm) return fail(UF3B_ERR_INVALID, "null handle");
+    const size_t n = (size_t)gm->n_cols;
+    for (int k = 0; k < 2; ++k) {
+        UF3B_CUDA(cudaMemsetAsync(gm->g[k], 0, sizeof(double) * n * n, stream));
+        UF3B_CUDA(cudaMemsetAsync(gm->b[k], 0, sizeof(double) * n, stream));
+    }
+    return UF3B_OK;
+}
+
+int uf3b::gram_add(uf3b_gram *dst, const uf3b_gram *src, cudaStream_t stream) {
+    if (!dst || !src || dst->n_cols != src->n_cols) return fail(UF3B_ERR_INVALID, "accumulators of different width");
+    const size_t n = (size_t)dst->n_cols;
+    for (int k = 0; k < 2; ++k) {
+        UF3B_LAUNCH(k_add_into, (unsigned)((n * n + 255) / 256), 256, 0, stream, dst->g[k], src->g[k], n * n);
+        UF3B_LAUNCH(k_add_into, (unsigned)((n + 255) / 256), 256, 0, stream, dst->b[k], src->b[k], n);
+    }
+    return UF3B_OK;
+}
 
 int uf3b::gram_accumulate_guarded(uf3b_gram *gm, const double *x, const double *y, int64_t rows, int64_t ld,
                                   int is_force, void *stream_, const int *invalid) {

@@ -81,6 +81,7 @@ struct uf3b_pipeline {
     // not lost (reported by the next submit / wait / export)
     int sticky_rc = UF3B_OK;
     std::string sticky_err;
+    uf3b_gram *total = nullptr;     // sum of the slots' normal equations (uf3b_pipeline_export_gram)
 };
 
 namespace {
@@ -238,6 +239,7 @@ void uf3b_pipeline_destroy(uf3b_pipeline *p) {
         if (s->stream) cudaStreamDestroy(s->stream);
         delete s;
     }
+    if (p->total) uf3b_gram_destroy(p->total);
     delete p;
 }
 
@@ -331,22 +333,30 @@ int uf3b_pipeline_export_gram(uf3b_pipeline *p, double *gram_out, double *ord_ou
     if (gram_out) std::fill(gram_out, gram_out + F * F, 0.0);
     if (ord_out) std::fill(ord_out, ord_out + F, 0.0);
     if (moments_out) moments_out[0] = moments_out[1] = moments_out[2] = 0.0;
-    std::vector<double> g(gram_out ? F * F : 0), b(ord_out ? F : 0);
     std::unique_lock<std::mutex> lk(p->m);
     p->cv.wait(lk, [&] {                                                            // every frame is out
         for (const PipeSlot *s : p->slots)
             if (s->state == QUEUED || s->state == INFLIGHT) return false;
         return true;
     });
+    // every frame is complete (its slot's event was waited for): the slots' accumulators are summed on the
+    // device and come back with ONE synchronisation and two copies
+    DeviceGuard on_device(p->device);
+    bool any = false;
     for (PipeSlot *s : p->slots) {
         if (s->rc != UF3B_OK) return fail(s->rc, "a frame failed: %s", s->err.c_str());
         if (moments_out)
             for (int k = 0; k < 3; ++k) moments_out[k] += s->moments[k];
         if (!s->gram) continue;
-        if (int rc = uf3b_gram_export(s->gram, 1, gram_out ? g.data() : nullptr, ord_out ? b.data() : nullptr)) return rc;
-        if (gram_out) for (size_t k = 0; k < F * F; ++k) gram_out[k] += g[k];
-        if (ord_out) for (size_t k = 0; k < F; ++k) ord_out[k] += b[k];
+        if (!p->total)
+            if (int rc = uf3b_gram_create((int32_t)F, &p->total)) return rc;
+        if (!any)
+            if (int rc = gram_clear(p->total, nullptr)) return rc;
+        any = true;
+        if (int rc = gram_add(p->total, s->gram, nullptr)) return rc;
     }
+    if (any)
+        if (int rc = uf3b_gram_export(p->total, 1, gram_out, ord_out)) return rc;
     if (p->sticky_rc != UF3B_OK) return fail(p->sticky_rc, "an earlier frame failed: %s", p->sticky_err.c_str());
     return UF3B_OK;
 }
