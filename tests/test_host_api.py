@@ -136,3 +136,17 @@ def test_trim_validation_and_unknown_strategy():
         bspline.BSplineBasis(chem, leading_trim={"2": 0})
     with pytest.raises(ValueError):
         bspline.BSplineBasis(chem, knot_strategy="cubic")
+
+
+def test_fit_spline_1d_reproduces_the_reference_fit():
+    """bspline.fit_spline_1d (bspline.py:898-950): the Lennard-Jones curve the reference's calculator test
+    fits (tests/test_calculator.py:20-33); its coefficients are in the fixture the reference wrote."""
+    import golden_util as gu
+    from uf3_b200 import bspline
+    case = gu.Case("calc_w_dimer_free")
+    knots = np.array(case.basis().knots_map[("W", "W")])
+    x = np.linspace(2.0, 6.0, 1000)
+    y = 4 * 0.87 * ((2.5 / x) ** 12 - (2.5 / x) ** 6)
+    coefficients = bspline.fit_spline_1d(x, y, knots)
+    want = np.array(case["coefficients"])[1:]
+    assert np.abs(coefficients - want).max() <= 1e-10 * np.abs(want).max()

@@ -569,3 +569,38 @@ def find_spline_indices(points, knot_sequence):
     A point exactly on a knot belongs to the interval on its left
     (`bspline.py:966`: `searchsorted(..., side='left') - 4`)."""
     return np.searchsorted(knot_sequence, points, side="left") - 4
+
+
+def fit_spline_1d(x, y, knot_sequence):
+    """Cubic B-spline coefficients of a sampled 1-D function in the least-squares sense — for comparing
+    fitted pair potentials with a known curve, or for building a model from one
+    (reference: representation/bspline.py:898-950, which hands the samples to FITPACK's
+    LSQUnivariateSpline; here the same normal equations are solved from the B-spline design matrix).
+    Samples outside the open knot range are dropped.  The reference then pads the samples so that no knot
+    interval is empty, with a rule that is kept as it is because it shapes the result: for every knot
+    interval whose LEFT edge lies below the smallest sample it adds (midpoint, y of the smallest sample) —
+    which always includes the first interval — and for every interval whose left edge lies above the
+    largest sample (midpoint, y of the largest sample)."""
+    from scipy.interpolate import BSpline
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    t = np.asarray(knot_sequence, dtype=np.float64)
+    inside = (x > t[0]) & (x < t[-1])
+    x, y = x[inside], y[inside]
+    if len(x) == 0:
+        raise ValueError("no sample inside the knot range")
+    lo, hi = int(np.argmin(x)), int(np.argmax(x))
+    x_min, y_min, x_max, y_max = x[lo], y[lo], x[hi], y[hi]
+    edges = np.unique(t)
+    pad_x, pad_y = [], []
+    for left, right in zip(edges[:-1], edges[1:]):
+        if x_min > left:
+            pad_x.append(0.5 * (left + right))
+            pad_y.append(y_min)
+        elif x_max < left:
+            pad_x.append(0.5 * (left + right))
+            pad_y.append(y_max)
+    x, y = np.concatenate([x, pad_x]), np.concatenate([y, pad_y])
+    order = np.argsort(x, kind="stable")
+    design = BSpline.design_matrix(x[order], t, 3).toarray()
+    coefficients, *_ = np.linalg.lstsq(design, y[order], rcond=None)
+    return coefficients
